@@ -1,0 +1,112 @@
+"""ctypes access to the oracle (oracle/liboracle{32,64}.so) and, when present, the compiled
+reference CPU classes (oracle/_ref/libnnpops_ref.so).  TEST INFRASTRUCTURE ONLY: imported by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs, never by nnpops_b200."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ODIR = os.path.join(ROOT, "oracle")
+
+_f = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_d = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_i = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+
+
+def build(force=False):
+    """Compile the C restatements (and oracle/_ref when /root/reference exists)."""
+    need = force or not all(os.path.exists(os.path.join(ODIR, n)) for n in ("liboracle32.so", "liboracle64.so"))
+    if need:
+        subprocess.check_call(["make", "-s", "-C", ODIR, "oracle"])
+    if os.path.isdir("/root/reference/src/ani") and (force or not os.path.exists(os.path.join(ODIR, "_ref", "libnnpops_ref.so"))):
+        subprocess.check_call(["make", "-s", "-C", ODIR, "ref"])
+
+
+_libs = {}
+
+
+def lib(bits=32):
+    if bits not in _libs:
+        build()
+        _libs[bits] = C.CDLL(os.path.join(ODIR, "liboracle%d.so" % bits))
+    return _libs[bits]
+
+
+def ref_lib():
+    """The compiled reference (None when it was never built, e.g. fresh checkout without /root/reference)."""
+    if "ref" not in _libs:
+        build()
+        p = os.path.join(ODIR, "_ref", "libnnpops_ref.so")
+        _libs["ref"] = C.CDLL(p) if os.path.exists(p) else None
+    return _libs["ref"]
+
+
+def _opt(a, dtype):
+    return None if a is None else np.ascontiguousarray(a, dtype).ctypes.data_as(C.c_void_p)
+
+
+def fn_tables(EtaR, ShfR, EtaA, Zeta, ShfA, ShfZ):
+    """Expand the TorchANI constant lists into the reference's function tables, in the order of
+    /root/reference/src/pytorch/SymmetryFunctions.cpp:110-120."""
+    radial = np.array([[e, s] for e in EtaR for s in ShfR], np.float32)
+    angular = np.array([[e, s, z, t] for e in EtaA for z in Zeta for s in ShfA for t in ShfZ], np.float32)
+    return radial, angular
+
+
+def ani_forward(pos, species, n_species, rcr, rca, radial_fn, angular_fn, box=None, torchani=True, bits=32, impl="oracle"):
+    pos = np.ascontiguousarray(pos, np.float32)
+    species = np.ascontiguousarray(species, np.int32)
+    radial_fn = np.ascontiguousarray(radial_fn, np.float32).reshape(-1, 2)
+    angular_fn = np.ascontiguousarray(angular_fn, np.float32).reshape(-1, 4)
+    n = pos.shape[0]
+    nr, na = len(radial_fn), len(angular_fn)
+    npairs = n_species * (n_species + 1) // 2
+    if impl == "ref":
+        bits = 32
+    dt = np.float32 if bits == 32 else np.float64
+    radial = np.zeros((n, n_species * nr), dt)
+    angular = np.zeros((n, npairs * na), dt)
+    boxp = _opt(box, np.float32)
+    if impl == "ref":
+        ref_lib().ref_ani(n, n_species, C.c_float(rcr), C.c_float(rca), int(torchani), species.ctypes.data_as(C.c_void_p), nr,
+                          radial_fn.ctypes.data_as(C.c_void_p), na, angular_fn.ctypes.data_as(C.c_void_p),
+                          pos.ctypes.data_as(C.c_void_p), boxp, radial.ctypes.data_as(C.c_void_p), angular.ctypes.data_as(C.c_void_p),
+                          None, None, None)
+    else:
+        lib(bits).oracle_ani_forward(n, n_species, C.c_float(rcr), C.c_float(rca), int(torchani), species.ctypes.data_as(C.c_void_p), nr,
+                                     radial_fn.ctypes.data_as(C.c_void_p), na, angular_fn.ctypes.data_as(C.c_void_p),
+                                     pos.ctypes.data_as(C.c_void_p), boxp, radial.ctypes.data_as(C.c_void_p),
+                                     angular.ctypes.data_as(C.c_void_p))
+    return radial, angular
+
+
+def ani_backward(pos, species, n_species, rcr, rca, radial_fn, angular_fn, radial_grad, angular_grad, box=None, torchani=True,
+                 bits=32, impl="oracle"):
+    pos = np.ascontiguousarray(pos, np.float32)
+    species = np.ascontiguousarray(species, np.int32)
+    radial_fn = np.ascontiguousarray(radial_fn, np.float32).reshape(-1, 2)
+    angular_fn = np.ascontiguousarray(angular_fn, np.float32).reshape(-1, 4)
+    n = pos.shape[0]
+    nr, na = len(radial_fn), len(angular_fn)
+    if impl == "ref":
+        bits = 32
+    dt = np.float32 if bits == 32 else np.float64
+    rg = np.ascontiguousarray(radial_grad, dt)
+    ag = np.ascontiguousarray(angular_grad, dt)
+    out = np.zeros((n, 3), dt)
+    boxp = _opt(box, np.float32)
+    if impl == "ref":
+        radial = np.zeros_like(rg)
+        angular = np.zeros_like(ag)
+        ref_lib().ref_ani(n, n_species, C.c_float(rcr), C.c_float(rca), int(torchani), species.ctypes.data_as(C.c_void_p), nr,
+                          radial_fn.ctypes.data_as(C.c_void_p), na, angular_fn.ctypes.data_as(C.c_void_p),
+                          pos.ctypes.data_as(C.c_void_p), boxp, radial.ctypes.data_as(C.c_void_p), angular.ctypes.data_as(C.c_void_p),
+                          rg.ctypes.data_as(C.c_void_p), ag.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    else:
+        lib(bits).oracle_ani_backward(n, n_species, C.c_float(rcr), C.c_float(rca), int(torchani), species.ctypes.data_as(C.c_void_p), nr,
+                                      radial_fn.ctypes.data_as(C.c_void_p), na, angular_fn.ctypes.data_as(C.c_void_p),
+                                      pos.ctypes.data_as(C.c_void_p), boxp, rg.ctypes.data_as(C.c_void_p),
+                                      ag.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out
