@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""Headline benchmark: ANI-2x energy+force evaluations/s on a 50 000-atom periodic water box (BASELINE.json configs[2]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mlp tcgen05|simt] [--atoms 50000]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A step = one energy+force evaluation (AEV forward -> ensemble MLP forward/backward -> AEV backward) of one conformer.  With N
+GPUs every rank evaluates its own conformers (independent conformers, no collective on the data path: weak scaling); the
+timed region is bracketed by barrier + synchronize and the MAX over ranks is reported.  Rank 0 prints ONE JSON line.
+
+--impl reference: the reference's own CPU implementation of the path (oracle/_ref = the unmodified reference C++ compiled from
+/root/reference) on the host cores, AEV forward+backward only (its MLP, BatchedLinear with per-atom replicated weights, needs
+541 GB at this size), bounded sample per step, converted to the metric's unit with a measured a*N^2 + b*N model.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "ANI-2x energy+force evals/sec on 50k-atom box"
+UNIT = "evals/s"
+DEFAULT_MLP = "simt"   # switched to "tcgen05" once the tensor-core GEMM is parity-green
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # derived SIMT peak at max clock
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi samples of SM clock / throttle reasons during the timed region."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+                for k, nme in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_conformer(n_atoms, c):
+    from systems import lattice, cubic_box
+    pos, L = lattice(n_atoms, 2.154, 0.3, 3000 + c)
+    return pos, cubic_box(L)
+
+
+def run_ours(args):
+    import torch
+    from systems import ANI2X, ANI2X_HIDDEN, ANI2X_ENSEMBLE, water_species
+    from mlp_ref import random_networks
+    from nnpops_b200.OptimizedTorchANI import FusedANI
+    from nnpops_b200._lib import lib
+
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    n = args.atoms
+    species = water_species(n)
+    nets = random_networks(7, ANI2X_HIDDEN, ANI2X_ENSEMBLE, 1008, seed=42)
+    model = FusedANI(7, 5.2, ANI2X["Rca"], ANI2X["EtaR"], ANI2X["ShfR"], ANI2X["EtaA"], ANI2X["Zeta"], ANI2X["ShfA"], ANI2X["ShfZ"], species,
+                     nets, mlp_impl=args.mlp, device="cuda:%d" % local)
+    # pool of conformers per rank: conformer c of BASELINE config 3 goes to rank c mod world
+    pool = 4
+    confs = [make_conformer(n, rank + world * i) for i in range(pool)]
+    d_pos = [torch.tensor(p, device=dev) for p, _ in confs]
+    d_box = [torch.tensor(b, device=dev) for _, b in confs]
+    h_pos = [torch.tensor(p).pin_memory() for p, _ in confs]
+    h_box = [torch.tensor(b).pin_memory() for _, b in confs]
+    h_e = torch.zeros(1).pin_memory(); h_g = torch.zeros((n, 3)).pin_memory()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def launches():
+        import ctypes
+        c = ctypes.c_ulonglong(0)
+        lib.nnpops_launch_count(ctypes.byref(c))
+        return c.value
+
+    # ---- device-resident throughput ("value") with per-stage CUDA events
+    for i in range(args.warmup):
+        model.energy_and_gradient(d_pos[i % pool], d_box[i % pool])
+    sync_all()
+    work = model.work()
+    assert model.overflowed() == 0, "neighbour rows overflowed"
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    model.timing_begin(args.steps)
+    l0 = launches()
+    sync_all()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        model.energy_and_gradient(d_pos[i % pool], d_box[i % pool])
+    t1.record()
+    sync_all()
+    ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    l1 = launches()
+    stages, nrec = model.timing_end()
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.cpu()[0])
+
+    # ---- end to end through the host-buffer C-ABI entry point (pinned host memory; H2D + D2H inside the timed region)
+    for i in range(min(args.warmup, 3)):
+        model.energy_and_gradient_host(h_pos[i % pool].numpy(), h_box[i % pool].numpy(), h_e.numpy(), h_g.numpy())
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        model.energy_and_gradient_host(h_pos[i % pool].numpy(), h_box[i % pool].numpy(), h_e.numpy(), h_g.numpy())
+    e1.record()
+    sync_all()
+    ems = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if dist is not None:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    e2e_ms = float(ems.cpu()[0])
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    value = world * args.steps / (ms_total / 1e3)
+    # ---- roofline of the dominant kernel and of the AEV kernels (algorithmic work: SURVEY.md section 8d)
+    mlp_flops = 2.0 * work["mlp_flops_forward"]                      # forward + input-gradient backward
+    mlp_ms = stages["mlp_fwd"] + stages["mlp_bwd"]
+    tri, prs = work["triples"], work["radial_pairs"]
+    kernels = []
+
+    def kern(name, ms_, work_units, unit_work, bound, peak, unit):
+        ach = work_units * unit_work / (ms_ * 1e-3) / (1e12 if unit == "TFLOP/s" else 1e9) if ms_ > 0 else 0.0
+        kernels.append({"name": name, "ms": round(ms_, 4), "bound": bound, "achieved": round(ach, 3), "peak": round(peak, 1), "unit": unit,
+                        "frac": round(ach / peak, 4)})
+        return ach
+
+    mlp_peak = pk["bf16_tflops_sustained"]
+    kern("ani_angular_fwd_kernel", stages["angular_fwd"], tri, 146.0, "fp32", FP32_PEAK_TFLOPS, "TFLOP/s")
+    kern("ani_angular_bwd_kernel", stages["angular_bwd"], tri, 370.0, "fp32", FP32_PEAK_TFLOPS, "TFLOP/s")
+    kern("ani_radial_fwd_kernel", stages["radial_fwd"], prs, 134.0, "fp32", FP32_PEAK_TFLOPS, "TFLOP/s")
+    kern("ani_radial_bwd_kernel", stages["radial_bwd"], prs, 212.0, "fp32", FP32_PEAK_TFLOPS, "TFLOP/s")
+    kern("cell_list+ani_rows_kernel", stages["cells+rows"], n, 64.0 + 4.0 * 2 * prs / max(n, 1), "hbm", pk["hbm_gbs"], "GB/s")
+    mlp_ach = mlp_flops / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
+    gemm_name = "gemm_tcgen05_kernel" if args.mlp == "tcgen05" else "gemm_tn_simt_kernel"
+    roofline = {"kernel": gemm_name + " (all MLP GEMM launches of a step, forward + backward)", "bound": "tensor",
+                "achieved": round(mlp_ach, 3), "peak": mlp_peak, "unit": "TFLOP/s", "frac": round(mlp_ach / mlp_peak, 4), "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % pk["source"],
+                "algorithmic_flops_per_step": mlp_flops, "ms_per_step": round(mlp_ms, 4),
+                "note": "fp32-accurate GEMM; achieved counts algorithmic fp32 flops (2*M*N*K un-padded), not the 3 split products"}
+    out = {
+        "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[2]: ANI-2x, %d-atom periodic water box (jittered lattice, H/H/O), Rcr 5.2 A, Rca 3.5 A, "
+                               "8-member ensemble with random ANI-2x-shaped weights, one conformer per step per GPU, "
+                               "conformers split across GPUs with no collective" % n,
+                   "atoms": n, "conformers_per_rank_pool": pool, "mlp_impl": args.mlp,
+                   "l2": "per-step working set (AEV 205 MB + activations > 2 GB) exceeds the 126 MB L2; positions rotate through %d conformers" % pool,
+                   "triples_per_step": tri, "radial_pairs_per_step": prs},
+        "e2e": {"value": round(world * args.steps / (e2e_ms / 1e3), 4), "unit": UNIT, "h2d_bytes_per_step": n * 12 + 36,
+                "d2h_bytes_per_step": n * 12 + 4, "api": "nnpops_ani_model_energy_grad_host (C ABI, pinned host buffers)"},
+        "gpu_launches": int(l1 - l0),
+        "roofline": roofline,
+        "kernels": kernels,
+        "stage_ms": {k: round(v, 4) for k, v in stages.items()},
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(n, budget_s=20.0)
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the reference's CpuANISymmetryFunctions through oracle/_ref (kind "reference") or, when that
+# was never built, the C restatement (kind "port").
+# ----------------------------------------------------------------------------------------------------------------------
+def _cpu_eval(n_atoms, seed):
+    """One AEV forward+backward of an n-atom periodic box on one core; returns seconds."""
+    import oracle_lib as O
+    from systems import ANI2X, lattice, cubic_box, water_species
+    pos, L = lattice(n_atoms, 2.154, 0.3, seed)
+    species = water_species(n_atoms)
+    rfn, afn = O.fn_tables(ANI2X["EtaR"], ANI2X["ShfR"], ANI2X["EtaA"], ANI2X["Zeta"], ANI2X["ShfA"], ANI2X["ShfZ"])
+    rg = np.ones((n_atoms, 112), np.float32); ag = np.ones((n_atoms, 896), np.float32)
+    impl = "ref" if O.ref_lib() is not None else "oracle"
+    t = time.perf_counter()
+    O.ani_backward(pos, species, 7, 5.2, 3.5, rfn, afn, rg, ag, box=cubic_box(L), impl=impl)   # ref_ani runs forward + backward
+    if impl == "oracle":
+        O.ani_forward(pos, species, 7, 5.2, 3.5, rfn, afn, box=cubic_box(L))
+    return time.perf_counter() - t
+
+
+def _scale_model(n_full):
+    """Fit t(N) = a N^2 + b N from two small sizes (the reference scans all pairs) and return (a, b, kind)."""
+    import oracle_lib as O
+    n1, n2 = 3000, 6000
+    t1, t2 = _cpu_eval(n1, 9001), _cpu_eval(n2, 9002)
+    a = (t2 / n2 - t1 / n1) / (n2 - n1)
+    b = t1 / n1 - a * n1
+    if a <= 0 or b <= 0:   # degenerate fit: fall back to pure N^2
+        a, b = t2 / (n2 * n2), 0.0
+    return a, b, ("reference" if O.ref_lib() is not None else "port")
+
+
+def cpu_baseline(n_full, budget_s):
+    a, b, kind = _scale_model(n_full)
+    n_s = 10000
+    t = _cpu_eval(n_s, 9003)
+    t_full = t * (a * n_full ** 2 + b * n_full) / (a * n_s ** 2 + b * n_s)
+    return {"value": round(1.0 / t_full, 6), "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": "reference CpuANISymmetryFunctions AEV forward+backward (no MLP: the reference's BatchedLinear needs 541 GB of "
+                      "replicated weights at this size) on a %d-atom periodic box of the same density, %.2f s on one core, scaled to "
+                      "%d atoms with the measured a*N^2+b*N model (a=%.3e, b=%.3e) -> %.1f s per evaluation" % (n_s, t, n_full, a, b, t_full)}
+
+
+def _worker(q_in, q_out):
+    while True:
+        job = q_in.get()
+        if job is None:
+            return
+        q_out.put(_cpu_eval(*job))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    import oracle_lib as O
+    O.build()
+    cores = os.cpu_count() or 1
+    n_s = 6000
+    a, b, kind = _scale_model(args.atoms)
+    scale = (a * args.atoms ** 2 + b * args.atoms) / (a * n_s ** 2 + b * n_s)
+    ctx = mp.get_context("fork")
+    q_in, q_out = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(q_in, q_out), daemon=True) for _ in range(cores)]
+    for p in procs:
+        p.start()
+
+    def step(i):
+        for c in range(cores):
+            q_in.put((n_s, 9100 + i * cores + c))
+        return [q_out.get() for _ in range(cores)]
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    dt = time.perf_counter() - t0
+    for _ in procs:
+        q_in.put(None)
+    # each step evaluated `cores` samples; one sample = 1/scale of a full evaluation's work
+    value = cores * args.steps / (dt * scale)
+    sample = ("reference CpuANISymmetryFunctions (oracle/_ref, unmodified reference C++) AEV forward+backward, one %d-atom periodic box "
+              "per core per step on %d cores, scaled to %d atoms by the measured a*N^2+b*N cost model (factor %.1f); the reference "
+              "cannot run its MLP at this size (541 GB of replicated weights), so this is an upper bound on its evals/s" % (n_s, cores, args.atoms, scale))
+    out = {"impl": "reference", "metric": METRIC, "value": round(value, 6), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "BASELINE configs[2]: ANI-2x, %d-atom periodic water box, Rcr 5.2 A, Rca 3.5 A" % args.atoms, "atoms": args.atoms},
+           "cpu_baseline": {"value": round(value, 6), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+           "e2e": {"value": round(value, 6), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mlp", default=os.environ.get("NNPOPS_MLP", DEFAULT_MLP), choices=["tcgen05", "simt"])
+    ap.add_argument("--atoms", type=int, default=50000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

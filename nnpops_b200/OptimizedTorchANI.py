@@ -1,0 +1,209 @@
+"""ANI energy + forces on the B200 kernels.
+
+``FusedANI`` is the scalable module behind the BASELINE.json headline metric: one C-ABI call evaluates
+AEV -> species-grouped ensemble MLP -> dE/dx for a whole system (src/pytorch/OptimizedTorchANI.py:45-54 plus the autograd
+backward of the reference, without per-atom weight replication and without materialising anything on the host).
+``OptimizedTorchANI`` keeps the reference's constructor (a TorchANI-like model + atomic numbers) and forward signature and is
+built on FusedANI; the TorchANI objects are duck-typed, so no torchani import is needed.
+"""
+import ctypes as C
+from typing import List, NamedTuple, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from ._lib import lib, check, ptr, current_stream
+from .SymmetryFunctions import function_tables
+
+
+class SpeciesEnergies(NamedTuple):
+    species: Tensor
+    energies: Tensor
+
+
+def pack_network_params(networks: Sequence[Sequence[Sequence[Tuple[np.ndarray, np.ndarray]]]]):
+    """networks[s][e][l] = (W [out, in], b [out]) -> (dims int32 [S, L+1], flat float32 params) in the C-ABI order."""
+    S = len(networks)
+    L = len(networks[0][0])
+    dims = np.zeros((S, L + 1), np.int32)
+    chunks = []
+    for s in range(S):
+        for e, member in enumerate(networks[s]):
+            assert len(member) == L
+            for l, (W, b) in enumerate(member):
+                W = np.ascontiguousarray(W, np.float32)
+                b = np.ascontiguousarray(b, np.float32).reshape(-1)
+                if e == 0:
+                    dims[s, l], dims[s, l + 1] = W.shape[1], W.shape[0]
+                assert W.shape == (dims[s, l + 1], dims[s, l]) and b.shape[0] == W.shape[0]
+                chunks += [W.reshape(-1), b]
+    return dims, np.concatenate(chunks)
+
+
+class _EnergyGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, positions, cell):
+        energy, grad = module._evaluate(positions, cell)
+        ctx.save_for_backward(grad)
+        return energy
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_energy):
+        (grad,) = ctx.saved_tensors
+        return None, grad * grad_energy, None
+
+
+class FusedANI(torch.nn.Module):
+    """AEV + ensemble of per-species networks + analytic position gradient in one fused pipeline.
+
+    species: int sequence [N] with values in [0, num_species); networks[s][e][l] = (W, b) numpy arrays.
+    mlp_impl: "tcgen05" (tensor cores) or "simt" (fp32 validation path).
+    """
+
+    def __init__(self, num_species: int, Rcr: float, Rca: float, EtaR, ShfR, EtaA, Zeta, ShfA, ShfZ, species: Sequence[int],
+                 networks, mlp_impl: str = "tcgen05", device: str = "cuda", max_radial_neighbors: int = 0,
+                 max_angular_neighbors: int = 0):
+        super().__init__()
+        self.num_atoms = len(species)
+        self.num_species = int(num_species)
+        self.device_ = torch.device(device)
+        if self.device_.type != "cuda":
+            raise RuntimeError("nnpops_b200 runs on CUDA devices only (no CPU fallback)")
+        radial_fn, angular_fn = function_tables(EtaR, ShfR, EtaA, Zeta, ShfA, ShfZ)
+        dims, params = pack_network_params(networks)
+        sp = np.ascontiguousarray(species, np.int32)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device_):
+            check(lib.nnpops_ani_model_create(C.byref(h), self.num_atoms, self.num_species, float(Rcr), float(Rca), ptr(sp),
+                                              len(radial_fn), ptr(radial_fn), len(angular_fn), ptr(angular_fn), len(networks[0]),
+                                              dims.shape[1] - 1, ptr(dims), ptr(params), {"simt": 0, "tcgen05": 1}[mlp_impl],
+                                              max_radial_neighbors, max_angular_neighbors))
+        self._h = h
+        self.mlp_impl = mlp_impl
+        self.aev_length = int(dims[0, 0])
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.nnpops_ani_model_destroy(self._h)
+            self._h = None
+
+    def _evaluate(self, positions: Tensor, cell: Optional[Tensor]):
+        if positions.dtype != torch.float32 or positions.dim() != 2 or positions.shape != (self.num_atoms, 3):
+            raise RuntimeError('"positions" has to be a float32 tensor of shape (%d, 3)' % self.num_atoms)
+        if positions.device.type != "cuda":
+            raise RuntimeError("nnpops_b200 runs on CUDA devices only (no CPU fallback)")
+        pos = positions.detach().contiguous()
+        box = None
+        if cell is not None:
+            if cell.dtype != torch.float32 or cell.shape != (3, 3) or cell.device != positions.device:
+                raise RuntimeError('"cell" has to be a float32 (3, 3) tensor on the device of "positions"')
+            box = cell.detach().contiguous()
+        energy = torch.empty(1, dtype=torch.float32, device=pos.device)
+        grad = torch.empty_like(pos)
+        with torch.cuda.device(pos.device):
+            check(lib.nnpops_ani_model_energy_grad(self._h, ptr(pos), ptr(box), ptr(energy), ptr(grad), current_stream(pos.device)))
+        return energy, grad
+
+    def energy_and_gradient(self, positions: Tensor, cell: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+        """(energy [1], dE/dx [N, 3]) without autograd bookkeeping."""
+        return self._evaluate(positions, cell)
+
+    def energy_and_gradient_host(self, positions: np.ndarray, cell: Optional[np.ndarray], energy_out: np.ndarray, grad_out: np.ndarray):
+        """Host-buffer entry point (copies inside the call): the end-to-end path measured by bench.py."""
+        check(lib.nnpops_ani_model_energy_grad_host(self._h, ptr(positions), ptr(cell), ptr(energy_out), ptr(grad_out),
+                                                    current_stream(self.device_)))
+
+    def forward(self, positions: Tensor, cell: Optional[Tensor] = None) -> Tensor:
+        return _EnergyGrad.apply(self, positions, cell)
+
+    # -- introspection for tests / benchmarks
+    def buffers(self):
+        f, g, st = C.c_void_p(), C.c_void_p(), C.c_int()
+        rows = np.zeros(self.num_atoms, np.int32)
+        check(lib.nnpops_ani_model_buffers(self._h, C.byref(f), C.byref(g), C.byref(st), ptr(rows)))
+        return f.value, g.value, st.value, rows
+
+    def _read(self, which: int) -> Tensor:
+        out = torch.empty((self.num_atoms, self.aev_length), dtype=torch.float32, device=self.device_)
+        with torch.cuda.device(self.device_):
+            check(lib.nnpops_ani_model_read_features(self._h, which, ptr(out), current_stream(self.device_)))
+        return out
+
+    def features(self) -> Tensor:
+        """Copy of the AEV matrix of the last evaluation, atom order, [N, aev_length]."""
+        return self._read(0)
+
+    def feature_grad(self) -> Tensor:
+        """Copy of dE/dAEV of the last evaluation, atom order, [N, aev_length]."""
+        return self._read(1)
+
+    def work(self):
+        t, p, fl = C.c_longlong(0), C.c_longlong(0), C.c_double(0)
+        check(lib.nnpops_ani_model_work(self._h, C.byref(t), C.byref(p), C.byref(fl), current_stream(self.device_)))
+        return {"triples": t.value, "radial_pairs": p.value, "mlp_flops_forward": fl.value}
+
+    STAGES = ("cells+rows", "radial_fwd", "angular_fwd", "mlp_fwd", "mlp_bwd", "radial_bwd", "angular_bwd")
+
+    def timing_begin(self, max_steps: int):
+        check(lib.nnpops_ani_model_timing_begin(self._h, int(max_steps)))
+
+    def timing_end(self):
+        """-> (dict stage -> mean ms per evaluation, evaluations recorded); synchronises."""
+        ms = np.zeros(7, np.float32)
+        steps = C.c_int(0)
+        check(lib.nnpops_ani_model_timing_end(self._h, ptr(ms), C.byref(steps)))
+        k = max(steps.value, 1)
+        return {name: float(ms[i]) / k for i, name in enumerate(self.STAGES)}, steps.value
+
+    def overflowed(self) -> int:
+        f = C.c_int(0)
+        check(lib.nnpops_ani_model_overflowed(self._h, C.byref(f)))
+        return f.value
+
+
+def _linear_layers(sequential) -> List[Tuple[np.ndarray, np.ndarray]]:
+    """(W, b) of the nn.Linear members of a TorchANI per-species Sequential (items 0, 2, 4, 6: BatchedNN.py:55-59)."""
+    out = []
+    for layer in sequential:
+        if hasattr(layer, "weight") and hasattr(layer, "bias") and getattr(layer, "weight").dim() == 2:
+            out.append((layer.weight.detach().cpu().numpy(), layer.bias.detach().cpu().numpy()))
+    return out
+
+
+class OptimizedTorchANI(torch.nn.Module):
+    """Reference-compatible wrapper (src/pytorch/OptimizedTorchANI.py:33-54): ``model`` is a TorchANI-like object with
+    ``species_converter``, ``aev_computer``, ``neural_networks`` and ``energy_shifter``; ``atomicNumbers`` is [[Z...]].
+    forward((species, coordinates[1, N, 3]), cell, pbc) -> SpeciesEnergies(species, energies[1])."""
+
+    def __init__(self, model, atomicNumbers: Tensor, mlp_impl: str = "tcgen05") -> None:
+        super().__init__()
+        conv = model.species_converter
+        aev = model.aev_computer
+        species = conv((atomicNumbers, torch.empty(0))).species
+        self.register_buffer("species", species)
+        nets = model.neural_networks
+        ensemble = list(nets) if isinstance(nets, torch.nn.ModuleList) else [nets]
+        members = [list(m.values()) for m in ensemble]               # members[e][s] = Sequential
+        num_species = aev.num_species
+        networks = [[_linear_layers(members[e][s]) for e in range(len(members))] for s in range(num_species)]
+        self.fused = FusedANI(num_species, aev.Rcr, aev.Rca, aev.EtaR[:, 0].tolist(), aev.ShfR[0, :].tolist(),
+                              aev.EtaA[:, 0, 0, 0].tolist(), aev.Zeta[0, :, 0, 0].tolist(), aev.ShfA[0, 0, :, 0].tolist(),
+                              aev.ShfZ[0, 0, 0, :].tolist(), species[0].tolist(), networks, mlp_impl=mlp_impl,
+                              device=str(atomicNumbers.device) if atomicNumbers.device.type == "cuda" else "cuda")
+        # self energies are a constant (EnergyShifter.py:42-52)
+        self.register_buffer("self_energies", model.energy_shifter.sae(species))
+
+    def forward(self, species_coordinates: Tuple[Tensor, Tensor], cell: Optional[Tensor] = None,
+                pbc: Optional[Tensor] = None) -> SpeciesEnergies:
+        _, coordinates = species_coordinates
+        if coordinates.shape[0] != 1:
+            raise ValueError('Batched computation of molecules is not supported')
+        if cell is not None:
+            if pbc is None:
+                raise ValueError('"pbc" has to be defined')
+            if pbc.tolist() != [True, True, True]:
+                raise ValueError('Only fully periodic systems are supported, i.e. pbc = [True, True, True]')
+        energies = self.fused(coordinates[0], cell)
+        return SpeciesEnergies(self.species, energies + self.self_energies.to(energies.device))

@@ -1,0 +1,782 @@
+// ANI AEV forward/backward kernels for sm_100a.  See ani_aev.cuh for the contract and DESIGN.md for the layout.
+//
+// Pipeline per forward:  cell list  ->  ani_rows_kernel (per-atom neighbour rows, grouped by species, written once and
+// reused by the four compute kernels)  ->  ani_radial_fwd_kernel + ani_angular_fwd_kernel.
+// Backward: ani_radial_bwd_kernel (gather-only, plain store) -> ani_angular_bwd_kernel (centre-owned triples, neighbour
+// forces exchanged by warp shuffles, one red.add per neighbour component).
+//
+// Mathematics: SURVEY.md appendix A.1/A.2; the behaviour being matched is CpuANISymmetryFunctions.cpp:112-194 (forward)
+// and :228-353 (backward).  cos(theta - thetas) is evaluated as c*cos(thetas) + sqrt(1-c^2)*sin(thetas) instead of through
+// acosf/cosf, and a^zeta as ex2(zeta*lg2(a)).
+#include "ani_aev.cuh"
+#include <cmath>
+#include <cstring>
+
+namespace nnpops {
+
+namespace {
+
+constexpr int kWPB = 8;   // warps (= centre atoms) per CTA
+
+__device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2a(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rsqrta(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__device__ __forceinline__ int pair_index(int S, int s, int t) {   // CpuANISymmetryFunctions.cpp:39-43
+    int lo = min(s, t), hi = max(s, t);
+    return lo * S - (lo * (lo - 1)) / 2 + (hi - lo);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Neighbour rows.  One warp per centre atom (sorted order).  Candidates come from the <= 18 contiguous runs of the cell
+// list; the accept test is the reference's fp32 expression (strict r2 < Rc^2, CpuANISymmetryFunctions.cpp:129-135).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWPB * 32)
+ani_rows_kernel(int n, const float4* __restrict__ sorted, const int* __restrict__ sortedCell, const Geom* __restrict__ geom,
+                const int* __restrict__ cellStart, const AniTables* __restrict__ tab, int capR, int capA,
+                int* __restrict__ rowRad, int* __restrict__ rowAng, int* __restrict__ offRad, int* __restrict__ offAng,
+                int* __restrict__ flag) {
+    extern __shared__ unsigned char smemRaw[];
+    __shared__ Geom g;
+    if (threadIdx.x == 0) g = *geom;
+    __syncthreads();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * kWPB + w;
+    if (p >= n) return;
+    uint32_t* list = reinterpret_cast<uint32_t*>(smemRaw) + (size_t)w * capR;
+    int* cnt = reinterpret_cast<int*>(reinterpret_cast<uint32_t*>(smemRaw) + (size_t)kWPB * capR) + w * 128;
+    int* cntR = cnt, *cntA = cnt + 32, *curR = cnt + 64, *curA = cnt + 96;
+    const int S = tab->nSpecies;
+    const float rcr2 = tab->rcr2, rca2 = tab->rca2;
+    const float4 ci = sorted[p];
+    int count = 0;
+    for_each_candidate_run(g, cellStart, sortedCell[p], [&](int b, int e) {
+        for (int q0 = b; q0 < e; q0 += 32) {
+            const int q = q0 + lane;
+            bool ok = false;
+            uint32_t packed = 0;
+            if (q < e && q != p) {
+                const float4 cj = sorted[q];
+                float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
+                const float r2 = min_image_mul(g, dx, dy, dz);
+                if (r2 < rcr2) {
+                    ok = true;
+                    packed = (uint32_t)q | ((uint32_t)__float_as_int(cj.w) << 24) | (r2 < rca2 ? 0x80000000u : 0u);
+                }
+            }
+            const unsigned m = __ballot_sync(kFull, ok);
+            if (ok) {
+                const int idx = count + __popc(m & ((1u << lane) - 1u));
+                if (idx < capR) list[idx] = packed;
+            }
+            count += __popc(m);
+        }
+    });
+    if (count > capR) { if (lane == 0) atomicOr(flag, 1); count = capR; }
+    cntR[lane] = 0; cntA[lane] = 0;
+    __syncwarp();
+    for (int i = lane; i < count; i += 32) {
+        const uint32_t e = list[i];
+        const int s = (e >> 24) & 0x7f;
+        atomicAdd(&cntR[s], 1);
+        if (e & 0x80000000u) atomicAdd(&cntA[s], 1);
+    }
+    __syncwarp();
+    {   // exclusive scans over species (lane = species)
+        int vr = lane < S ? cntR[lane] : 0, va = lane < S ? cntA[lane] : 0;
+        int xr = vr, xa = va;
+        for (int o = 1; o < 32; o <<= 1) {
+            int yr = __shfl_up_sync(kFull, xr, o), ya = __shfl_up_sync(kFull, xa, o);
+            if (lane >= o) { xr += yr; xa += ya; }
+        }
+        const int totR = __shfl_sync(kFull, xr, 31), totA = __shfl_sync(kFull, xa, 31);
+        if (totA > capA && lane == 0) atomicOr(flag, 2);
+        curR[lane] = xr - vr; curA[lane] = xa - va;
+        if (lane < S) {
+            offRad[(size_t)p * (S + 1) + lane] = xr - vr;
+            offAng[(size_t)p * (S + 1) + lane] = min(xa - va, capA);
+        }
+        if (lane == 0) {
+            offRad[(size_t)p * (S + 1) + S] = totR;
+            offAng[(size_t)p * (S + 1) + S] = min(totA, capA);
+        }
+    }
+    __syncwarp();
+    // ordered placement: chunks of 32 entries in list order, rank inside a chunk from match_any -> deterministic rows
+    for (int base = 0; base < count; base += 32) {
+        const int i = base + lane;
+        const bool valid = i < count;
+        const uint32_t e = valid ? list[i] : 0u;
+        const int s = valid ? (int)((e >> 24) & 0x7f) : 0xff;
+        const bool ang = valid && (e & 0x80000000u);
+        const unsigned lt = (1u << lane) - 1u;
+        const unsigned mr = __match_any_sync(kFull, s);
+        const unsigned ma = __match_any_sync(kFull, ang ? s : 0xff);
+        int dstR = 0, dstA = 0;
+        if (valid) dstR = curR[s] + __popc(mr & lt);
+        if (ang) dstA = curA[s] + __popc(ma & lt);
+        __syncwarp();
+        if (valid && (mr & lt) == 0) curR[s] += __popc(mr);
+        if (ang && (ma & lt) == 0) curA[s] += __popc(ma);
+        __syncwarp();
+        const int j = (int)(e & 0x00ffffffu);
+        if (valid) rowRad[(size_t)p * capR + dstR] = j;
+        if (ang && dstA < capA) rowAng[(size_t)p * capA + dstA] = j;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Radial forward:  radial[i][s][k] = scale * sum_{j in species s} fc(r_ij) exp(-eta_k (r_ij - Rs_k)^2)
+// lane = (h, k): k = radial function, h = neighbour sub-stream; accumulators live in registers, no atomics, one store/element.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWPB * 32)
+ani_radial_fwd_kernel(int n, const float4* __restrict__ sorted, const int* __restrict__ sortedOrig, const Geom* __restrict__ geom,
+                      const AniTables* __restrict__ tab, const int* __restrict__ rowRad, const int* __restrict__ offRad, int capR,
+                      const int* __restrict__ rowMap, float* __restrict__ out, int stride) {
+    extern __shared__ unsigned char smemRaw[];
+    __shared__ Geom g;
+    __shared__ float sEtaL2[kAniMaxRadial], sShf[kAniMaxRadial];
+    const int nR = tab->nRadial, S = tab->nSpecies;
+    if (threadIdx.x == 0) g = *geom;
+    for (int i = threadIdx.x; i < nR; i += blockDim.x) { sEtaL2[i] = tab->rEtaL2[i]; sShf[i] = tab->rShf[i]; }
+    __syncthreads();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * kWPB + w;
+    if (p >= n) return;
+    float* sr = reinterpret_cast<float*>(smemRaw) + (size_t)w * 2 * capR;
+    float* sfc = sr + capR;
+    const int* off = offRad + (size_t)p * (S + 1);
+    const int cnt = min(off[S], capR);
+    const float4 ci = sorted[p];
+    const float rcr = tab->rcr;
+    const float kf = kPi / rcr;
+    for (int q = lane; q < cnt; q += 32) {
+        const float4 cj = sorted[rowRad[(size_t)p * capR + q]];
+        float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
+        const float r = sqrtf(min_image_mul(g, dx, dy, dz));
+        sr[q] = r;
+        sfc[q] = 0.5f * cosf(r * kf) + 0.5f;
+    }
+    __syncwarp();
+    const int orig = sortedOrig[p];
+    float* orow = out + (size_t)(rowMap ? rowMap[orig] : orig) * stride;
+    const float scale = tab->radialScale;
+    for (int k0 = 0; k0 < nR; k0 += 32) {
+        const int kk = min(nR - k0, 32);
+        int KP = 1;
+        while (KP < kk) KP <<= 1;
+        const int H = 32 / KP, k = lane % KP, h = lane / KP;
+        const bool kval = k < kk;
+        const float eta2 = kval ? sEtaL2[k0 + k] : 0.0f, shf = kval ? sShf[k0 + k] : 0.0f;
+        for (int s = 0; s < S; s++) {
+            const int b = off[s], e = min(off[s + 1], capR);
+            float acc = 0.0f;
+            for (int q = b + h; q < e; q += H) {
+                const float t = sr[q] - shf;
+                acc = fmaf(sfc[q], ex2a(-eta2 * t * t), acc);
+            }
+            for (int o = KP; o < 32; o <<= 1) acc += __shfl_xor_sync(kFull, acc, o);
+            if (h == 0 && kval) orow[s * nR + k0 + k] = acc * scale;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Angular forward.  Neighbours of the centre are staged in shared memory grouped by species, so every species-pair block
+// (s, t) is a dense index range of triples.  lane <-> triple; each lane keeps 32 channel accumulators in registers; a
+// butterfly transpose-reduce leaves lane m with channel m, written as one coalesced 128-byte store with the 2^(1-zeta)
+// scale folded in (the reference's separate scale pass, K3, disappears).
+// MODE 0: generic function table (any list of angular functions, literal evaluation per channel)
+// MODE 1: factorised  m = a*NSZ + z  with a single EtaA and a single Zeta (ANI-1x/2x shapes): NSZ pow + NSA exp per triple
+// ------------------------------------------------------------------------------------------------------------------
+struct AngTablesSmem {
+    float etaL2[kAniMaxAngular], eta[kAniMaxAngular], shf[kAniMaxAngular], zeta[kAniMaxAngular], cosT[kAniMaxAngular],
+        sinT[kAniMaxAngular], scale[kAniMaxAngular];
+};
+
+__device__ __forceinline__ void load_ang_tables(AngTablesSmem& t, const AniTables* __restrict__ tab) {
+    const int nA = tab->nAngular;
+    for (int i = threadIdx.x; i < nA; i += blockDim.x) {
+        t.etaL2[i] = tab->aEtaL2[i]; t.eta[i] = tab->aEta[i]; t.shf[i] = tab->aShf[i]; t.zeta[i] = tab->aZeta[i];
+        t.cosT[i] = tab->aCos[i]; t.sinT[i] = tab->aSin[i]; t.scale[i] = tab->aScale[i];
+    }
+}
+
+// lane L ends with sum over lanes of v[L]
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16, cnt = 16; off >= 1; off >>= 1, cnt >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < cnt; i++) {
+            const float send = up ? v[i] : v[i + cnt];
+            const float keep = up ? v[i + cnt] : v[i];
+            v[i] = keep + __shfl_xor_sync(kFull, send, off);
+        }
+    }
+    return v[0];
+}
+
+template <int MODE, int NSA, int NSZ, bool TORCHANI>
+__global__ void __launch_bounds__(kWPB * 32)
+ani_angular_fwd_kernel(int n, const float4* __restrict__ sorted, const int* __restrict__ sortedOrig, const Geom* __restrict__ geom,
+                       const AniTables* __restrict__ tab, const int* __restrict__ rowAng, const int* __restrict__ offAng, int capA,
+                       const int* __restrict__ rowMap, float* __restrict__ out, int stride) {
+    extern __shared__ unsigned char smemRaw[];
+    __shared__ Geom g;
+    __shared__ AngTablesSmem T;
+    __shared__ float fShfA[kAniMaxShf], fCos[kAniMaxShf], fSin[kAniMaxShf];
+    if (threadIdx.x == 0) g = *geom;
+    load_ang_tables(T, tab);
+    if (threadIdx.x < kAniMaxShf) { fShfA[threadIdx.x] = tab->fShfA[threadIdx.x]; fCos[threadIdx.x] = tab->fCos[threadIdx.x]; fSin[threadIdx.x] = tab->fSin[threadIdx.x]; }
+    __syncthreads();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * kWPB + w;
+    if (p >= n) return;
+    const int S = tab->nSpecies, nA = tab->nAngular;
+    float* sdx = reinterpret_cast<float*>(smemRaw) + (size_t)w * 6 * capA;
+    float *sdy = sdx + capA, *sdz = sdy + capA, *sr = sdz + capA, *sir = sr + capA, *sfc = sir + capA;
+    const int* off = offAng + (size_t)p * (S + 1);
+    const int cnt = min(off[S], capA);
+    const float4 ci = sorted[p];
+    const float kf = kPi / tab->rca;
+    for (int q = lane; q < cnt; q += 32) {
+        const float4 cj = sorted[rowAng[(size_t)p * capA + q]];
+        float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
+        const float r = sqrtf(min_image_mul(g, dx, dy, dz));
+        sdx[q] = dx; sdy[q] = dy; sdz[q] = dz; sr[q] = r; sir[q] = 1.0f / r;
+        sfc[q] = 0.5f * cosf(r * kf) + 0.5f;
+    }
+    __syncwarp();
+    const int orig = sortedOrig[p];
+    float* orow = out + (size_t)(rowMap ? rowMap[orig] : orig) * stride;
+    const float cosScale = tab->cosScale;
+    const float fEtaL2 = tab->fEtaL2, fZeta = tab->fZeta, fScale = tab->fScale;
+
+    for (int m0 = 0; m0 < nA; m0 += 32) {
+        int pIdx = 0;
+        for (int s = 0; s < S; s++) {
+            const int bs = off[s], ns = min(off[s + 1], capA) - bs;
+            for (int t = s; t < S; t++, pIdx++) {
+                const int bt = off[t], nt = min(off[t + 1], capA) - bt;
+                const int ntrip = (s == t) ? (ns * (ns - 1)) / 2 : ns * nt;
+                float* dst = orow + pIdx * nA + m0;
+                if (ntrip <= 0) {
+                    if (m0 + lane < nA) dst[lane] = 0.0f;
+                    continue;
+                }
+                float acc[32];
+#pragma unroll
+                for (int i = 0; i < 32; i++) acc[i] = 0.0f;
+                for (int q0 = 0; q0 < ntrip; q0 += 32) {
+                    const int q = q0 + lane;
+                    const bool valid = q < ntrip;
+                    const int qq = valid ? q : 0;
+                    int ia, ib;
+                    if (s == t) {   // unordered pairs a < b inside one segment: qq = b(b-1)/2 + a
+                        int b = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)qq)) * 0.5f);
+                        while ((b * (b - 1)) / 2 > qq) b--;
+                        while ((b * (b + 1)) / 2 <= qq) b++;
+                        ia = bs + qq - (b * (b - 1)) / 2; ib = bs + b;
+                    } else {
+                        const int a = (int)(((float)qq + 0.5f) / (float)nt);
+                        ia = bs + a; ib = bt + qq - a * nt;
+                    }
+                    const float ax = sdx[ia], ay = sdy[ia], az = sdz[ia], bx = sdx[ib], by = sdy[ib], bz = sdz[ib];
+                    const float dot = ax * bx + ay * by + az * bz;
+                    const float ipr = sir[ia] * sir[ib];
+                    const float c = cosScale * dot * ipr;
+                    float sn;
+                    if (TORCHANI) {
+                        sn = sqrtf(fmaxf(1.0f - c * c, 0.0f));
+                    } else {   // the reference switches to asin of the cross product near |cos| = 1 (CpuANISymmetryFunctions.cpp:396-404)
+                        const float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+                        sn = sqrtf(cx * cx + cy * cy + cz * cz) * ipr;
+                    }
+                    const float rm = 0.5f * (sr[ia] + sr[ib]);
+                    const float F = valid ? sfc[ia] * sfc[ib] : 0.0f;
+                    if (MODE == 1) {
+                        float P[NSZ];
+#pragma unroll
+                        for (int z = 0; z < NSZ; z++) {
+                            const float base = fmaxf(1.0f + c * fCos[z] + sn * fSin[z], 0.0f);
+                            P[z] = F * ex2a(fZeta * lg2a(base));
+                        }
+#pragma unroll
+                        for (int a = 0; a < NSA; a++) {
+                            const float tt = rm - fShfA[a];
+                            const float E = ex2a(-fEtaL2 * tt * tt);
+#pragma unroll
+                            for (int z = 0; z < NSZ; z++) acc[a * NSZ + z] = fmaf(P[z], E, acc[a * NSZ + z]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int mm = 0; mm < 32; mm++) {
+                            const int m = m0 + mm;
+                            if (m < nA) {
+                                const float base = fmaxf(1.0f + c * T.cosT[m] + sn * T.sinT[m], 0.0f);
+                                const float tt = rm - T.shf[m];
+                                acc[mm] = fmaf(F * ex2a(T.zeta[m] * lg2a(base)), ex2a(-T.etaL2[m] * tt * tt), acc[mm]);
+                            }
+                        }
+                    }
+                }
+                const float v = transpose_reduce32(acc, lane);
+                if (m0 + lane < nA) dst[lane] = v * (MODE == 1 ? fScale : T.scale[m0 + lane]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Radial backward, gather-only: dE/dx_i = -sum_j w_ij delta_ij / r_ij with
+// w_ij = scale * sum_k (G[i][s_j][k] + G[j][s_i][k]) * exp(..)(fc' - 2 eta (r - Rs_k) fc)   (CpuANISymmetryFunctions.cpp:228-263).
+// Every directed pair is evaluated by its centre, so there are no atomics and the result is a plain store that also
+// initialises positionGrad for the angular kernel that follows on the same stream.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWPB * 32)
+ani_radial_bwd_kernel(int n, const float4* __restrict__ sorted, const int* __restrict__ sortedOrig, const Geom* __restrict__ geom,
+                      const AniTables* __restrict__ tab, const int* __restrict__ rowRad, const int* __restrict__ offRad, int capR,
+                      const int* __restrict__ rowMap, const float* __restrict__ grad, int stride, float* __restrict__ posGrad) {
+    extern __shared__ unsigned char smemRaw[];
+    __shared__ Geom g;
+    __shared__ float sEtaL2[kAniMaxRadial], sEta[kAniMaxRadial], sShf[kAniMaxRadial];
+    const int nR = tab->nRadial, S = tab->nSpecies;
+    if (threadIdx.x == 0) g = *geom;
+    for (int i = threadIdx.x; i < nR; i += blockDim.x) { sEtaL2[i] = tab->rEtaL2[i]; sEta[i] = tab->rEta[i]; sShf[i] = tab->rShf[i]; }
+    __syncthreads();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * kWPB + w;
+    if (p >= n) return;
+    float* sux = reinterpret_cast<float*>(smemRaw) + (size_t)w * 7 * capR;
+    float *suy = sux + capR, *suz = suy + capR, *sr = suz + capR, *sfc = sr + capR, *sdfc = sfc + capR;
+    int* srow = reinterpret_cast<int*>(sdfc + capR);
+    const int* off = offRad + (size_t)p * (S + 1);
+    const int cnt = min(off[S], capR);
+    const float4 ci = sorted[p];
+    const int sp = __float_as_int(ci.w);
+    const float rcr = tab->rcr, kf = kPi / rcr;
+    for (int q = lane; q < cnt; q += 32) {
+        const int j = rowRad[(size_t)p * capR + q];
+        const float4 cj = sorted[j];
+        float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
+        const float r = sqrtf(min_image_mul(g, dx, dy, dz));
+        const float ir = 1.0f / r;
+        float sn, cs;
+        sincosf(r * kf, &sn, &cs);
+        sux[q] = dx * ir; suy[q] = dy * ir; suz[q] = dz * ir; sr[q] = r;
+        sfc[q] = 0.5f * cs + 0.5f;
+        sdfc[q] = -0.5f * kf * sn;
+        const int oj = sortedOrig[j];
+        srow[q] = rowMap ? rowMap[oj] : oj;
+    }
+    __syncwarp();
+    const int orig = sortedOrig[p];
+    const float* gi = grad + (size_t)(rowMap ? rowMap[orig] : orig) * stride;
+    float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+    for (int k0 = 0; k0 < nR; k0 += 32) {
+        const int kk = min(nR - k0, 32);
+        int KP = 1;
+        while (KP < kk) KP <<= 1;
+        const int H = 32 / KP, k = lane % KP, h = lane / KP;
+        const bool kval = k < kk;
+        const float eta2 = kval ? sEtaL2[k0 + k] : 0.0f, eta = kval ? sEta[k0 + k] : 0.0f, shf = kval ? sShf[k0 + k] : 0.0f;
+        for (int s = 0; s < S; s++) {
+            const int b = off[s], e = min(off[s + 1], capR);
+            if (b >= e) continue;
+            const float gc = kval ? gi[s * nR + k0 + k] : 0.0f;
+            for (int q = b + h; q < e; q += H) {
+                const float t = sr[q] - shf;
+                const float ex = ex2a(-eta2 * t * t);
+                const float dv = ex * (sdfc[q] - 2.0f * eta * t * sfc[q]);
+                const float gj = kval ? grad[(size_t)srow[q] * stride + sp * nR + k0 + k] : 0.0f;
+                const float wgt = (gc + gj) * dv;
+                fx = fmaf(wgt, sux[q], fx); fy = fmaf(wgt, suy[q], fy); fz = fmaf(wgt, suz[q], fz);
+            }
+        }
+    }
+    fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
+    if (lane == 0) {
+        const float sc = -tab->radialScale;
+        posGrad[3 * (size_t)orig] = sc * fx; posGrad[3 * (size_t)orig + 1] = sc * fy; posGrad[3 * (size_t)orig + 2] = sc * fz;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Angular backward (CpuANISymmetryFunctions.cpp:265-353).  lane <-> neighbour a of the centre.  In step d lane a evaluates
+// the triple (a, b = a + d mod n): it keeps the force on a, and the force on b travels to lane b by one shuffle (a rotation,
+// so all targets are distinct) -- no shared or global atomics inside the triple loop.  Rows longer than 32 fall back to
+// ordered pairs (each triple evaluated from both ends, still no communication).
+// ------------------------------------------------------------------------------------------------------------------
+struct TripleForce {
+    float ax, ay, az, bx, by, bz;
+};
+
+template <int MODE, int NSA, int NSZ, bool TORCHANI>
+__device__ __forceinline__ TripleForce
+triple_backward(float dax, float day, float daz, float ra, float ira, float fa, float dfa, float dbx, float dby, float dbz, float rb,
+                float irb, float fb, float dfb, const float* __restrict__ gp, int m0, int nA, const AngTablesSmem& T,
+                const float* __restrict__ fShfA, const float* __restrict__ fCos, const float* __restrict__ fSin, float cosScale,
+                float fEta, float fEtaL2, float fZeta, float fScale) {
+    const float dot = dax * dbx + day * dby + daz * dbz;
+    const float ipr = ira * irb;
+    const float c = cosScale * dot * ipr;
+    float sn, isn;
+    if (TORCHANI) {
+        sn = sqrtf(fmaxf(1.0f - c * c, 1e-30f));
+        isn = 1.0f / sn;
+    } else {
+        const float cx = day * dbz - daz * dby, cy = daz * dbx - dax * dbz, cz = dax * dby - day * dbx;
+        sn = sqrtf(cx * cx + cy * cy + cz * cz) * ipr;
+        isn = 1.0f / sn;
+    }
+    const float rm = 0.5f * (ra + rb);
+    float A = 0.0f, B = 0.0f, C = 0.0f;
+    if (MODE == 1) {
+        float P[NSZ], Q[NSZ];
+#pragma unroll
+        for (int z = 0; z < NSZ; z++) {
+            const float base = fmaxf(1.0f + c * fCos[z] + sn * fSin[z], 0.0f);
+            const float pm1 = ex2a((fZeta - 1.0f) * lg2a(base));
+            P[z] = pm1 * base;
+            Q[z] = -fZeta * pm1 * (sn * fCos[z] - c * fSin[z]);
+        }
+#pragma unroll
+        for (int a = 0; a < NSA; a++) {
+            const float tt = rm - fShfA[a];
+            const float E = ex2a(-fEtaL2 * tt * tt);
+            const float dE = -fEta * tt * E;
+            float Ta = 0.0f, Ua = 0.0f;
+#pragma unroll
+            for (int z = 0; z < NSZ; z++) {
+                const float gv = gp[a * NSZ + z];
+                Ta = fmaf(gv, P[z], Ta);
+                Ua = fmaf(gv, Q[z], Ua);
+            }
+            A = fmaf(Ta, E, A); B = fmaf(Ta, dE, B); C = fmaf(Ua, E, C);
+        }
+        A *= fScale; B *= fScale; C *= fScale;
+    } else {
+        for (int m = m0; m < nA; m++) {
+            const float base = fmaxf(1.0f + c * T.cosT[m] + sn * T.sinT[m], 0.0f);
+            const float pm1 = ex2a((T.zeta[m] - 1.0f) * lg2a(base));
+            const float Pz = pm1 * base;
+            const float Qz = -T.zeta[m] * pm1 * (sn * T.cosT[m] - c * T.sinT[m]);
+            const float tt = rm - T.shf[m];
+            const float E = ex2a(-T.etaL2[m] * tt * tt);
+            const float dE = -T.eta[m] * tt * E;
+            const float gv = gp[m] * T.scale[m];
+            A = fmaf(gv * Pz, E, A); B = fmaf(gv * Pz, dE, B); C = fmaf(gv * Qz, E, C);
+        }
+    }
+    const float F = fa * fb;
+    const float wa = (dfa * fb * A + F * B) * ira;
+    const float wb = (fa * dfb * A + F * B) * irb;
+    const float kk = -cosScale * isn * ipr * (F * C);
+    const float pa = dot * ira * ira, pb = dot * irb * irb;
+    TripleForce f;
+    f.ax = wa * dax + kk * (dbx - pa * dax); f.ay = wa * day + kk * (dby - pa * day); f.az = wa * daz + kk * (dbz - pa * daz);
+    f.bx = wb * dbx + kk * (dax - pb * dbx); f.by = wb * dby + kk * (day - pb * dby); f.bz = wb * dbz + kk * (daz - pb * dbz);
+    return f;
+}
+
+template <int MODE, int NSA, int NSZ, bool TORCHANI>
+__global__ void __launch_bounds__(kWPB * 32)
+ani_angular_bwd_kernel(int n, const float4* __restrict__ sorted, const int* __restrict__ sortedOrig, const Geom* __restrict__ geom,
+                       const AniTables* __restrict__ tab, const int* __restrict__ rowAng, const int* __restrict__ offAng, int capA,
+                       const int* __restrict__ rowMap, const float* __restrict__ grad, int stride, float* __restrict__ posGrad,
+                       int gPitch) {
+    extern __shared__ unsigned char smemRaw[];
+    __shared__ Geom g;
+    __shared__ AngTablesSmem T;
+    __shared__ float fShfA[kAniMaxShf], fCos[kAniMaxShf], fSin[kAniMaxShf];
+    if (threadIdx.x == 0) g = *geom;
+    load_ang_tables(T, tab);
+    if (threadIdx.x < kAniMaxShf) { fShfA[threadIdx.x] = tab->fShfA[threadIdx.x]; fCos[threadIdx.x] = tab->fCos[threadIdx.x]; fSin[threadIdx.x] = tab->fSin[threadIdx.x]; }
+    __syncthreads();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * kWPB + w;
+    if (p >= n) return;
+    const int S = tab->nSpecies, nA = tab->nAngular, nPairs = tab->nPairs;
+    const size_t perWarp = (size_t)9 * capA + (size_t)nPairs * gPitch;
+    float* sdx = reinterpret_cast<float*>(smemRaw) + (size_t)w * perWarp;
+    float *sdy = sdx + capA, *sdz = sdy + capA, *sr = sdz + capA, *sir = sr + capA, *sfc = sir + capA, *sdfc = sfc + capA;
+    int* ssp = reinterpret_cast<int*>(sdfc + capA);
+    int* sorig = ssp + capA;
+    float* sG = reinterpret_cast<float*>(sorig + capA);
+    const int* off = offAng + (size_t)p * (S + 1);
+    const int cnt = min(off[S], capA);
+    const int orig = sortedOrig[p];
+    if (cnt < 2) return;   // no triples -> no contribution (positionGrad was initialised by the radial kernel)
+    const float4 ci = sorted[p];
+    const float kf = kPi / tab->rca;
+    for (int q = lane; q < cnt; q += 32) {
+        const int j = rowAng[(size_t)p * capA + q];
+        const float4 cj = sorted[j];
+        float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
+        const float r = sqrtf(min_image_mul(g, dx, dy, dz));
+        float sn, cs;
+        sincosf(r * kf, &sn, &cs);
+        sdx[q] = dx; sdy[q] = dy; sdz[q] = dz; sr[q] = r; sir[q] = 1.0f / r;
+        sfc[q] = 0.5f * cs + 0.5f; sdfc[q] = -0.5f * kf * sn;
+        ssp[q] = __float_as_int(cj.w);
+        sorig[q] = sortedOrig[j];
+    }
+    {   // stage the centre's gradient row [nPairs][nA] with a pitch that spreads species pairs over banks
+        const float* gi = grad + (size_t)(rowMap ? rowMap[orig] : orig) * stride;
+        const int tot = nPairs * nA;
+        for (int i = lane; i < tot; i += 32) sG[(i / nA) * gPitch + (i % nA)] = gi[i];
+    }
+    __syncwarp();
+    const float cosScale = tab->cosScale, fEta = tab->fEta, fEtaL2 = tab->fEtaL2, fZeta = tab->fZeta, fScale = tab->fScale;
+    float cxs = 0.0f, cys = 0.0f, czs = 0.0f;   // force on the centre (negated sum)
+    auto eval = [&](int a, int b) {
+        const float* gp = sG + pair_index(S, ssp[a], ssp[b]) * gPitch;
+        return triple_backward<MODE, NSA, NSZ, TORCHANI>(sdx[a], sdy[a], sdz[a], sr[a], sir[a], sfc[a], sdfc[a], sdx[b], sdy[b], sdz[b],
+                                                         sr[b], sir[b], sfc[b], sdfc[b], gp, 0, nA, T, fShfA, fCos, fSin, cosScale, fEta,
+                                                         fEtaL2, fZeta, fScale);
+    };
+    if (cnt <= 32) {
+        const bool va = lane < cnt;
+        float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+        for (int d = 1; 2 * d <= cnt; d++) {
+            const bool act = va && (2 * d < cnt || lane < d);
+            TripleForce f = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+            if (act) {
+                int b = lane + d;
+                if (b >= cnt) b -= cnt;
+                f = eval(lane, b);
+                fx += f.ax; fy += f.ay; fz += f.az;
+                cxs -= f.ax + f.bx; cys -= f.ay + f.by; czs -= f.az + f.bz;
+            }
+            int src = lane - d;
+            if (src < 0) src += cnt;
+            src &= 31;
+            const float rx = __shfl_sync(kFull, f.bx, src), ry = __shfl_sync(kFull, f.by, src), rz = __shfl_sync(kFull, f.bz, src);
+            if (va) { fx += rx; fy += ry; fz += rz; }
+        }
+        if (va) {
+            float* dst = posGrad + 3 * (size_t)sorig[lane];
+            atomicAdd(dst, fx); atomicAdd(dst + 1, fy); atomicAdd(dst + 2, fz);
+        }
+    } else {
+        for (int a = lane; a < cnt; a += 32) {
+            float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+            for (int b = 0; b < cnt; b++) {
+                if (b == a) continue;
+                const TripleForce f = eval(a, b);
+                fx += f.ax; fy += f.ay; fz += f.az;
+            }
+            cxs -= fx; cys -= fy; czs -= fz;
+            float* dst = posGrad + 3 * (size_t)sorig[a];
+            atomicAdd(dst, fx); atomicAdd(dst + 1, fy); atomicAdd(dst + 2, fz);
+        }
+    }
+    cxs = warp_sum(cxs); cys = warp_sum(cys); czs = warp_sum(czs);
+    if (lane == 0) {
+        float* dst = posGrad + 3 * (size_t)orig;
+        atomicAdd(dst, cxs); atomicAdd(dst + 1, cys); atomicAdd(dst + 2, czs);
+    }
+}
+
+__global__ void count_kernel_triples(int n, int S, const int* __restrict__ offRad, const int* __restrict__ offAng, int capR, int capA,
+                                     unsigned long long* __restrict__ counters) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long tr = 0, pr = 0;
+    if (p < n) {
+        const long long na = min(offAng[(size_t)p * (S + 1) + S], capA);
+        tr = (unsigned long long)(na * (na - 1) / 2);
+        pr = (unsigned long long)min(offRad[(size_t)p * (S + 1) + S], capR);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        tr += __shfl_xor_sync(kFull, tr, o);
+        pr += __shfl_xor_sync(kFull, pr, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&counters[0], tr); atomicAdd(&counters[1], pr); }
+}
+
+template <typename K>
+void set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) NNP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------------
+
+AniAev::AniAev(int numAtoms, int numSpecies, float rcr, float rca, const int* atomSpecies, int nRadial, const float* radialFn,
+               int nAngular, const float* angularFn, bool torchani, int maxRadialNeighbors, int maxAngularNeighbors)
+    : n_(numAtoms) {
+    NNP_REQUIRE(numAtoms >= 0 && numAtoms < (1 << 24), "numAtoms must be in [0, 2^24)");
+    NNP_REQUIRE(numSpecies >= 1 && numSpecies <= kAniMaxSpecies, "numSpecies must be in [1, 32]");
+    NNP_REQUIRE(nRadial >= 0 && nRadial <= kAniMaxRadial, "at most 64 radial functions are supported");
+    NNP_REQUIRE(nAngular >= 0 && nAngular <= kAniMaxAngular, "at most 128 angular functions are supported");
+    for (int i = 0; i < numAtoms; i++)
+        NNP_REQUIRE(atomSpecies[i] >= 0 && atomSpecies[i] < numSpecies, "atomSpecies entries must be in [0, numSpecies)");
+    capR_ = maxRadialNeighbors > 0 ? maxRadialNeighbors : 256;
+    capA_ = maxAngularNeighbors > 0 ? maxAngularNeighbors : 96;
+    capR_ = (capR_ + 31) / 32 * 32;
+    capA_ = (capA_ + 31) / 32 * 32;
+    AniTables& t = tabHost_;
+    std::memset(&t, 0, sizeof(t));
+    t.nSpecies = numSpecies; t.nRadial = nRadial; t.nAngular = nAngular; t.nPairs = numSpecies * (numSpecies + 1) / 2;
+    t.rcr = rcr; t.rca = rca; t.rcr2 = rcr * rcr; t.rca2 = rca * rca;
+    t.torchani = torchani ? 1 : 0;
+    t.radialScale = torchani ? 0.25f : 1.0f;
+    t.cosScale = torchani ? 0.95f : 1.0f;
+    const double log2e = 1.4426950408889634;
+    for (int k = 0; k < nRadial; k++) {
+        t.rEta[k] = radialFn[2 * k]; t.rShf[k] = radialFn[2 * k + 1];
+        t.rEtaL2[k] = (float)((double)radialFn[2 * k] * log2e);
+    }
+    for (int m = 0; m < nAngular; m++) {
+        const float eta = angularFn[4 * m], rs = angularFn[4 * m + 1], zeta = angularFn[4 * m + 2], th = angularFn[4 * m + 3];
+        t.aEta[m] = eta; t.aEtaL2[m] = (float)((double)eta * log2e); t.aShf[m] = rs; t.aZeta[m] = zeta;
+        t.aCos[m] = (float)std::cos((double)th); t.aSin[m] = (float)std::sin((double)th);
+        t.aScale[m] = (float)std::pow(2.0, 1.0 - (double)zeta);
+    }
+    // detect the factorised TorchANI layout m = a * nShfZ + z with one EtaA and one Zeta
+    t.fast = 0;
+    if (nAngular == 32) {
+        for (int nz : {4, 8}) {
+            const int na = 32 / nz;
+            bool ok = true;
+            for (int m = 0; m < 32 && ok; m++) {
+                const int a = m / nz, z = m % nz;
+                ok = angularFn[4 * m] == angularFn[0] && angularFn[4 * m + 2] == angularFn[2] &&
+                     angularFn[4 * m + 1] == angularFn[4 * (a * nz) + 1] && angularFn[4 * m + 3] == angularFn[4 * z + 3];
+            }
+            if (ok) {
+                t.fast = 1; t.nShfA = na; t.nShfZ = nz;
+                t.fEta = angularFn[0]; t.fEtaL2 = (float)((double)angularFn[0] * log2e); t.fZeta = angularFn[2];
+                t.fScale = (float)std::pow(2.0, 1.0 - (double)angularFn[2]);
+                for (int a = 0; a < na; a++) t.fShfA[a] = angularFn[4 * (a * nz) + 1];
+                for (int z = 0; z < nz; z++) {
+                    t.fCos[z] = (float)std::cos((double)angularFn[4 * z + 3]);
+                    t.fSin[z] = (float)std::sin((double)angularFn[4 * z + 3]);
+                }
+                break;
+            }
+        }
+    }
+    const size_t na = (size_t)(n_ > 0 ? n_ : 1);
+    NNP_CUDA_CHECK(cudaMalloc(&tab_, sizeof(AniTables)));
+    NNP_CUDA_CHECK(cudaMemcpy(tab_, &t, sizeof(AniTables), cudaMemcpyHostToDevice));
+    NNP_CUDA_CHECK(cudaMalloc(&species_, sizeof(int) * na));
+    if (n_ > 0) NNP_CUDA_CHECK(cudaMemcpy(species_, atomSpecies, sizeof(int) * n_, cudaMemcpyHostToDevice));
+    cells_.init(n_);
+    NNP_CUDA_CHECK(cudaMalloc(&rowRad_, sizeof(int) * na * capR_));
+    NNP_CUDA_CHECK(cudaMalloc(&rowAng_, sizeof(int) * na * capA_));
+    NNP_CUDA_CHECK(cudaMalloc(&offRad_, sizeof(int) * na * (numSpecies + 1)));
+    NNP_CUDA_CHECK(cudaMalloc(&offAng_, sizeof(int) * na * (numSpecies + 1)));
+    NNP_CUDA_CHECK(cudaMalloc(&flag_, sizeof(int)));
+    NNP_CUDA_CHECK(cudaMemset(flag_, 0, sizeof(int)));
+    NNP_CUDA_CHECK(cudaMalloc(&counters_, 2 * sizeof(unsigned long long)));
+}
+
+AniAev::~AniAev() {
+    cudaFree(tab_); cudaFree(species_); cudaFree(rowRad_); cudaFree(rowAng_); cudaFree(offRad_); cudaFree(offAng_);
+    cudaFree(flag_); cudaFree(counters_);
+    cells_.release();
+}
+
+#define ANI_DISPATCH(KERNEL, ...)                                                                                      \
+    do {                                                                                                               \
+        const bool ta = tabHost_.torchani != 0;                                                                        \
+        if (tabHost_.fast && tabHost_.nShfA == 8 && tabHost_.nShfZ == 4) {                                             \
+            if (ta) { auto k = KERNEL<1, 8, 4, true>; set_smem(k, smem); k<<<grid, kWPB * 32, smem, stream>>>(__VA_ARGS__); } \
+            else    { auto k = KERNEL<1, 8, 4, false>; set_smem(k, smem); k<<<grid, kWPB * 32, smem, stream>>>(__VA_ARGS__); } \
+        } else if (tabHost_.fast && tabHost_.nShfA == 4 && tabHost_.nShfZ == 8) {                                      \
+            if (ta) { auto k = KERNEL<1, 4, 8, true>; set_smem(k, smem); k<<<grid, kWPB * 32, smem, stream>>>(__VA_ARGS__); } \
+            else    { auto k = KERNEL<1, 4, 8, false>; set_smem(k, smem); k<<<grid, kWPB * 32, smem, stream>>>(__VA_ARGS__); } \
+        } else {                                                                                                       \
+            if (ta) { auto k = KERNEL<0, 1, 1, true>; set_smem(k, smem); k<<<grid, kWPB * 32, smem, stream>>>(__VA_ARGS__); } \
+            else    { auto k = KERNEL<0, 1, 1, false>; set_smem(k, smem); k<<<grid, kWPB * 32, smem, stream>>>(__VA_ARGS__); } \
+        }                                                                                                              \
+    } while (0)
+
+void AniAev::forward(const float* positions, const float* box, float* radial, int radialStride, float* angular, int angularStride,
+                     cudaStream_t stream, cudaEvent_t* ev) {
+    if (n_ == 0) return;
+    cells_.build<float>(positions, box, species_, tabHost_.rcr > tabHost_.rca ? tabHost_.rcr : tabHost_.rca, stream);
+    const int grid = (n_ + kWPB - 1) / kWPB;
+    {
+        const size_t smem = (size_t)kWPB * capR_ * sizeof(uint32_t) + (size_t)kWPB * 128 * sizeof(int);
+        set_smem(ani_rows_kernel, smem);
+        ani_rows_kernel<<<grid, kWPB * 32, smem, stream>>>(n_, cells_.sorted, cells_.sortedCell, cells_.geom, cells_.cellStart, tab_,
+                                                           capR_, capA_, rowRad_, rowAng_, offRad_, offAng_, flag_);
+        count_launch();
+    }
+    if (ev) cudaEventRecord(ev[0], stream);
+    if (tabHost_.nRadial > 0) {
+        const size_t smem = (size_t)kWPB * 2 * capR_ * sizeof(float);
+        set_smem(ani_radial_fwd_kernel, smem);
+        ani_radial_fwd_kernel<<<grid, kWPB * 32, smem, stream>>>(n_, cells_.sorted, cells_.sortedOrig, cells_.geom, tab_, rowRad_, offRad_,
+                                                                 capR_, rowMap_, radial, radialStride);
+        count_launch();
+    }
+    if (ev) cudaEventRecord(ev[1], stream);
+    if (tabHost_.nAngular > 0) {
+        const size_t smem = (size_t)kWPB * 6 * capA_ * sizeof(float);
+        ANI_DISPATCH(ani_angular_fwd_kernel, n_, cells_.sorted, cells_.sortedOrig, cells_.geom, tab_, rowAng_, offAng_, capA_, rowMap_,
+                     angular, angularStride);
+        count_launch();
+    }
+    NNP_CUDA_CHECK(cudaGetLastError());
+    haveForward_ = true;
+}
+
+void AniAev::backward(const float* radialGrad, int radialStride, const float* angularGrad, int angularStride, float* positionGrad,
+                      cudaStream_t stream, cudaEvent_t* ev) {
+    if (n_ == 0) return;
+    NNP_REQUIRE(haveForward_, "backward() called before forward()");
+    const int grid = (n_ + kWPB - 1) / kWPB;
+    if (tabHost_.nRadial > 0) {
+        const size_t smem = (size_t)kWPB * 7 * capR_ * sizeof(float);
+        set_smem(ani_radial_bwd_kernel, smem);
+        ani_radial_bwd_kernel<<<grid, kWPB * 32, smem, stream>>>(n_, cells_.sorted, cells_.sortedOrig, cells_.geom, tab_, rowRad_, offRad_,
+                                                                 capR_, rowMap_, radialGrad, radialStride, positionGrad);
+        count_launch();
+    } else {
+        NNP_CUDA_CHECK(cudaMemsetAsync(positionGrad, 0, sizeof(float) * 3 * n_, stream));
+    }
+    if (ev) cudaEventRecord(ev[0], stream);
+    if (tabHost_.nAngular > 0) {
+        const int gPitch = tabHost_.nAngular + 1;
+        const size_t smem = (size_t)kWPB * ((size_t)9 * capA_ + (size_t)tabHost_.nPairs * gPitch) * sizeof(float);
+        NNP_REQUIRE(smem <= 200 * 1024, "angular gradient row does not fit in shared memory (numSpecies^2 * numAngular too large)");
+        ANI_DISPATCH(ani_angular_bwd_kernel, n_, cells_.sorted, cells_.sortedOrig, cells_.geom, tab_, rowAng_, offAng_, capA_, rowMap_,
+                     angularGrad, angularStride, positionGrad, gPitch);
+        count_launch();
+    }
+    NNP_CUDA_CHECK(cudaGetLastError());
+}
+
+int AniAev::overflowed() {
+    int h = 0;
+    NNP_CUDA_CHECK(cudaDeviceSynchronize());
+    NNP_CUDA_CHECK(cudaMemcpy(&h, flag_, sizeof(int), cudaMemcpyDeviceToHost));
+    return h;
+}
+
+long long AniAev::countTriples(cudaStream_t stream) {
+    if (n_ == 0 || !haveForward_) return 0;
+    unsigned long long h[2] = {0, 0};
+    NNP_CUDA_CHECK(cudaMemsetAsync(counters_, 0, 2 * sizeof(unsigned long long), stream));
+    count_kernel_triples<<<(n_ + 255) / 256, 256, 0, stream>>>(n_, tabHost_.nSpecies, offRad_, offAng_, capR_, capA_, counters_);
+    NNP_CUDA_CHECK(cudaMemcpyAsync(h, counters_, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    NNP_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return (long long)h[0];
+}
+
+long long AniAev::countRadialPairs(cudaStream_t stream) {
+    if (n_ == 0 || !haveForward_) return 0;
+    unsigned long long h[2] = {0, 0};
+    NNP_CUDA_CHECK(cudaMemsetAsync(counters_, 0, 2 * sizeof(unsigned long long), stream));
+    count_kernel_triples<<<(n_ + 255) / 256, 256, 0, stream>>>(n_, tabHost_.nSpecies, offRad_, offAng_, capR_, capA_, counters_);
+    NNP_CUDA_CHECK(cudaMemcpyAsync(h, counters_, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    NNP_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return (long long)(h[1] / 2);
+}
+
+}  // namespace nnpops

@@ -1,0 +1,81 @@
+// ANI atomic-environment-vector (AEV) forward/backward on sm_100a.  Replaces the reference's
+// CudaANISymmetryFunctions (src/ani/CudaANISymmetryFunctions.cu:186-670, kernels K1-K5 of SURVEY.md section 2.3) behind the same
+// contract as the abstract class ANISymmetryFunctions (src/ani/ANISymmetryFunctions.h:29-154).
+#pragma once
+#include <vector>
+#include "cell_list.cuh"
+
+namespace nnpops {
+
+constexpr int kAniMaxRadial = 64;
+constexpr int kAniMaxAngular = 128;
+constexpr int kAniMaxSpecies = 32;
+constexpr int kAniMaxShf = 16;
+
+// Parameter tables, resident in HBM and staged to shared memory by each kernel.
+struct AniTables {
+    int nSpecies, nRadial, nAngular, nPairs;
+    float rcr, rca;
+    float rcr2, rca2;            // cutoff^2 formed in fp32 exactly like the reference (radialCutoff*radialCutoff)
+    int torchani;
+    float radialScale;           // 0.25 (TorchANI) or 1            CpuANISymmetryFunctions.cpp:99-103
+    float cosScale;              // 0.95 (TorchANI) or 1            CpuANISymmetryFunctions.cpp:391-392
+    float rEta[kAniMaxRadial], rEtaL2[kAniMaxRadial], rShf[kAniMaxRadial];
+    float aEta[kAniMaxAngular], aEtaL2[kAniMaxAngular], aShf[kAniMaxAngular], aZeta[kAniMaxAngular];
+    float aCos[kAniMaxAngular], aSin[kAniMaxAngular], aScale[kAniMaxAngular];   // cos/sin(thetas), 2^(1-zeta)
+    // factorised form  m = a * nShfZ + z  (single EtaA, single Zeta), used by the fast kernels when fast != 0
+    int fast, nShfA, nShfZ;
+    float fEta, fEtaL2, fZeta, fScale;
+    float fShfA[kAniMaxShf], fCos[kAniMaxShf], fSin[kAniMaxShf];
+};
+
+class AniAev {
+public:
+    // radialFn: nRadial x {eta, rs}; angularFn: nAngular x {eta, rs, zeta, thetas}  (RadialFunction / AngularFunction of
+    // ANISymmetryFunctions.h:29-39); atomSpecies: host array [numAtoms].
+    AniAev(int numAtoms, int numSpecies, float rcr, float rca, const int* atomSpecies, int nRadial, const float* radialFn,
+           int nAngular, const float* angularFn, bool torchani, int maxRadialNeighbors, int maxAngularNeighbors);
+    ~AniAev();
+    AniAev(const AniAev&) = delete;
+    AniAev& operator=(const AniAev&) = delete;
+
+    // Optional map atom -> output row (device int[numAtoms]); nullptr = identity.  Used by the fused ANI model to write the AEV
+    // matrix in species-sorted row order.
+    void setRowMap(const int* deviceRowMap) { rowMap_ = deviceRowMap; }
+
+    // positions [n][3], box [3][3] or nullptr (all device, fp32).  radial/angular: device, row strides in floats.
+    // ev (optional): forward records ev[0] after the neighbour rows and ev[1] after the radial kernel; backward records ev[0]
+    // after the radial kernel -- used by the benchmark to time each kernel on the launching stream.
+    void forward(const float* positions, const float* box, float* radial, int radialStride, float* angular, int angularStride,
+                 cudaStream_t stream, cudaEvent_t* ev = nullptr);
+    // uses the positions/box of the most recent forward (ANISymmetryFunctions.h:83-84)
+    void backward(const float* radialGrad, int radialStride, const float* angularGrad, int angularStride, float* positionGrad,
+                  cudaStream_t stream, cudaEvent_t* ev = nullptr);
+    // synchronises; returns nonzero when a neighbour row overflowed its capacity during any call so far
+    int overflowed();
+
+    int numAtoms() const { return n_; }
+    int numSpecies() const { return tabHost_.nSpecies; }
+    int radialWidth() const { return tabHost_.nSpecies * tabHost_.nRadial; }
+    int angularWidth() const { return tabHost_.nPairs * tabHost_.nAngular; }
+    long long countTriples(cudaStream_t stream);   // sum_i n_i (n_i - 1) / 2 over the last forward (synchronises)
+    long long countRadialPairs(cudaStream_t stream);   // undirected pairs within Rcr over the last forward (synchronises)
+
+private:
+    int n_;
+    int capR_, capA_;
+    AniTables tabHost_;
+    AniTables* tab_ = nullptr;
+    int* species_ = nullptr;     // device [n]
+    CellList cells_;
+    int* rowRad_ = nullptr;      // [n][capR] sorted indices, grouped by species
+    int* rowAng_ = nullptr;      // [n][capA]
+    int* offRad_ = nullptr;      // [n][S+1]
+    int* offAng_ = nullptr;      // [n][S+1]
+    int* flag_ = nullptr;        // overflow flag
+    unsigned long long* counters_ = nullptr;   // [2] scratch for countTriples / countRadialPairs
+    const int* rowMap_ = nullptr;
+    bool haveForward_ = false;
+};
+
+}  // namespace nnpops

@@ -1,0 +1,239 @@
+// extern "C" boundary of libnnpops_b200.so; see include/nnpops_b200.h for the contract of every entry point.
+#include "../../include/nnpops_b200.h"
+#include <cstring>
+#include <string>
+#include "ani_model.cuh"
+
+namespace nnpops {
+void batched_linear_forward(const float*, const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+void batched_linear_backward(const float*, const float*, float*, int, int, int, int, cudaStream_t);
+}
+
+using namespace nnpops;
+
+namespace {
+thread_local std::string g_error;
+
+template <typename F>
+int guarded(F&& f) {
+    try {
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return 1;
+    } catch (...) {
+        g_error = "unknown error";
+        return 2;
+    }
+}
+
+void require_device() {
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        throw std::runtime_error("nnpops_b200 needs a CUDA device (there is no CPU fallback)");
+    }
+}
+}  // namespace
+
+struct nnpops_ani {
+    AniAev* impl;
+};
+struct nnpops_ani_model {
+    AniModel* impl;
+    float* dPos = nullptr;   // staging for the host-buffer entry point
+    float* dBox = nullptr;
+    float* dGrad = nullptr;
+    float* dEnergy = nullptr;
+    int n = 0;
+};
+
+extern "C" {
+
+const char* nnpops_last_error(void) { return g_error.c_str(); }
+int nnpops_abi_version(void) { return 1; }
+
+int nnpops_ani_create(nnpops_ani_t* out, int num_atoms, int num_species, float radial_cutoff, float angular_cutoff,
+                      const int* atom_species, int n_radial, const float* radial_fn, int n_angular, const float* angular_fn,
+                      int torchani, int max_radial_neighbors, int max_angular_neighbors) {
+    return guarded([&] {
+        require_device();
+        NNP_REQUIRE(out != nullptr, "out must not be NULL");
+        auto* h = new nnpops_ani;
+        h->impl = nullptr;
+        try {
+            h->impl = new AniAev(num_atoms, num_species, radial_cutoff, angular_cutoff, atom_species, n_radial, radial_fn, n_angular,
+                                 angular_fn, torchani != 0, max_radial_neighbors, max_angular_neighbors);
+        } catch (...) {
+            delete h;
+            throw;
+        }
+        *out = h;
+    });
+}
+
+void nnpops_ani_destroy(nnpops_ani_t h) {
+    if (!h) return;
+    delete h->impl;
+    delete h;
+}
+
+int nnpops_ani_forward(nnpops_ani_t h, const float* positions, const float* box, float* radial, float* angular, void* stream) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl, "invalid handle");
+        h->impl->forward(positions, box, radial, h->impl->radialWidth(), angular, h->impl->angularWidth(), (cudaStream_t)stream);
+    });
+}
+
+int nnpops_ani_backward(nnpops_ani_t h, const float* radial_grad, const float* angular_grad, float* position_grad, void* stream) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl, "invalid handle");
+        h->impl->backward(radial_grad, h->impl->radialWidth(), angular_grad, h->impl->angularWidth(), position_grad, (cudaStream_t)stream);
+    });
+}
+
+int nnpops_ani_overflowed(nnpops_ani_t h, int* flags) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl && flags, "invalid argument");
+        *flags = h->impl->overflowed();
+    });
+}
+
+int nnpops_ani_work(nnpops_ani_t h, long long* triples, long long* radial_pairs, void* stream) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl, "invalid handle");
+        if (triples) *triples = h->impl->countTriples((cudaStream_t)stream);
+        if (radial_pairs) *radial_pairs = h->impl->countRadialPairs((cudaStream_t)stream);
+    });
+}
+
+int nnpops_ani_model_create(nnpops_ani_model_t* out, int num_atoms, int num_species, float radial_cutoff, float angular_cutoff,
+                            const int* atom_species, int n_radial, const float* radial_fn, int n_angular, const float* angular_fn,
+                            int ensemble_size, int num_layers, const int* dims, const float* params, int mlp_impl,
+                            int max_radial_neighbors, int max_angular_neighbors) {
+    return guarded([&] {
+        require_device();
+        NNP_REQUIRE(out != nullptr, "out must not be NULL");
+        auto* h = new nnpops_ani_model;
+        try {
+            h->impl = new AniModel(num_atoms, num_species, radial_cutoff, angular_cutoff, atom_species, n_radial, radial_fn, n_angular,
+                                   angular_fn, ensemble_size, num_layers, dims, params, max_radial_neighbors, max_angular_neighbors);
+            h->impl->mlp().setImpl(mlp_impl == 1 ? MlpImpl::Tcgen05 : MlpImpl::Simt);
+            h->n = num_atoms;
+        } catch (...) {
+            delete h;
+            throw;
+        }
+        *out = h;
+    });
+}
+
+void nnpops_ani_model_destroy(nnpops_ani_model_t h) {
+    if (!h) return;
+    delete h->impl;
+    cudaFree(h->dPos); cudaFree(h->dBox); cudaFree(h->dGrad); cudaFree(h->dEnergy);
+    delete h;
+}
+
+int nnpops_ani_model_energy_grad(nnpops_ani_model_t h, const float* positions, const float* box, float* energy, float* position_grad,
+                                 void* stream) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl, "invalid handle");
+        h->impl->energyAndGradient(positions, box, energy, position_grad, (cudaStream_t)stream);
+    });
+}
+
+int nnpops_ani_model_energy_grad_host(nnpops_ani_model_t h, const float* positions_host, const float* box_host, float* energy_host,
+                                      float* position_grad_host, void* stream) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl, "invalid handle");
+        cudaStream_t s = (cudaStream_t)stream;
+        const size_t n = (size_t)(h->n > 0 ? h->n : 1);
+        if (!h->dPos) {
+            NNP_CUDA_CHECK(cudaMalloc(&h->dPos, sizeof(float) * 3 * n));
+            NNP_CUDA_CHECK(cudaMalloc(&h->dBox, sizeof(float) * 9));
+            NNP_CUDA_CHECK(cudaMalloc(&h->dGrad, sizeof(float) * 3 * n));
+            NNP_CUDA_CHECK(cudaMalloc(&h->dEnergy, sizeof(float)));
+        }
+        NNP_CUDA_CHECK(cudaMemcpyAsync(h->dPos, positions_host, sizeof(float) * 3 * h->n, cudaMemcpyHostToDevice, s));
+        if (box_host) NNP_CUDA_CHECK(cudaMemcpyAsync(h->dBox, box_host, sizeof(float) * 9, cudaMemcpyHostToDevice, s));
+        h->impl->energyAndGradient(h->dPos, box_host ? h->dBox : nullptr, h->dEnergy, h->dGrad, s);
+        NNP_CUDA_CHECK(cudaMemcpyAsync(energy_host, h->dEnergy, sizeof(float), cudaMemcpyDeviceToHost, s));
+        NNP_CUDA_CHECK(cudaMemcpyAsync(position_grad_host, h->dGrad, sizeof(float) * 3 * h->n, cudaMemcpyDeviceToHost, s));
+        NNP_CUDA_CHECK(cudaStreamSynchronize(s));
+    });
+}
+
+int nnpops_ani_model_buffers(nnpops_ani_model_t h, float** features, float** feature_grad, int* stride, int* row_of_atom) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl, "invalid handle");
+        if (features) *features = h->impl->features();
+        if (feature_grad) *feature_grad = h->impl->featureGrad();
+        if (stride) *stride = h->impl->featureStride();
+        if (row_of_atom) std::memcpy(row_of_atom, h->impl->rowOfAtom().data(), sizeof(int) * h->impl->rowOfAtom().size());
+    });
+}
+
+int nnpops_ani_model_read_features(nnpops_ani_model_t h, int which, float* out, void* stream) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl && out, "invalid argument");
+        h->impl->readFeatures(which, out, (cudaStream_t)stream);
+    });
+}
+
+int nnpops_ani_model_work(nnpops_ani_model_t h, long long* triples, long long* radial_pairs, double* mlp_flops_forward, void* stream) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl, "invalid handle");
+        if (triples) *triples = h->impl->aev().countTriples((cudaStream_t)stream);
+        if (radial_pairs) *radial_pairs = h->impl->aev().countRadialPairs((cudaStream_t)stream);
+        if (mlp_flops_forward) *mlp_flops_forward = h->impl->mlp().flopsForward();
+    });
+}
+
+int nnpops_ani_model_overflowed(nnpops_ani_model_t h, int* flags) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl && flags, "invalid argument");
+        *flags = h->impl->aev().overflowed();
+    });
+}
+
+int nnpops_ani_model_timing_begin(nnpops_ani_model_t h, int max_steps) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl && max_steps > 0, "invalid argument");
+        h->impl->timingBegin(max_steps);
+    });
+}
+
+int nnpops_ani_model_timing_end(nnpops_ani_model_t h, float* stage_ms, int* steps) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl && stage_ms && steps, "invalid argument");
+        *steps = h->impl->timingEnd(stage_ms);
+    });
+}
+
+int nnpops_launch_count(unsigned long long* count) {
+    return guarded([&] {
+        NNP_REQUIRE(count, "invalid argument");
+        *count = g_launches;
+    });
+}
+
+int nnpops_batched_linear_forward(const float* vectors, const float* weights, const float* biases, float* out, int num_atoms,
+                                  int num_models, int vec_models, int n_out, int n_in, void* stream) {
+    return guarded([&] {
+        require_device();
+        batched_linear_forward(vectors, weights, biases, out, num_atoms, num_models, vec_models, n_out, n_in, (cudaStream_t)stream);
+    });
+}
+
+int nnpops_batched_linear_backward(const float* grad_out, const float* weights, float* grad_vectors, int num_atoms, int num_models,
+                                   int n_out, int n_in, void* stream) {
+    return guarded([&] {
+        require_device();
+        batched_linear_backward(grad_out, weights, grad_vectors, num_atoms, num_models, n_out, n_in, (cudaStream_t)stream);
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,284 @@
+// Species-grouped MLP: host orchestration + the fp32 SIMT GEMM (validation path).  The tensor-core path lives in
+// mlp_tcgen05.cu and plugs in through the same GemmArgs.
+#include "species_mlp.cuh"
+#include <algorithm>
+#include <cstring>
+
+namespace nnpops {
+
+void launch_gemm_tcgen05(const GemmArgs& a, cudaStream_t stream);   // mlp_tcgen05.cu
+
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 16;
+
+__device__ __forceinline__ float celu(float x) { return x > 0.0f ? x : kCeluAlpha * (__expf(x * (1.0f / kCeluAlpha)) - 1.0f); }
+// derivative recovered from the activation value a = celu(z): 1 for a > 0, exp(z/alpha) = a/alpha + 1 otherwise
+__device__ __forceinline__ float celu_grad_from_act(float a) { return a > 0.0f ? 1.0f : a * (1.0f / kCeluAlpha) + 1.0f; }
+
+__global__ void __launch_bounds__(256) gemm_tn_simt_kernel(GemmArgs g) {
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int z = blockIdx.z;
+    const float* A = g.A + (size_t)z * g.aBatchCols;
+    const float* B = g.B + (size_t)z * g.bBatch;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+    for (int k0 = 0; k0 < g.K; k0 += BK) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int idx = tid + i * 256, row = idx >> 2, kq = idx & 3;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + row < g.M) v = *reinterpret_cast<const float4*>(A + (size_t)(m0 + row) * g.lda + k0 + kq * 4);
+            As[kq * 4 + 0][row] = v.x; As[kq * 4 + 1][row] = v.y; As[kq * 4 + 2][row] = v.z; As[kq * 4 + 3][row] = v.w;
+        }
+        {
+            const int row = tid >> 2, kq = tid & 3;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n0 + row < g.N) v = *reinterpret_cast<const float4*>(B + (size_t)(n0 + row) * g.ldb + k0 + kq * 4);
+            Bs[kq * 4 + 0][row] = v.x; Bs[kq * 4 + 1][row] = v.y; Bs[kq * 4 + 2][row] = v.z; Bs[kq * 4 + 3][row] = v.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; k++) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* C = g.C + (size_t)z * g.cBatchCols;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int m = m0 + ty * 8 + i;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= g.N) continue;
+            float v = acc[i][j];
+            if (g.epilogue == 1) v = celu(v + g.bias[(size_t)z * g.biasBatch + n]);
+            else if (g.epilogue == 2) v *= celu_grad_from_act(g.act[(size_t)m * g.ldact + (size_t)z * g.actBatchCols + n]);
+            C[(size_t)m * g.ldc + n] = v;
+        }
+    }
+}
+
+// last layer (out = 1): E[r, e] = sum_c A[r, e*hP + c] * w[e][c] + b[e]; accumulate sum over rows and members in double
+__global__ void final_energy_kernel(const float* __restrict__ act, int ld, int rows, int M, int hP, const float* __restrict__ w,
+                                    const float* __restrict__ b, double* __restrict__ acc) {
+    // one warp per (row, member)
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    float s = 0.0f;
+    if (gw < rows * M) {
+        const int r = gw / M, e = gw % M;
+        const float* a = act + (size_t)r * ld + (size_t)e * hP;
+        for (int c = lane; c < hP; c += 32) s = fmaf(a[c], w[e * hP + c], s);
+        s = warp_sum(s);
+        if (lane == 0) s += b[e];
+    }
+    __shared__ double part[32];
+    double d = (gw < rows * M && lane == 0) ? (double)s : 0.0;
+    if (lane == 0) part[threadIdx.x >> 5] = d;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += part[i];
+        atomicAdd(acc, t);
+    }
+}
+
+__global__ void finish_energy_kernel(const double* __restrict__ acc, int M, float* __restrict__ energy) { *energy = (float)(*acc / M); }
+
+// dZ[r, e*hP + c] = (w[e][c] / M) * celu'(A[r, e*hP + c])
+__global__ void backward_seed_kernel(const float* __restrict__ act, int ld, int rows, int M, int hP, const float* __restrict__ w,
+                                     float* __restrict__ dz, int lddz) {
+    const int width = M * hP;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)rows * width) return;
+    const int r = (int)(idx / width), c = (int)(idx % width);
+    dz[(size_t)r * lddz + c] = (w[c] * (1.0f / M)) * celu_grad_from_act(act[(size_t)r * ld + c]);
+}
+
+}  // namespace
+
+void launch_gemm_simt(const GemmArgs& a, cudaStream_t stream) {
+    if (a.M <= 0 || a.N <= 0) return;
+    NNP_REQUIRE(a.K % BK == 0 && a.lda % 4 == 0 && a.ldb % 4 == 0 && a.aBatchCols % 4 == 0 && a.bBatch % 4 == 0,
+                "gemm_simt: K must be a multiple of 16 and leading dimensions multiples of 4");
+    dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, a.batch);
+    gemm_tn_simt_kernel<<<grid, 256, 0, stream>>>(a);
+    count_launch();
+}
+
+static int pad_to(int x, int p) { return (x + p - 1) / p * p; }
+
+SpeciesMlp::SpeciesMlp(int numSpecies, int ensemble, int numLayers, const int* dims, const float* params, const int* rowStart,
+                       int featureStride)
+    : S_(numSpecies), M_(ensemble), L_(numLayers), featStride_(featureStride) {
+    NNP_REQUIRE(numLayers >= 2, "the per-atom network needs at least two layers");
+    NNP_REQUIRE(ensemble >= 1, "ensemble size must be >= 1");
+    rowStart_.assign(rowStart, rowStart + numSpecies + 1);
+    rows_ = rowStart_[numSpecies];
+    const int nFeat = dims[0];
+    featP_ = pad_to(nFeat, kMlpPad);
+    NNP_REQUIRE(featureStride >= featP_ && featureStride % 4 == 0, "featureStride must be >= numFeatures padded to 64");
+    layers_.resize(S_);
+    width_.assign(L_ - 1, 0);
+    const float* p = params;
+    for (int s = 0; s < S_; s++) {
+        const int* d = dims + (size_t)s * (L_ + 1);
+        NNP_REQUIRE(d[0] == nFeat, "all species must take the same number of input features");
+        NNP_REQUIRE(d[L_] == 1, "the last layer must have one output");
+        layers_[s].resize(L_);
+        for (int l = 0; l < L_; l++) {
+            Layer& ly = layers_[s][l];
+            ly.in = d[l]; ly.out = d[l + 1];
+            ly.inP = pad_to(ly.in, kMlpPad);
+            ly.outP = (l == L_ - 1) ? 1 : pad_to(ly.out, kMlpPad);
+            if (l < L_ - 1) width_[l] = std::max(width_[l], M_ * ly.outP);
+        }
+    }
+    // params are laid out species -> member -> layer, so walk them in that order while filling the per-layer staging
+    std::vector<std::vector<std::vector<float>>> hW(S_), hWt(S_), hb(S_);
+    for (int s = 0; s < S_; s++) {
+        hW[s].resize(L_); hWt[s].resize(L_); hb[s].resize(L_);
+        for (int l = 0; l < L_; l++) {
+            const Layer& ly = layers_[s][l];
+            hW[s][l].assign((size_t)M_ * ly.outP * ly.inP, 0.0f);
+            hWt[s][l].assign((size_t)M_ * ly.outP * ly.inP, 0.0f);
+            hb[s][l].assign((size_t)M_ * ly.outP, 0.0f);
+        }
+        for (int e = 0; e < M_; e++)
+            for (int l = 0; l < L_; l++) {
+                const Layer& ly = layers_[s][l];
+                for (int o = 0; o < ly.out; o++)
+                    for (int i = 0; i < ly.in; i++) {
+                        const float v = p[(size_t)o * ly.in + i];
+                        hW[s][l][((size_t)e * ly.outP + o) * ly.inP + i] = v;
+                        if (l == 0) hWt[s][l][(size_t)i * (M_ * ly.outP) + (size_t)e * ly.outP + o] = v;   // [inP][M*outP]
+                        else hWt[s][l][((size_t)e * ly.inP + i) * ly.outP + o] = v;                          // [M][inP][outP]
+                    }
+                p += (size_t)ly.out * ly.in;
+                for (int o = 0; o < ly.out; o++) hb[s][l][(size_t)e * ly.outP + o] = p[o];
+                p += ly.out;
+                if (l < L_ - 1) flopsFwd_ += 2.0 * ly.in * ly.out * (double)(rowStart_[s + 1] - rowStart_[s]);
+                else flopsFwd_ += 2.0 * ly.in * (double)(rowStart_[s + 1] - rowStart_[s]);
+            }
+        for (int l = 0; l < L_; l++) {
+            Layer& ly = layers_[s][l];
+            const size_t nw = hW[s][l].size(), nb = hb[s][l].size();
+            NNP_CUDA_CHECK(cudaMalloc(&ly.W, sizeof(float) * nw));
+            NNP_CUDA_CHECK(cudaMalloc(&ly.Wt, sizeof(float) * nw));
+            NNP_CUDA_CHECK(cudaMalloc(&ly.b, sizeof(float) * nb));
+            NNP_CUDA_CHECK(cudaMemcpy(ly.W, hW[s][l].data(), sizeof(float) * nw, cudaMemcpyHostToDevice));
+            NNP_CUDA_CHECK(cudaMemcpy(ly.Wt, hWt[s][l].data(), sizeof(float) * nw, cudaMemcpyHostToDevice));
+            NNP_CUDA_CHECK(cudaMemcpy(ly.b, hb[s][l].data(), sizeof(float) * nb, cudaMemcpyHostToDevice));
+        }
+    }
+    act_.assign(L_ - 1, nullptr);
+    dz_.assign(L_ - 1, nullptr);
+    const size_t nr = (size_t)std::max(rows_, 1);
+    for (int l = 0; l < L_ - 1; l++) {
+        NNP_CUDA_CHECK(cudaMalloc(&act_[l], sizeof(float) * nr * width_[l]));
+        NNP_CUDA_CHECK(cudaMalloc(&dz_[l], sizeof(float) * nr * width_[l]));
+    }
+    NNP_CUDA_CHECK(cudaMalloc(&energyAcc_, sizeof(double)));
+}
+
+SpeciesMlp::~SpeciesMlp() {
+    for (auto& sp : layers_)
+        for (auto& ly : sp) { cudaFree(ly.W); cudaFree(ly.Wt); cudaFree(ly.b); }
+    for (float* p : act_) cudaFree(p);
+    for (float* p : dz_) cudaFree(p);
+    cudaFree(energyAcc_);
+}
+
+static void run_gemm(MlpImpl impl, const GemmArgs& a, cudaStream_t stream) {
+    if (impl == MlpImpl::Tcgen05) launch_gemm_tcgen05(a, stream);
+    else launch_gemm_simt(a, stream);
+}
+
+void SpeciesMlp::forward(const float* features, float* energy, cudaStream_t stream) {
+    NNP_CUDA_CHECK(cudaMemsetAsync(energyAcc_, 0, sizeof(double), stream));
+    for (int s = 0; s < S_; s++) {
+        const int r0 = rowStart_[s], nr = rowStart_[s + 1] - r0;
+        if (nr == 0) continue;
+        for (int l = 0; l < L_ - 1; l++) {
+            const Layer& ly = layers_[s][l];
+            GemmArgs g;
+            std::memset(&g, 0, sizeof(g));
+            g.M = nr; g.epilogue = 1; g.bias = ly.b; g.ldb = ly.inP; g.K = ly.inP;
+            g.C = act_[l] + (size_t)r0 * width_[l]; g.ldc = width_[l];
+            if (l == 0) {   // all ensemble members side by side: N = M * outP
+                g.A = features + (size_t)r0 * featStride_; g.lda = featStride_; g.aBatchCols = 0;
+                g.B = ly.W; g.bBatch = 0; g.N = M_ * ly.outP; g.batch = 1; g.cBatchCols = 0; g.biasBatch = 0;
+            } else {
+                g.A = act_[l - 1] + (size_t)r0 * width_[l - 1]; g.lda = width_[l - 1]; g.aBatchCols = ly.inP;
+                g.B = ly.W; g.bBatch = (long long)ly.outP * ly.inP; g.N = ly.outP; g.batch = M_; g.cBatchCols = ly.outP;
+                g.biasBatch = ly.outP;
+            }
+            run_gemm(impl_, g, stream);
+        }
+        const Layer& last = layers_[s][L_ - 1];
+        const int warps = nr * M_;
+        final_energy_kernel<<<(warps * 32 + 255) / 256, 256, 0, stream>>>(act_[L_ - 2] + (size_t)r0 * width_[L_ - 2], width_[L_ - 2], nr, M_,
+                                                                           last.inP, last.W, last.b, energyAcc_);
+        count_launch();
+    }
+    finish_energy_kernel<<<1, 1, 0, stream>>>(energyAcc_, M_, energy);
+    count_launch();
+    NNP_CUDA_CHECK(cudaGetLastError());
+    haveForward_ = true;
+}
+
+void SpeciesMlp::backward(float* featureGrad, cudaStream_t stream) {
+    NNP_REQUIRE(haveForward_, "SpeciesMlp::backward called before forward");
+    for (int s = 0; s < S_; s++) {
+        const int r0 = rowStart_[s], nr = rowStart_[s + 1] - r0;
+        if (nr == 0) continue;
+        {   // seed: gradient w.r.t. the pre-activation of the last hidden layer
+            const Layer& last = layers_[s][L_ - 1];
+            const int l = L_ - 2;
+            const size_t tot = (size_t)nr * M_ * last.inP;
+            backward_seed_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(act_[l] + (size_t)r0 * width_[l], width_[l], nr, M_, last.inP,
+                                                                                    last.W, dz_[l] + (size_t)r0 * width_[l], width_[l]);
+            count_launch();
+        }
+        for (int l = L_ - 2; l >= 1; l--) {   // dZ_{l-1} = (dZ_l . W_l) * celu'(A_{l-1}),  per member
+            const Layer& ly = layers_[s][l];
+            GemmArgs g;
+            std::memset(&g, 0, sizeof(g));
+            g.M = nr; g.N = ly.inP; g.K = ly.outP; g.batch = M_; g.epilogue = 2;
+            g.A = dz_[l] + (size_t)r0 * width_[l]; g.lda = width_[l]; g.aBatchCols = ly.outP;
+            g.B = ly.Wt; g.ldb = ly.outP; g.bBatch = (long long)ly.inP * ly.outP;
+            g.C = dz_[l - 1] + (size_t)r0 * width_[l - 1]; g.ldc = width_[l - 1]; g.cBatchCols = ly.inP;
+            g.act = act_[l - 1] + (size_t)r0 * width_[l - 1]; g.ldact = width_[l - 1]; g.actBatchCols = ly.inP;
+            run_gemm(impl_, g, stream);
+        }
+        {   // dX = dZ_0 . W_0  (sum over ensemble members is part of the contraction: K = M * outP)
+            const Layer& ly = layers_[s][0];
+            GemmArgs g;
+            std::memset(&g, 0, sizeof(g));
+            g.M = nr; g.N = ly.inP; g.K = M_ * ly.outP; g.batch = 1; g.epilogue = 0;
+            g.A = dz_[0] + (size_t)r0 * width_[0]; g.lda = width_[0];
+            g.B = ly.Wt; g.ldb = M_ * ly.outP;
+            g.C = featureGrad + (size_t)r0 * featStride_; g.ldc = featStride_;
+            run_gemm(impl_, g, stream);
+        }
+    }
+    NNP_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace nnpops

@@ -1,0 +1,74 @@
+// Species-grouped per-atom MLP ("BatchedNN" of the reference, src/pytorch/BatchedNN.py:41-111 + BatchedNN.cpp:30-42).
+//
+// The reference replicates the network weights PER ATOM (weights[1, N, M, out, in]) and streams them through a batched
+// mat-vec; here atoms are grouped by species once (the species of a Holder never change) and every layer becomes a real GEMM
+//   Z[n_s x (M*out)] = A[n_s x in] . W^T     (layer 0: all M ensemble members side by side; deeper layers: one GEMM per member)
+// with bias + CELU(0.1) fused in the epilogue.  Backward is the transposed chain with celu' recovered from the saved
+// activations (celu'(z) = 1 for a > 0 else a/alpha + 1), giving dE/dAEV; no parameter gradients (BatchedNN.cpp:40).
+// Zero padding of layer widths to multiples of 64 is exact (celu(0) = 0), exactly like the reference's own padding to
+// the per-layer maximum (BatchedNN.py:71-83).
+#pragma once
+#include <vector>
+#include "common.cuh"
+
+namespace nnpops {
+
+constexpr int kMlpPad = 64;
+constexpr float kCeluAlpha = 0.1f;
+
+enum class MlpImpl : int { Simt = 0, Tcgen05 = 1 };
+
+class SpeciesMlp {
+public:
+    // dims[s][l], l = 0..numLayers: layer l of species s maps dims[s][l] -> dims[s][l+1]; dims[s][0] = numFeatures for all s and
+    // dims[s][numLayers] = 1.  params: for s, for member e, for layer l: W (out x in, row-major) followed by b (out).
+    // rowStart[s]..rowStart[s+1]: rows of species s in the species-sorted feature matrix.
+    SpeciesMlp(int numSpecies, int ensemble, int numLayers, const int* dims, const float* params, const int* rowStart,
+               int featureStride);
+    ~SpeciesMlp();
+    SpeciesMlp(const SpeciesMlp&) = delete;
+    SpeciesMlp& operator=(const SpeciesMlp&) = delete;
+
+    void setImpl(MlpImpl impl) { impl_ = impl; }
+    // features: device [rows][featureStride] fp32 (species-sorted rows, columns >= numFeatures must be zero);
+    // energy: device float[1] = (1/M) sum_atoms sum_members E.
+    void forward(const float* features, float* energy, cudaStream_t stream);
+    // featureGrad: device [rows][featureStride] <- dE/dfeatures (same row order); uses the activations of the last forward
+    void backward(float* featureGrad, cudaStream_t stream);
+
+    int numRows() const { return rows_; }
+    double flopsForward() const { return flopsFwd_; }   // algorithmic (un-padded) flops of one forward pass
+
+private:
+    struct Layer {
+        int in, out;         // true sizes
+        int inP, outP;       // padded sizes
+        float* W = nullptr;  // [M*outP][inP]          (K-major for the forward GEMM)
+        float* Wt = nullptr; // layer 0: [inP][M*outP]; deeper: [M][inP][outP]   (K-major for the backward GEMM)
+        float* b = nullptr;  // [M*outP]
+    };
+    int S_, M_, L_, rows_, featStride_, featP_;
+    std::vector<std::vector<Layer>> layers_;   // [S][L]
+    std::vector<int> rowStart_;
+    std::vector<float*> act_;    // [L-1] activation buffers  [rows][M*maxOutP(l)]
+    std::vector<float*> dz_;     // [L-1] gradient buffers of the same shapes
+    std::vector<int> width_;     // [L-1] M*maxOutP(l)
+    double* energyAcc_ = nullptr;
+    MlpImpl impl_ = MlpImpl::Simt;
+    double flopsFwd_ = 0;
+    bool haveForward_ = false;
+};
+
+// C[m, n] (+epilogue) = sum_k A[m, k] * B[n, k];  batched over blockIdx.z with column/row offsets.  fp32 SIMT version.
+struct GemmArgs {
+    const float* A; int lda; int aBatchCols;     // A + batch*aBatchCols
+    const float* B; int ldb; long long bBatch;   // B + batch*bBatch (elements)
+    float* C; int ldc; int cBatchCols;
+    const float* bias; int biasBatch;            // epilogue 1: bias[batch*biasBatch + n]
+    const float* act; int ldact; int actBatchCols;   // epilogue 2: multiply by celu'(act[m, batch*actBatchCols + n])
+    int M, N, K, batch;
+    int epilogue;                                // 0 plain, 1 bias + celu, 2 times celu'(act)
+};
+void launch_gemm_simt(const GemmArgs& a, cudaStream_t stream);
+
+}  // namespace nnpops
