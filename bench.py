@@ -28,7 +28,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "ANI-2x energy+force evals/sec on 50k-atom box"
 UNIT = "evals/s"
-DEFAULT_MLP = "simt"   # switched to "tcgen05" once the tensor-core GEMM is parity-green
+DEFAULT_MLP = "tcgen05"   # "simt" selects the fp32 validation GEMM
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # derived SIMT peak at max clock
 
 
@@ -250,7 +250,7 @@ def _cpu_eval(n_atoms, seed):
 def _scale_model(n_full):
     """Fit t(N) = a N^2 + b N from two small sizes (the reference scans all pairs) and return (a, b, kind)."""
     import oracle_lib as O
-    n1, n2 = 3000, 6000
+    n1, n2 = 5000, 15000
     t1, t2 = _cpu_eval(n1, 9001), _cpu_eval(n2, 9002)
     a = (t2 / n2 - t1 / n1) / (n2 - n1)
     b = t1 / n1 - a * n1
@@ -286,7 +286,7 @@ def run_reference(args):
     import oracle_lib as O
     O.build()
     cores = os.cpu_count() or 1
-    n_s = 6000
+    n_s = 10000
     a, b, kind = _scale_model(args.atoms)
     scale = (a * args.atoms ** 2 + b * args.atoms) / (a * n_s ** 2 + b * n_s)
     ctx = mp.get_context("fork")

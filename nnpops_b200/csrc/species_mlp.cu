@@ -6,7 +6,6 @@
 
 namespace nnpops {
 
-void launch_gemm_tcgen05(const GemmArgs& a, cudaStream_t stream);   // mlp_tcgen05.cu
 
 namespace {
 
@@ -111,6 +110,62 @@ __global__ void backward_seed_kernel(const float* __restrict__ act, int ld, int 
     dz[(size_t)r * lddz + c] = (w[c] * (1.0f / M)) * celu_grad_from_act(act[(size_t)r * ld + c]);
 }
 
+constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
+constexpr float kGradScale = 1024.0f;   // power-of-two lift of the backward chain into fp16's comfortable range (exact)
+
+__device__ __forceinline__ void split_h(float v, __half& hi, __half& lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn((v - __half2float(hi)) * kLoScale);
+}
+__device__ __forceinline__ float join_h(__half hi, __half lo) { return fmaf(__half2float(lo), kLoInv, __half2float(hi)); }
+
+// fp32 [rows][ld] -> hi/lo fp16 pairs, 8 elements per thread
+__global__ void split_rows_kernel(const float* __restrict__ src, size_t n8, __half* __restrict__ hi, __half* __restrict__ lo) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    const float4 a = reinterpret_cast<const float4*>(src)[2 * i], b = reinterpret_cast<const float4*>(src)[2 * i + 1];
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint4 ph, pl;
+    __half* hh = reinterpret_cast<__half*>(&ph);
+    __half* hl = reinterpret_cast<__half*>(&pl);
+#pragma unroll
+    for (int k = 0; k < 8; k++) split_h(v[k], hh[k], hl[k]);
+    reinterpret_cast<uint4*>(hi)[i] = ph;
+    reinterpret_cast<uint4*>(lo)[i] = pl;
+}
+
+__global__ void final_energy_h_kernel(const __half* __restrict__ actHi, const __half* __restrict__ actLo, int ld, int rows, int M, int hP,
+                                      const float* __restrict__ w, const float* __restrict__ b, double* __restrict__ acc) {
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    float s = 0.0f;
+    if (gw < rows * M) {
+        const int r = gw / M, e = gw % M;
+        const size_t o = (size_t)r * ld + (size_t)e * hP;
+        for (int c = lane; c < hP; c += 32) s = fmaf(join_h(actHi[o + c], actLo[o + c]), w[e * hP + c], s);
+        s = warp_sum(s);
+        if (lane == 0) s += b[e];
+    }
+    __shared__ double part[32];
+    if (lane == 0) part[threadIdx.x >> 5] = (gw < rows * M) ? (double)s : 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += part[i];
+        atomicAdd(acc, t);
+    }
+}
+
+__global__ void backward_seed_h_kernel(const __half* __restrict__ actHi, const __half* __restrict__ actLo, int ld, int rows, int M, int hP,
+                                       const float* __restrict__ w, __half* __restrict__ dzHi, __half* __restrict__ dzLo, int lddz) {
+    const int width = M * hP;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)rows * width) return;
+    const int r = (int)(idx / width), c = (int)(idx % width);
+    const float a = join_h(actHi[(size_t)r * ld + c], actLo[(size_t)r * ld + c]);
+    const float v = (w[c] * (kGradScale / M)) * celu_grad_from_act(a);
+    split_h(v, dzHi[(size_t)r * lddz + c], dzLo[(size_t)r * lddz + c]);
+}
+
 }  // namespace
 
 void launch_gemm_simt(const GemmArgs& a, cudaStream_t stream) {
@@ -199,19 +254,139 @@ SpeciesMlp::SpeciesMlp(int numSpecies, int ensemble, int numLayers, const int* d
 
 SpeciesMlp::~SpeciesMlp() {
     for (auto& sp : layers_)
-        for (auto& ly : sp) { cudaFree(ly.W); cudaFree(ly.Wt); cudaFree(ly.b); }
+        for (auto& ly : sp) {
+            cudaFree(ly.W); cudaFree(ly.Wt); cudaFree(ly.b);
+            cudaFree(ly.Whi); cudaFree(ly.Wlo); cudaFree(ly.Wthi); cudaFree(ly.Wtlo);
+        }
+    for (auto* v : {&actHi_, &actLo_, &dzHi_, &dzLo_})
+        for (__half* p : *v) cudaFree(p);
+    cudaFree(featHi_); cudaFree(featLo_);
     for (float* p : act_) cudaFree(p);
     for (float* p : dz_) cudaFree(p);
     cudaFree(energyAcc_);
 }
 
-static void run_gemm(MlpImpl impl, const GemmArgs& a, cudaStream_t stream) {
-    if (impl == MlpImpl::Tcgen05) launch_gemm_tcgen05(a, stream);
-    else launch_gemm_simt(a, stream);
+static void to_split_device(const float* src, size_t count, __half** hi, __half** lo) {
+    NNP_REQUIRE(count % 8 == 0, "split: element count must be a multiple of 8");
+    NNP_CUDA_CHECK(cudaMalloc(hi, sizeof(__half) * count));
+    NNP_CUDA_CHECK(cudaMalloc(lo, sizeof(__half) * count));
+    split_rows_kernel<<<(unsigned)((count / 8 + 255) / 256), 256>>>(src, count / 8, *hi, *lo);
+    NNP_CUDA_CHECK(cudaGetLastError());
+}
+
+void SpeciesMlp::setImpl(MlpImpl impl) {
+    impl_ = impl;
+    if (impl != MlpImpl::Tcgen05 || featHi_ != nullptr) return;
+    // one-time preparation of the tensor-core representation: weights and work buffers as fp16 hi/lo pairs
+    for (int s = 0; s < S_; s++)
+        for (int l = 0; l < L_ - 1; l++) {
+            Layer& ly = layers_[s][l];
+            const size_t cnt = (size_t)M_ * ly.outP * ly.inP;
+            to_split_device(ly.W, cnt, &ly.Whi, &ly.Wlo);
+            to_split_device(ly.Wt, cnt, &ly.Wthi, &ly.Wtlo);
+        }
+    const size_t nr = (size_t)std::max(rows_, 1);
+    actHi_.assign(L_ - 1, nullptr); actLo_.assign(L_ - 1, nullptr); dzHi_.assign(L_ - 1, nullptr); dzLo_.assign(L_ - 1, nullptr);
+    for (int l = 0; l < L_ - 1; l++) {
+        for (__half** p : {&actHi_[l], &actLo_[l], &dzHi_[l], &dzLo_[l]}) {
+            NNP_CUDA_CHECK(cudaMalloc(p, sizeof(__half) * nr * width_[l]));
+            NNP_CUDA_CHECK(cudaMemset(*p, 0, sizeof(__half) * nr * width_[l]));
+        }
+    }
+    NNP_CUDA_CHECK(cudaMalloc(&featHi_, sizeof(__half) * nr * featStride_));
+    NNP_CUDA_CHECK(cudaMalloc(&featLo_, sizeof(__half) * nr * featStride_));
+    NNP_CUDA_CHECK(cudaDeviceSynchronize());
+    // the fp32 activation buffers of the validation path are not needed any more
+    for (float*& p : act_) { cudaFree(p); p = nullptr; }
+    for (float*& p : dz_) { cudaFree(p); p = nullptr; }
+}
+
+void SpeciesMlp::forwardTc(const float* features, float* energy, cudaStream_t stream) {
+    NNP_REQUIRE(featStride_ % 8 == 0, "feature stride must be a multiple of 8");
+    if (rows_ > 0) {
+        const size_t n8 = (size_t)rows_ * featStride_ / 8;
+        split_rows_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>(features, n8, featHi_, featLo_);
+        count_launch();
+    }
+    for (int s = 0; s < S_; s++) {
+        const int r0 = rowStart_[s], nr = rowStart_[s + 1] - r0;
+        if (nr == 0) continue;
+        for (int l = 0; l < L_ - 1; l++) {
+            const Layer& ly = layers_[s][l];
+            GemmArgsH g;
+            std::memset(&g, 0, sizeof(g));
+            g.M = nr; g.epilogue = 1; g.bias = ly.b; g.K = ly.inP; g.outScale = 1.0f;
+            g.Bhi = ly.Whi; g.Blo = ly.Wlo; g.ldb = ly.inP; g.bRows = M_ * ly.outP;
+            g.Chi = actHi_[l] + (size_t)r0 * width_[l]; g.Clo = actLo_[l] + (size_t)r0 * width_[l]; g.ldc = width_[l];
+            if (l == 0) {
+                g.Ahi = featHi_ + (size_t)r0 * featStride_; g.Alo = featLo_ + (size_t)r0 * featStride_; g.lda = featStride_;
+                g.aCols = featStride_; g.aBatchCols = 0; g.bBatchRows = 0; g.N = M_ * ly.outP; g.batch = 1; g.cBatchCols = 0; g.biasBatch = 0;
+            } else {
+                g.Ahi = actHi_[l - 1] + (size_t)r0 * width_[l - 1]; g.Alo = actLo_[l - 1] + (size_t)r0 * width_[l - 1];
+                g.lda = width_[l - 1]; g.aCols = width_[l - 1]; g.aBatchCols = ly.inP; g.bBatchRows = ly.outP; g.N = ly.outP; g.batch = M_;
+                g.cBatchCols = ly.outP; g.biasBatch = ly.outP;
+            }
+            launch_gemm_tcgen05(g, stream);
+        }
+        const Layer& last = layers_[s][L_ - 1];
+        const int warps = nr * M_;
+        final_energy_h_kernel<<<(warps * 32 + 255) / 256, 256, 0, stream>>>(actHi_[L_ - 2] + (size_t)r0 * width_[L_ - 2],
+                                                                             actLo_[L_ - 2] + (size_t)r0 * width_[L_ - 2], width_[L_ - 2], nr, M_,
+                                                                             last.inP, last.W, last.b, energyAcc_);
+        count_launch();
+    }
+}
+
+void SpeciesMlp::backwardTc(float* featureGrad, cudaStream_t stream) {
+    for (int s = 0; s < S_; s++) {
+        const int r0 = rowStart_[s], nr = rowStart_[s + 1] - r0;
+        if (nr == 0) continue;
+        {
+            const Layer& last = layers_[s][L_ - 1];
+            const int l = L_ - 2;
+            const size_t tot = (size_t)nr * M_ * last.inP;
+            backward_seed_h_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(
+                actHi_[l] + (size_t)r0 * width_[l], actLo_[l] + (size_t)r0 * width_[l], width_[l], nr, M_, last.inP, last.W,
+                dzHi_[l] + (size_t)r0 * width_[l], dzLo_[l] + (size_t)r0 * width_[l], width_[l]);
+            count_launch();
+        }
+        for (int l = L_ - 2; l >= 1; l--) {
+            const Layer& ly = layers_[s][l];
+            GemmArgsH g;
+            std::memset(&g, 0, sizeof(g));
+            g.M = nr; g.N = ly.inP; g.K = ly.outP; g.batch = M_; g.epilogue = 2; g.outScale = 1.0f;
+            g.Ahi = dzHi_[l] + (size_t)r0 * width_[l]; g.Alo = dzLo_[l] + (size_t)r0 * width_[l]; g.lda = width_[l]; g.aCols = width_[l];
+            g.aBatchCols = ly.outP;
+            g.Bhi = ly.Wthi; g.Blo = ly.Wtlo; g.ldb = ly.outP; g.bRows = M_ * ly.inP; g.bBatchRows = ly.inP;
+            g.Chi = dzHi_[l - 1] + (size_t)r0 * width_[l - 1]; g.Clo = dzLo_[l - 1] + (size_t)r0 * width_[l - 1]; g.ldc = width_[l - 1];
+            g.cBatchCols = ly.inP;
+            g.actHi = actHi_[l - 1] + (size_t)r0 * width_[l - 1]; g.actLo = actLo_[l - 1] + (size_t)r0 * width_[l - 1];
+            g.ldact = width_[l - 1]; g.actBatchCols = ly.inP;
+            launch_gemm_tcgen05(g, stream);
+        }
+        {
+            const Layer& ly = layers_[s][0];
+            GemmArgsH g;
+            std::memset(&g, 0, sizeof(g));
+            g.M = nr; g.N = ly.inP; g.K = M_ * ly.outP; g.batch = 1; g.epilogue = 0; g.outScale = 1.0f / kGradScale;
+            g.Ahi = dzHi_[0] + (size_t)r0 * width_[0]; g.Alo = dzLo_[0] + (size_t)r0 * width_[0]; g.lda = width_[0]; g.aCols = width_[0];
+            g.Bhi = ly.Wthi; g.Blo = ly.Wtlo; g.ldb = M_ * ly.outP; g.bRows = ly.inP;
+            g.C32 = featureGrad + (size_t)r0 * featStride_; g.ldc = featStride_;
+            launch_gemm_tcgen05(g, stream);
+        }
+    }
 }
 
 void SpeciesMlp::forward(const float* features, float* energy, cudaStream_t stream) {
     NNP_CUDA_CHECK(cudaMemsetAsync(energyAcc_, 0, sizeof(double), stream));
+    if (impl_ == MlpImpl::Tcgen05) {
+        forwardTc(features, energy, stream);
+        finish_energy_kernel<<<1, 1, 0, stream>>>(energyAcc_, M_, energy);
+        count_launch();
+        NNP_CUDA_CHECK(cudaGetLastError());
+        haveForward_ = true;
+        return;
+    }
     for (int s = 0; s < S_; s++) {
         const int r0 = rowStart_[s], nr = rowStart_[s + 1] - r0;
         if (nr == 0) continue;
@@ -229,7 +404,7 @@ void SpeciesMlp::forward(const float* features, float* energy, cudaStream_t stre
                 g.B = ly.W; g.bBatch = (long long)ly.outP * ly.inP; g.N = ly.outP; g.batch = M_; g.cBatchCols = ly.outP;
                 g.biasBatch = ly.outP;
             }
-            run_gemm(impl_, g, stream);
+            launch_gemm_simt(g, stream);
         }
         const Layer& last = layers_[s][L_ - 1];
         const int warps = nr * M_;
@@ -245,6 +420,11 @@ void SpeciesMlp::forward(const float* features, float* energy, cudaStream_t stre
 
 void SpeciesMlp::backward(float* featureGrad, cudaStream_t stream) {
     NNP_REQUIRE(haveForward_, "SpeciesMlp::backward called before forward");
+    if (impl_ == MlpImpl::Tcgen05) {
+        backwardTc(featureGrad, stream);
+        NNP_CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     for (int s = 0; s < S_; s++) {
         const int r0 = rowStart_[s], nr = rowStart_[s + 1] - r0;
         if (nr == 0) continue;
@@ -265,7 +445,7 @@ void SpeciesMlp::backward(float* featureGrad, cudaStream_t stream) {
             g.B = ly.Wt; g.ldb = ly.outP; g.bBatch = (long long)ly.inP * ly.outP;
             g.C = dz_[l - 1] + (size_t)r0 * width_[l - 1]; g.ldc = width_[l - 1]; g.cBatchCols = ly.inP;
             g.act = act_[l - 1] + (size_t)r0 * width_[l - 1]; g.ldact = width_[l - 1]; g.actBatchCols = ly.inP;
-            run_gemm(impl_, g, stream);
+            launch_gemm_simt(g, stream);
         }
         {   // dX = dZ_0 . W_0  (sum over ensemble members is part of the contraction: K = M * outP)
             const Layer& ly = layers_[s][0];
@@ -275,7 +455,7 @@ void SpeciesMlp::backward(float* featureGrad, cudaStream_t stream) {
             g.A = dz_[0] + (size_t)r0 * width_[0]; g.lda = width_[0];
             g.B = ly.Wt; g.ldb = M_ * ly.outP;
             g.C = featureGrad + (size_t)r0 * featStride_; g.ldc = featStride_;
-            run_gemm(impl_, g, stream);
+            launch_gemm_simt(g, stream);
         }
     }
     NNP_CUDA_CHECK(cudaGetLastError());

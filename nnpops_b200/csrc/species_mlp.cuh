@@ -8,6 +8,7 @@
 // Zero padding of layer widths to multiples of 64 is exact (celu(0) = 0), exactly like the reference's own padding to
 // the per-layer maximum (BatchedNN.py:71-83).
 #pragma once
+#include <cuda_fp16.h>
 #include <vector>
 #include "common.cuh"
 
@@ -29,7 +30,7 @@ public:
     SpeciesMlp(const SpeciesMlp&) = delete;
     SpeciesMlp& operator=(const SpeciesMlp&) = delete;
 
-    void setImpl(MlpImpl impl) { impl_ = impl; }
+    void setImpl(MlpImpl impl);
     // features: device [rows][featureStride] fp32 (species-sorted rows, columns >= numFeatures must be zero);
     // energy: device float[1] = (1/M) sum_atoms sum_members E.
     void forward(const float* features, float* energy, cudaStream_t stream);
@@ -46,6 +47,7 @@ private:
         float* W = nullptr;  // [M*outP][inP]          (K-major for the forward GEMM)
         float* Wt = nullptr; // layer 0: [inP][M*outP]; deeper: [M][inP][outP]   (K-major for the backward GEMM)
         float* b = nullptr;  // [M*outP]
+        __half *Whi = nullptr, *Wlo = nullptr, *Wthi = nullptr, *Wtlo = nullptr;   // fp16 hi/lo pairs of W and Wt (tensor-core path)
     };
     int S_, M_, L_, rows_, featStride_, featP_;
     std::vector<std::vector<Layer>> layers_;   // [S][L]
@@ -53,6 +55,11 @@ private:
     std::vector<float*> act_;    // [L-1] activation buffers  [rows][M*maxOutP(l)]
     std::vector<float*> dz_;     // [L-1] gradient buffers of the same shapes
     std::vector<int> width_;     // [L-1] M*maxOutP(l)
+    // tensor-core path: every matrix lives as an fp16 hi/lo pair
+    std::vector<__half*> actHi_, actLo_, dzHi_, dzLo_;
+    __half *featHi_ = nullptr, *featLo_ = nullptr;
+    void forwardTc(const float* features, float* energy, cudaStream_t stream);
+    void backwardTc(float* featureGrad, cudaStream_t stream);
     double* energyAcc_ = nullptr;
     MlpImpl impl_ = MlpImpl::Simt;
     double flopsFwd_ = 0;
@@ -70,5 +77,18 @@ struct GemmArgs {
     int epilogue;                                // 0 plain, 1 bias + celu, 2 times celu'(act)
 };
 void launch_gemm_simt(const GemmArgs& a, cudaStream_t stream);
+
+// Same contraction on the tensor cores with operands stored as fp16 hi/lo pairs (see mlp_tcgen05.cu).
+struct GemmArgsH {
+    const __half* Ahi; const __half* Alo; int lda; int aCols; int aBatchCols;      // A: [M][lda], batch b reads columns b*aBatchCols + k
+    const __half* Bhi; const __half* Blo; int ldb; int bRows; int bBatchRows;      // B: [bRows][ldb], batch b reads rows b*bBatchRows + n
+    __half* Chi; __half* Clo; float* C32; int ldc; int cBatchCols;
+    const float* bias; int biasBatch;
+    const __half* actHi; const __half* actLo; int ldact; int actBatchCols;
+    float outScale;
+    int M, N, K, batch;
+    int epilogue;                                // 0 fp32 out * outScale, 1 bias + celu -> hi/lo, 2 times celu'(act) -> hi/lo
+};
+void launch_gemm_tcgen05(const GemmArgsH& a, cudaStream_t stream);
 
 }  // namespace nnpops

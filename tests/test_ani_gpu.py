@@ -34,7 +34,7 @@ def run_aev(pos, species, n_species, rcr, rca, rfn, afn, box, torchani=True, gra
     from nnpops_b200.SymmetryFunctions import Holder
     h = Holder.from_function_lists(n_species, rcr, rca, rfn, afn, list(species), torchani=torchani)
     p = dev(pos)
-    b = dev(box) if box is not None else None
+    b = dev(np.asarray(box, np.float32).reshape(3, 3)) if box is not None else None
     radial, angular = h.forward(p, b)
     out = [radial.cpu().numpy(), angular.cpu().numpy()]
     if grads is not None:
@@ -201,7 +201,8 @@ def test_fused_host_entry_point_matches_device_path():
     e, g = m.energy_and_gradient(dev(pos), dev(box))
     eh = np.zeros(1, np.float32); gh = np.zeros((len(pos), 3), np.float32)
     m.energy_and_gradient_host(np.ascontiguousarray(pos), np.ascontiguousarray(box), eh, gh)
-    assert np.array_equal(gh, g.cpu().numpy()) and eh[0] == float(e.cpu()[0])
+    # the angular backward accumulates neighbour forces with float atomics, so two runs agree to round-off, not bit for bit
+    assert rel_err(gh, g.cpu().numpy()) < 1e-6 and abs(eh[0] - float(e.cpu()[0])) <= 1e-6 * abs(eh[0])
 
 
 def test_translation_and_linearity_properties_at_scale():
