@@ -9,6 +9,7 @@
 // and :228-353 (backward).  cos(theta - thetas) is evaluated as c*cos(thetas) + sqrt(1-c^2)*sin(thetas) instead of through
 // acosf/cosf, and a^zeta as ex2(zeta*lg2(a)).
 #include "ani_aev.cuh"
+#include <cuda_fp16.h>
 #include <cmath>
 #include <cstring>
 
@@ -21,6 +22,22 @@ constexpr int kWPB = 8;   // warps (= centre atoms) per CTA
 __device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2a(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rsqrta(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// One AEV element: fp32, or the fp16 hi/lo pair consumed by the tensor-core MLP (hi = fp16(v), lo = fp16((v - hi) * 2^11))
+struct AevOut {
+    float* f32;
+    __half* hi;
+    __half* lo;
+};
+__device__ __forceinline__ void store_aev(const AevOut& o, size_t idx, float v) {
+    if (o.hi) {
+        const __half h = __float2half_rn(v);
+        o.hi[idx] = h;
+        o.lo[idx] = __float2half_rn((v - __half2float(h)) * 2048.0f);
+    } else {
+        o.f32[idx] = v;
+    }
+}
 
 __device__ __forceinline__ int pair_index(int S, int s, int t) {   // CpuANISymmetryFunctions.cpp:39-43
     int lo = min(s, t), hi = max(s, t);
@@ -132,7 +149,7 @@ ani_rows_kernel(int n, const float4* __restrict__ sorted, const int* __restrict_
 __global__ void __launch_bounds__(kWPB * 32)
 ani_radial_fwd_kernel(int n, const float4* __restrict__ sorted, const int* __restrict__ sortedOrig, const Geom* __restrict__ geom,
                       const AniTables* __restrict__ tab, const int* __restrict__ rowRad, const int* __restrict__ offRad, int capR,
-                      const int* __restrict__ rowMap, float* __restrict__ out, int stride) {
+                      const int* __restrict__ rowMap, AevOut out, int stride) {
     extern __shared__ unsigned char smemRaw[];
     __shared__ Geom g;
     __shared__ float sEtaL2[kAniMaxRadial], sShf[kAniMaxRadial];
@@ -159,7 +176,7 @@ ani_radial_fwd_kernel(int n, const float4* __restrict__ sorted, const int* __res
     }
     __syncwarp();
     const int orig = sortedOrig[p];
-    float* orow = out + (size_t)(rowMap ? rowMap[orig] : orig) * stride;
+    const size_t orow = (size_t)(rowMap ? rowMap[orig] : orig) * stride;
     const float scale = tab->radialScale;
     for (int k0 = 0; k0 < nR; k0 += 32) {
         const int kk = min(nR - k0, 32);
@@ -176,7 +193,7 @@ ani_radial_fwd_kernel(int n, const float4* __restrict__ sorted, const int* __res
                 acc = fmaf(sfc[q], ex2a(-eta2 * t * t), acc);
             }
             for (int o = KP; o < 32; o <<= 1) acc += __shfl_xor_sync(kFull, acc, o);
-            if (h == 0 && kval) orow[s * nR + k0 + k] = acc * scale;
+            if (h == 0 && kval) store_aev(out, orow + s * nR + k0 + k, acc * scale);
         }
     }
 }
@@ -221,7 +238,7 @@ template <int MODE, int NSA, int NSZ, bool TORCHANI>
 __global__ void __launch_bounds__(kWPB * 32)
 ani_angular_fwd_kernel(int n, const float4* __restrict__ sorted, const int* __restrict__ sortedOrig, const Geom* __restrict__ geom,
                        const AniTables* __restrict__ tab, const int* __restrict__ rowAng, const int* __restrict__ offAng, int capA,
-                       const int* __restrict__ rowMap, float* __restrict__ out, int stride) {
+                       const int* __restrict__ rowMap, AevOut out, int stride) {
     extern __shared__ unsigned char smemRaw[];
     __shared__ Geom g;
     __shared__ AngTablesSmem T;
@@ -249,7 +266,7 @@ ani_angular_fwd_kernel(int n, const float4* __restrict__ sorted, const int* __re
     }
     __syncwarp();
     const int orig = sortedOrig[p];
-    float* orow = out + (size_t)(rowMap ? rowMap[orig] : orig) * stride;
+    const size_t orow = (size_t)(rowMap ? rowMap[orig] : orig) * stride;
     const float cosScale = tab->cosScale;
     const float fEtaL2 = tab->fEtaL2, fZeta = tab->fZeta, fScale = tab->fScale;
 
@@ -260,9 +277,9 @@ ani_angular_fwd_kernel(int n, const float4* __restrict__ sorted, const int* __re
             for (int t = s; t < S; t++, pIdx++) {
                 const int bt = off[t], nt = min(off[t + 1], capA) - bt;
                 const int ntrip = (s == t) ? (ns * (ns - 1)) / 2 : ns * nt;
-                float* dst = orow + pIdx * nA + m0;
+                const size_t dst = orow + pIdx * nA + m0;
                 if (ntrip <= 0) {
-                    if (m0 + lane < nA) dst[lane] = 0.0f;
+                    if (m0 + lane < nA) store_aev(out, dst + lane, 0.0f);
                     continue;
                 }
                 float acc[32];
@@ -322,7 +339,7 @@ ani_angular_fwd_kernel(int n, const float4* __restrict__ sorted, const int* __re
                     }
                 }
                 const float v = transpose_reduce32(acc, lane);
-                if (m0 + lane < nA) dst[lane] = v * (MODE == 1 ? fScale : T.scale[m0 + lane]);
+                if (m0 + lane < nA) store_aev(out, dst + lane, v * (MODE == 1 ? fScale : T.scale[m0 + lane]));
             }
         }
     }
@@ -696,8 +713,11 @@ AniAev::~AniAev() {
     } while (0)
 
 void AniAev::forward(const float* positions, const float* box, float* radial, int radialStride, float* angular, int angularStride,
-                     cudaStream_t stream, cudaEvent_t* ev) {
+                     cudaStream_t stream, cudaEvent_t* ev, __half* splitHi, __half* splitLo) {
     if (n_ == 0) return;
+    // split output: one [n][radialStride] matrix pair, radial block first (radial/angular then only carry the column offsets)
+    const AevOut radialOut = {radial, splitHi, splitLo};
+    const AevOut angularOut = {angular, splitHi ? splitHi + radialWidth() : nullptr, splitLo ? splitLo + radialWidth() : nullptr};
     cells_.build<float>(positions, box, species_, tabHost_.rcr > tabHost_.rca ? tabHost_.rcr : tabHost_.rca, stream);
     const int grid = (n_ + kWPB - 1) / kWPB;
     {
@@ -712,14 +732,14 @@ void AniAev::forward(const float* positions, const float* box, float* radial, in
         const size_t smem = (size_t)kWPB * 2 * capR_ * sizeof(float);
         set_smem(ani_radial_fwd_kernel, smem);
         ani_radial_fwd_kernel<<<grid, kWPB * 32, smem, stream>>>(n_, cells_.sorted, cells_.sortedOrig, cells_.geom, tab_, rowRad_, offRad_,
-                                                                 capR_, rowMap_, radial, radialStride);
+                                                                 capR_, rowMap_, radialOut, radialStride);
         count_launch();
     }
     if (ev) cudaEventRecord(ev[1], stream);
     if (tabHost_.nAngular > 0) {
         const size_t smem = (size_t)kWPB * 6 * capA_ * sizeof(float);
         ANI_DISPATCH(ani_angular_fwd_kernel, n_, cells_.sorted, cells_.sortedOrig, cells_.geom, tab_, rowAng_, offAng_, capA_, rowMap_,
-                     angular, angularStride);
+                     angularOut, angularStride);
         count_launch();
     }
     NNP_CUDA_CHECK(cudaGetLastError());

@@ -2,6 +2,7 @@
 // CudaANISymmetryFunctions (src/ani/CudaANISymmetryFunctions.cu:186-670, kernels K1-K5 of SURVEY.md section 2.3) behind the same
 // contract as the abstract class ANISymmetryFunctions (src/ani/ANISymmetryFunctions.h:29-154).
 #pragma once
+#include <cuda_fp16.h>
 #include <vector>
 #include "cell_list.cuh"
 
@@ -46,8 +47,10 @@ public:
     // positions [n][3], box [3][3] or nullptr (all device, fp32).  radial/angular: device, row strides in floats.
     // ev (optional): forward records ev[0] after the neighbour rows and ev[1] after the radial kernel; backward records ev[0]
     // after the radial kernel -- used by the benchmark to time each kernel on the launching stream.
+    // splitHi/splitLo (optional): write the AEV as fp16 hi/lo pairs into one [n][radialStride] matrix pair (radial block first,
+    // angular block at column radialWidth()) instead of fp32 -- the operand format of the tensor-core MLP.
     void forward(const float* positions, const float* box, float* radial, int radialStride, float* angular, int angularStride,
-                 cudaStream_t stream, cudaEvent_t* ev = nullptr);
+                 cudaStream_t stream, cudaEvent_t* ev = nullptr, __half* splitHi = nullptr, __half* splitLo = nullptr);
     // uses the positions/box of the most recent forward (ANISymmetryFunctions.h:83-84)
     void backward(const float* radialGrad, int radialStride, const float* angularGrad, int angularStride, float* positionGrad,
                   cudaStream_t stream, cudaEvent_t* ev = nullptr);

@@ -3,19 +3,22 @@
 namespace nnpops {
 
 namespace {
-__global__ void gather_rows_kernel(const float* __restrict__ src, int stride, const int* __restrict__ rowMap, int n, int width,
-                                   float* __restrict__ out) {
+__global__ void gather_rows_kernel(const float* __restrict__ src, const __half* __restrict__ hi, const __half* __restrict__ lo, int stride,
+                                   const int* __restrict__ rowMap, int n, int width, float* __restrict__ out) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)n * width) return;
     const int i = (int)(idx / width), c = (int)(idx % width);
-    out[idx] = src[(size_t)rowMap[i] * stride + c];
+    const size_t o = (size_t)rowMap[i] * stride + c;
+    out[idx] = hi ? fmaf(__half2float(lo[o]), 1.0f / 2048.0f, __half2float(hi[o])) : src[o];
 }
 }  // namespace
 
 void AniModel::readFeatures(int which, float* out, cudaStream_t stream) {
     if (n_ == 0) return;
     const size_t tot = (size_t)n_ * nFeat_;
-    gather_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(which == 0 ? feat_ : featGrad_, stride_, rowMap_, n_, nFeat_, out);
+    const bool split = which == 0 && mlp_->tensorCore();
+    gather_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(which == 0 ? feat_ : featGrad_, split ? mlp_->featHi() : nullptr,
+                                                                          split ? mlp_->featLo() : nullptr, stride_, rowMap_, n_, nFeat_, out);
     NNP_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -57,9 +60,11 @@ void AniModel::energyAndGradient(const float* positions, const float* box, float
     cudaEvent_t* ev = nullptr;
     if (timingUsed_ < timingCap_) ev = events_.data() + (size_t)(timingUsed_++) * (kStages + 1);
     if (ev) cudaEventRecord(ev[0], stream);
-    aev_->forward(positions, box, feat_, stride_, feat_ + rw, stride_, stream, ev ? ev + 1 : nullptr);   // ev[1], ev[2]
+    const bool tc = mlp_->tensorCore();   // the AEV kernels then write the fp16 hi/lo operand pair of the MLP directly
+    aev_->forward(positions, box, feat_, stride_, feat_ + rw, stride_, stream, ev ? ev + 1 : nullptr,   // ev[1], ev[2]
+                  tc ? mlp_->featHi() : nullptr, tc ? mlp_->featLo() : nullptr);
     if (ev) cudaEventRecord(ev[3], stream);
-    mlp_->forward(feat_, energy, stream);
+    mlp_->forward(tc ? nullptr : feat_, energy, stream);
     if (ev) cudaEventRecord(ev[4], stream);
     mlp_->backward(featGrad_, stream);
     if (ev) cudaEventRecord(ev[5], stream);

@@ -115,6 +115,7 @@ struct TcArgs {
     const float* bias; int biasBatch;
     const __half* actHi; const __half* actLo; int ldact; int actBatchCols;
     float outScale;
+    const float* w3; double* energyAcc; float seedScale;
 };
 
 __global__ void __launch_bounds__(256, 1)
@@ -214,6 +215,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
         for (int t = blockIdx.x; t < numTiles; t += gridDim.x) {
             const int nt = t % tilesN, mt = (t / tilesN) % tilesM, z = t / (tilesN * tilesM);
             const int m = mt * TBM + q * 32 + lane, n0 = nt * TBN;
+            float esum = 0.0f;
             mbar_wait(accFullBar(acc), accPhase);
             tc_fence_after();
             const uint32_t tbase = tmemBase + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * TBN);
@@ -240,6 +242,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
                             const float* bp = g.bias + (size_t)z * g.biasBatch + n;
 #pragma unroll
                             for (int j = 0; j < 32; j++) v[j] = celu_f(v[j] + __ldg(bp + j));
+                        } else if (g.mode == 3) {
+                            const float* bp = g.bias + (size_t)z * g.biasBatch + n;
+                            const float* wp = g.w3 + (size_t)z * g.biasBatch + n;
+#pragma unroll
+                            for (int j = 0; j < 32; j++) {
+                                const float a = celu_f(v[j] + __ldg(bp + j));
+                                const float wv = __ldg(wp + j);
+                                esum = fmaf(a, wv, esum);
+                                v[j] = g.seedScale * wv * celu_grad_from_act_f(a);
+                            }
                         } else {
                             const size_t ao = (size_t)m * g.ldact + (size_t)z * g.actBatchCols + n;
 #pragma unroll
@@ -272,6 +284,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(accEmptyBar(acc));
+            if (g.mode == 3) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
+                if (lane == 0) atomicAdd(g.energyAcc, (double)esum);
+            }
             if (++acc == kAccStages) { acc = 0; accPhase ^= 1u; }
         }
     }
@@ -346,6 +363,7 @@ void launch_gemm_tcgen05(const GemmArgsH& a, cudaStream_t stream) {
     g.M = a.M; g.N = a.N; g.K = a.K; g.batch = a.batch; g.aBatchCols = a.aBatchCols; g.bBatchRows = a.bBatchRows; g.mode = a.epilogue;
     g.Chi = a.Chi; g.Clo = a.Clo; g.C32 = a.C32; g.ldc = a.ldc; g.cBatchCols = a.cBatchCols; g.bias = a.bias; g.biasBatch = a.biasBatch;
     g.actHi = a.actHi; g.actLo = a.actLo; g.ldact = a.ldact; g.actBatchCols = a.actBatchCols; g.outScale = a.outScale;
+    g.w3 = a.w3; g.energyAcc = a.energyAcc; g.seedScale = a.seedScale;
     const int tiles = ((a.M + TBM - 1) / TBM) * ((a.N + TBN - 1) / TBN) * a.batch;
     const int grid = tiles < num_sms() ? tiles : num_sms();
     gemm_tcgen05_kernel<<<grid, 256, kSmemBytes, stream>>>(mAhi, mAlo, mBhi, mBlo, g);

@@ -98,7 +98,9 @@ __global__ void final_energy_kernel(const float* __restrict__ act, int ld, int r
     }
 }
 
-__global__ void finish_energy_kernel(const double* __restrict__ acc, int M, float* __restrict__ energy) { *energy = (float)(*acc / M); }
+__global__ void finish_energy_kernel(const double* __restrict__ acc, double bias, int M, float* __restrict__ energy) {
+    *energy = (float)((*acc + bias) / M);
+}
 
 // dZ[r, e*hP + c] = (w[e][c] / M) * celu'(A[r, e*hP + c])
 __global__ void backward_seed_kernel(const float* __restrict__ act, int ld, int rows, int M, int hP, const float* __restrict__ w,
@@ -227,6 +229,7 @@ SpeciesMlp::SpeciesMlp(int numSpecies, int ensemble, int numLayers, const int* d
                     }
                 p += (size_t)ly.out * ly.in;
                 for (int o = 0; o < ly.out; o++) hb[s][l][(size_t)e * ly.outP + o] = p[o];
+                if (l == L_ - 1) energyBias_ += (double)p[0] * (double)(rowStart_[s + 1] - rowStart_[s]);
                 p += ly.out;
                 if (l < L_ - 1) flopsFwd_ += 2.0 * ly.in * ly.out * (double)(rowStart_[s + 1] - rowStart_[s]);
                 else flopsFwd_ += 2.0 * ly.in * (double)(rowStart_[s + 1] - rowStart_[s]);
@@ -295,6 +298,8 @@ void SpeciesMlp::setImpl(MlpImpl impl) {
     }
     NNP_CUDA_CHECK(cudaMalloc(&featHi_, sizeof(__half) * nr * featStride_));
     NNP_CUDA_CHECK(cudaMalloc(&featLo_, sizeof(__half) * nr * featStride_));
+    NNP_CUDA_CHECK(cudaMemset(featHi_, 0, sizeof(__half) * nr * featStride_));   // padding columns stay zero
+    NNP_CUDA_CHECK(cudaMemset(featLo_, 0, sizeof(__half) * nr * featStride_));
     NNP_CUDA_CHECK(cudaDeviceSynchronize());
     // the fp32 activation buffers of the validation path are not needed any more
     for (float*& p : act_) { cudaFree(p); p = nullptr; }
@@ -303,7 +308,7 @@ void SpeciesMlp::setImpl(MlpImpl impl) {
 
 void SpeciesMlp::forwardTc(const float* features, float* energy, cudaStream_t stream) {
     NNP_REQUIRE(featStride_ % 8 == 0, "feature stride must be a multiple of 8");
-    if (rows_ > 0) {
+    if (rows_ > 0 && features != nullptr) {
         const size_t n8 = (size_t)rows_ * featStride_ / 8;
         split_rows_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>(features, n8, featHi_, featLo_);
         count_launch();
@@ -318,6 +323,10 @@ void SpeciesMlp::forwardTc(const float* features, float* energy, cudaStream_t st
             g.M = nr; g.epilogue = 1; g.bias = ly.b; g.K = ly.inP; g.outScale = 1.0f;
             g.Bhi = ly.Whi; g.Blo = ly.Wlo; g.ldb = ly.inP; g.bRows = M_ * ly.outP;
             g.Chi = actHi_[l] + (size_t)r0 * width_[l]; g.Clo = actLo_[l] + (size_t)r0 * width_[l]; g.ldc = width_[l];
+            if (l == L_ - 2) {   // last hidden layer: energy and the backward seed come straight out of the epilogue
+                g.epilogue = 3; g.w3 = layers_[s][L_ - 1].W; g.energyAcc = energyAcc_; g.seedScale = kGradScale / M_;
+                g.Chi = dzHi_[l] + (size_t)r0 * width_[l]; g.Clo = dzLo_[l] + (size_t)r0 * width_[l];
+            }
             if (l == 0) {
                 g.Ahi = featHi_ + (size_t)r0 * featStride_; g.Alo = featLo_ + (size_t)r0 * featStride_; g.lda = featStride_;
                 g.aCols = featStride_; g.aBatchCols = 0; g.bBatchRows = 0; g.N = M_ * ly.outP; g.batch = 1; g.cBatchCols = 0; g.biasBatch = 0;
@@ -328,12 +337,6 @@ void SpeciesMlp::forwardTc(const float* features, float* energy, cudaStream_t st
             }
             launch_gemm_tcgen05(g, stream);
         }
-        const Layer& last = layers_[s][L_ - 1];
-        const int warps = nr * M_;
-        final_energy_h_kernel<<<(warps * 32 + 255) / 256, 256, 0, stream>>>(actHi_[L_ - 2] + (size_t)r0 * width_[L_ - 2],
-                                                                             actLo_[L_ - 2] + (size_t)r0 * width_[L_ - 2], width_[L_ - 2], nr, M_,
-                                                                             last.inP, last.W, last.b, energyAcc_);
-        count_launch();
     }
 }
 
@@ -341,15 +344,6 @@ void SpeciesMlp::backwardTc(float* featureGrad, cudaStream_t stream) {
     for (int s = 0; s < S_; s++) {
         const int r0 = rowStart_[s], nr = rowStart_[s + 1] - r0;
         if (nr == 0) continue;
-        {
-            const Layer& last = layers_[s][L_ - 1];
-            const int l = L_ - 2;
-            const size_t tot = (size_t)nr * M_ * last.inP;
-            backward_seed_h_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(
-                actHi_[l] + (size_t)r0 * width_[l], actLo_[l] + (size_t)r0 * width_[l], width_[l], nr, M_, last.inP, last.W,
-                dzHi_[l] + (size_t)r0 * width_[l], dzLo_[l] + (size_t)r0 * width_[l], width_[l]);
-            count_launch();
-        }
         for (int l = L_ - 2; l >= 1; l--) {
             const Layer& ly = layers_[s][l];
             GemmArgsH g;
@@ -381,7 +375,7 @@ void SpeciesMlp::forward(const float* features, float* energy, cudaStream_t stre
     NNP_CUDA_CHECK(cudaMemsetAsync(energyAcc_, 0, sizeof(double), stream));
     if (impl_ == MlpImpl::Tcgen05) {
         forwardTc(features, energy, stream);
-        finish_energy_kernel<<<1, 1, 0, stream>>>(energyAcc_, M_, energy);
+        finish_energy_kernel<<<1, 1, 0, stream>>>(energyAcc_, energyBias_, M_, energy);
         count_launch();
         NNP_CUDA_CHECK(cudaGetLastError());
         haveForward_ = true;
@@ -412,7 +406,7 @@ void SpeciesMlp::forward(const float* features, float* energy, cudaStream_t stre
                                                                            last.inP, last.W, last.b, energyAcc_);
         count_launch();
     }
-    finish_energy_kernel<<<1, 1, 0, stream>>>(energyAcc_, M_, energy);
+    finish_energy_kernel<<<1, 1, 0, stream>>>(energyAcc_, 0.0, M_, energy);
     count_launch();
     NNP_CUDA_CHECK(cudaGetLastError());
     haveForward_ = true;

@@ -37,6 +37,11 @@ public:
     // featureGrad: device [rows][featureStride] <- dE/dfeatures (same row order); uses the activations of the last forward
     void backward(float* featureGrad, cudaStream_t stream);
 
+    // tensor-core path: the feature matrix as fp16 hi/lo pairs [rows][featureStride]; the AEV kernels write it directly and
+    // forward() is then called with features == nullptr
+    __half* featHi() { return featHi_; }
+    __half* featLo() { return featLo_; }
+    bool tensorCore() const { return impl_ == MlpImpl::Tcgen05; }
     int numRows() const { return rows_; }
     double flopsForward() const { return flopsFwd_; }   // algorithmic (un-padded) flops of one forward pass
 
@@ -61,6 +66,7 @@ private:
     void forwardTc(const float* features, float* energy, cudaStream_t stream);
     void backwardTc(float* featureGrad, cudaStream_t stream);
     double* energyAcc_ = nullptr;
+    double energyBias_ = 0;      // sum over atoms and members of the last-layer bias
     MlpImpl impl_ = MlpImpl::Simt;
     double flopsFwd_ = 0;
     bool haveForward_ = false;
@@ -86,8 +92,11 @@ struct GemmArgsH {
     const float* bias; int biasBatch;
     const __half* actHi; const __half* actLo; int ldact; int actBatchCols;
     float outScale;
+    const float* w3; double* energyAcc; float seedScale;   // epilogue 3 (last hidden layer): w3[batch*biasBatch + n]
     int M, N, K, batch;
-    int epilogue;                                // 0 fp32 out * outScale, 1 bias + celu -> hi/lo, 2 times celu'(act) -> hi/lo
+    // 0 fp32 out * outScale, 1 bias + celu -> hi/lo, 2 times celu'(act) -> hi/lo,
+    // 3 last hidden layer: a = celu(z + bias); energy += a*w3; out = seedScale*w3*celu'(a) -> hi/lo (the backward seed)
+    int epilogue;
 };
 void launch_gemm_tcgen05(const GemmArgsH& a, cudaStream_t stream);
 
