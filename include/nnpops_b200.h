@@ -105,6 +105,47 @@ NNPOPS_API int nnpops_batched_linear_forward(const float* vectors, const float* 
 NNPOPS_API int nnpops_batched_linear_backward(const float* grad_out, const float* weights, float* grad_vectors, int num_atoms, int num_models,
                                    int n_out, int n_in, void* stream);
 
+/* --------------------------------------------------------------------------------------------------------------------
+ * getNeighborPairs.  Replaces torch op neighbors::getNeighborPairs (schema src/pytorch/neighbors/neighbors.cpp:4; kernels
+ * getNeighborPairsCUDA.cu:31-195; semantics getNeighborPairsCPU.cpp:56-98 and getNeighborPairs.py:60-96).
+ * positions: device [num_atoms][3]; box: device [3][3] or NULL; cutoff inclusive (distance <= cutoff);
+ * max_num_pairs: -1 = all pairs (outputs of length num_atoms(num_atoms-1)/2, slot row(row-1)/2+col, misses -1 / NaN), or a
+ * positive capacity (compacted list, padded with -1 / NaN, overflow dropped);
+ * neighbors: device int32 [2][P] (row > col); deltas: device [P][3] = pos[row]-pos[col] (minimum image); distances: device [P];
+ * num_found: device int32 [1] = number of pairs inside the cutoff (may exceed the capacity).  No host synchronisation:
+ * CUDA-graph capturable after one warm-up call with the same num_atoms.
+ * ------------------------------------------------------------------------------------------------------------------ */
+NNPOPS_API int nnpops_neighbor_pairs_f32(const float* positions, const float* box, int num_atoms, float cutoff, long long max_num_pairs,
+                                         int* neighbors, float* deltas, float* distances, int* num_found, void* stream);
+NNPOPS_API int nnpops_neighbor_pairs_f64(const double* positions, const double* box, int num_atoms, double cutoff, long long max_num_pairs,
+                                         int* neighbors, double* deltas, double* distances, int* num_found, void* stream);
+/* backward (getNeighborPairsCUDA.cu:80-101,166-195): grad_positions [num_atoms][3] is overwritten */
+NNPOPS_API int nnpops_neighbor_pairs_backward_f32(const int* neighbors, const float* deltas, const float* distances, const float* grad_deltas,
+                                                  const float* grad_distances, long long num_pairs, int num_atoms, float* grad_positions,
+                                                  void* stream);
+NNPOPS_API int nnpops_neighbor_pairs_backward_f64(const int* neighbors, const double* deltas, const double* distances,
+                                                  const double* grad_deltas, const double* grad_distances, long long num_pairs,
+                                                  int num_atoms, double* grad_positions, void* stream);
+
+/* --------------------------------------------------------------------------------------------------------------------
+ * PME.  Replaces torch ops pme::pme_direct and pme::pme_reciprocal (schemas src/pytorch/pme/pme.cpp:3-6; CUDA
+ * implementations pmeCUDA.cu:278-317 and :319-418).  All arrays device, fp32; exclusions int32 [num_atoms][max_exclusions] with
+ * rows sorted descending and padded with -1 (as pme.py:92 prepares them).
+ * pme_direct: energy [1]; pos_deriv [num_atoms][3] and charge_deriv [num_atoms] receive dE/dx and dE/dq (the reference
+ *   computes them in forward and scales them in backward, pmeCUDA.cu:306,310-316).
+ * pme_reciprocal_forward: energy [1]; recip_grid: float2 [gridx][gridy][gridz/2+1], the convolved half-complex grid to keep for
+ *   backward (pmeCUDA.cu:365).  order 4 or 5 only, like the reference CUDA path (pmeCUDA.cu:347).
+ * ------------------------------------------------------------------------------------------------------------------ */
+NNPOPS_API int nnpops_pme_direct(const float* positions, const float* charges, const int* neighbors, const float* deltas,
+                                 const float* distances, const int* exclusions, int num_atoms, long long num_pairs, int max_exclusions,
+                                 float alpha, float coulomb, float* energy, float* pos_deriv, float* charge_deriv, void* stream);
+NNPOPS_API int nnpops_pme_reciprocal_forward(const float* positions, const float* charges, const float* box, int num_atoms, int gridx,
+                                             int gridy, int gridz, int order, float alpha, float coulomb, const float* xmoduli,
+                                             const float* ymoduli, const float* zmoduli, float* energy, float* recip_grid, void* stream);
+NNPOPS_API int nnpops_pme_reciprocal_backward(const float* positions, const float* charges, const float* box, int num_atoms, int gridx,
+                                              int gridy, int gridz, int order, float coulomb, const float* recip_grid, float* pos_deriv,
+                                              float* charge_deriv, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

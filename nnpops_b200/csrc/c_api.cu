@@ -7,6 +7,16 @@
 namespace nnpops {
 void batched_linear_forward(const float*, const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 void batched_linear_backward(const float*, const float*, float*, int, int, int, int, cudaStream_t);
+template <typename T>
+void neighbor_pairs(const T*, const T*, int, T, long long, int*, T*, T*, int*, cudaStream_t);
+template <typename T>
+void neighbor_pairs_backward(const int*, const T*, const T*, const T*, const T*, long long, int, T*, cudaStream_t);
+void pme_direct(const float*, const float*, const int*, const float*, const float*, const int*, int, long long, int, float, float, float*,
+                float*, float*, cudaStream_t);
+void pme_reciprocal_forward(const float*, const float*, const float*, int, int, int, int, int, float, float, const float*, const float*,
+                            const float*, float*, float*, cudaStream_t);
+void pme_reciprocal_backward(const float*, const float*, const float*, int, int, int, int, int, float, const float*, float*, float*,
+                             cudaStream_t);
 }
 
 using namespace nnpops;
@@ -233,6 +243,71 @@ int nnpops_batched_linear_backward(const float* grad_out, const float* weights, 
     return guarded([&] {
         require_device();
         batched_linear_backward(grad_out, weights, grad_vectors, num_atoms, num_models, n_out, n_in, (cudaStream_t)stream);
+    });
+}
+
+int nnpops_neighbor_pairs_f32(const float* positions, const float* box, int num_atoms, float cutoff, long long max_num_pairs,
+                              int* neighbors, float* deltas, float* distances, int* num_found, void* stream) {
+    return guarded([&] {
+        require_device();
+        neighbor_pairs<float>(positions, box, num_atoms, cutoff, max_num_pairs, neighbors, deltas, distances, num_found, (cudaStream_t)stream);
+    });
+}
+
+int nnpops_neighbor_pairs_f64(const double* positions, const double* box, int num_atoms, double cutoff, long long max_num_pairs,
+                              int* neighbors, double* deltas, double* distances, int* num_found, void* stream) {
+    return guarded([&] {
+        require_device();
+        neighbor_pairs<double>(positions, box, num_atoms, cutoff, max_num_pairs, neighbors, deltas, distances, num_found, (cudaStream_t)stream);
+    });
+}
+
+int nnpops_neighbor_pairs_backward_f32(const int* neighbors, const float* deltas, const float* distances, const float* grad_deltas,
+                                       const float* grad_distances, long long num_pairs, int num_atoms, float* grad_positions, void* stream) {
+    return guarded([&] {
+        require_device();
+        neighbor_pairs_backward<float>(neighbors, deltas, distances, grad_deltas, grad_distances, num_pairs, num_atoms, grad_positions,
+                                       (cudaStream_t)stream);
+    });
+}
+
+int nnpops_neighbor_pairs_backward_f64(const int* neighbors, const double* deltas, const double* distances, const double* grad_deltas,
+                                       const double* grad_distances, long long num_pairs, int num_atoms, double* grad_positions,
+                                       void* stream) {
+    return guarded([&] {
+        require_device();
+        neighbor_pairs_backward<double>(neighbors, deltas, distances, grad_deltas, grad_distances, num_pairs, num_atoms, grad_positions,
+                                        (cudaStream_t)stream);
+    });
+}
+
+int nnpops_pme_direct(const float* positions, const float* charges, const int* neighbors, const float* deltas, const float* distances,
+                      const int* exclusions, int num_atoms, long long num_pairs, int max_exclusions, float alpha, float coulomb, float* energy,
+                      float* pos_deriv, float* charge_deriv, void* stream) {
+    return guarded([&] {
+        require_device();
+        pme_direct(positions, charges, neighbors, deltas, distances, exclusions, num_atoms, num_pairs, max_exclusions, alpha, coulomb, energy,
+                   pos_deriv, charge_deriv, (cudaStream_t)stream);
+    });
+}
+
+int nnpops_pme_reciprocal_forward(const float* positions, const float* charges, const float* box, int num_atoms, int gridx, int gridy,
+                                  int gridz, int order, float alpha, float coulomb, const float* xmoduli, const float* ymoduli,
+                                  const float* zmoduli, float* energy, float* recip_grid, void* stream) {
+    return guarded([&] {
+        require_device();
+        pme_reciprocal_forward(positions, charges, box, num_atoms, gridx, gridy, gridz, order, alpha, coulomb, xmoduli, ymoduli, zmoduli,
+                               energy, recip_grid, (cudaStream_t)stream);
+    });
+}
+
+int nnpops_pme_reciprocal_backward(const float* positions, const float* charges, const float* box, int num_atoms, int gridx, int gridy,
+                                   int gridz, int order, float coulomb, const float* recip_grid, float* pos_deriv, float* charge_deriv,
+                                   void* stream) {
+    return guarded([&] {
+        require_device();
+        pme_reciprocal_backward(positions, charges, box, num_atoms, gridx, gridy, gridz, order, coulomb, recip_grid, pos_deriv, charge_deriv,
+                                (cudaStream_t)stream);
     });
 }
 

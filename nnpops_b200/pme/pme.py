@@ -1,0 +1,171 @@
+"""PME on the B200 kernels: same class, constructor arguments and methods as the reference's ``NNPOps.pme.PME``
+(src/pytorch/pme/pme.py:5-196): ``PME(gridx, gridy, gridz, order, alpha, coulomb, exclusions)`` with ``compute_direct`` and
+``compute_reciprocal``; gradients with respect to positions and charges only; second derivatives raise."""
+import ctypes as C
+import math
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from .._lib import lib, check, ptr, current_stream, register
+from ..neighbors import getNeighborPairs
+
+_vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+register({
+    "nnpops_pme_direct": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _f, _f, _vp, _vp, _vp, _vp],
+    "nnpops_pme_reciprocal_forward": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp],
+    "nnpops_pme_reciprocal_backward": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp],
+})
+
+
+def _f32(t: Tensor, what: str) -> Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("nnpops_b200 runs on CUDA devices only (no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise RuntimeError('"%s" has to be float32' % what)
+    return t.detach().contiguous()
+
+
+class _Direct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, positions, charges, neighbors, deltas, distances, exclusions, alpha, coulomb):
+        pos, q = _f32(positions, "positions"), _f32(charges, "charges")
+        d, r = _f32(deltas, "deltas"), _f32(distances, "distances")
+        nb = neighbors.detach().to(torch.int32).contiguous()
+        ex = exclusions.detach().to(device=pos.device, dtype=torch.int32).contiguous()
+        n = q.shape[0]
+        energy = torch.empty((), dtype=torch.float32, device=pos.device)
+        pos_deriv = torch.empty((n, 3), dtype=torch.float32, device=pos.device)
+        charge_deriv = torch.empty((n,), dtype=torch.float32, device=pos.device)
+        with torch.cuda.device(pos.device):
+            check(lib.nnpops_pme_direct(ptr(pos), ptr(q), ptr(nb), ptr(d), ptr(r), ptr(ex) if ex.numel() else None, n, nb.shape[1],
+                                        ex.shape[1] if ex.dim() == 2 else 0, float(alpha), float(coulomb), ptr(energy), ptr(pos_deriv),
+                                        ptr(charge_deriv), current_stream(pos.device)))
+        ctx.save_for_backward(pos_deriv, charge_deriv)
+        return energy
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad):
+        pos_deriv, charge_deriv = ctx.saved_tensors
+        return pos_deriv * grad, charge_deriv * grad, None, None, None, None, None, None
+
+
+class _Reciprocal(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, positions, charges, box_vectors, gridx, gridy, gridz, order, alpha, coulomb, xmoduli, ymoduli, zmoduli):
+        pos, q, box = _f32(positions, "positions"), _f32(charges, "charges"), _f32(box_vectors, "box_vectors")
+        dev = pos.device
+        xm, ym, zm = (m.detach().to(device=dev, dtype=torch.float32).contiguous() for m in (xmoduli, ymoduli, zmoduli))
+        energy = torch.empty((), dtype=torch.float32, device=dev)
+        recip = torch.empty((gridx, gridy, gridz // 2 + 1, 2), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.nnpops_pme_reciprocal_forward(ptr(pos), ptr(q), ptr(box), q.shape[0], gridx, gridy, gridz, order, float(alpha),
+                                                    float(coulomb), ptr(xm), ptr(ym), ptr(zm), ptr(energy), ptr(recip), current_stream(dev)))
+        ctx.save_for_backward(pos, q, box, recip)
+        ctx.params = (gridx, gridy, gridz, order, float(coulomb))
+        return energy
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad):
+        pos, q, box, recip = ctx.saved_tensors
+        gridx, gridy, gridz, order, coulomb = ctx.params
+        dev = pos.device
+        pos_deriv = torch.empty_like(pos)
+        charge_deriv = torch.empty_like(q)
+        with torch.cuda.device(dev):
+            check(lib.nnpops_pme_reciprocal_backward(ptr(pos), ptr(q), ptr(box), q.shape[0], gridx, gridy, gridz, order, coulomb, ptr(recip),
+                                                     ptr(pos_deriv), ptr(charge_deriv), current_stream(dev)))
+        return (pos_deriv * grad, charge_deriv * grad) + (None,) * 10
+
+
+def pme_direct(positions, charges, neighbors, deltas, distances, exclusions, alpha, coulomb):
+    """Functional form of the op pme::pme_direct (pme.cpp:3-4)."""
+    return _Direct.apply(positions, charges, neighbors, deltas, distances, exclusions, alpha, coulomb)
+
+
+def pme_reciprocal(positions, charges, box_vectors, gridx, gridy, gridz, order, alpha, coulomb, xmoduli, ymoduli, zmoduli):
+    """Functional form of the op pme::pme_reciprocal (pme.cpp:5-6)."""
+    return _Reciprocal.apply(positions, charges, box_vectors, int(gridx), int(gridy), int(gridz), int(order), alpha, coulomb, xmoduli,
+                             ymoduli, zmoduli)
+
+
+def bspline_moduli(order: int, sizes):
+    """|DFT of the order-`order` cardinal B-spline sampled at the integers|^2 for each grid size, in float32 exactly as the
+    reference builds them in PME.__init__ (pme.py:94-129); moduli below 1e-7 are replaced by the mean of their neighbours."""
+    max_size = max(sizes)
+    data = torch.zeros(order, dtype=torch.float32)
+    bsplines_data = torch.zeros(max(max_size, order + 1), dtype=torch.float32)
+    data[0] = 1
+    for i in range(3, order):
+        data[i - 1] = 0
+        for j in range(1, i - 1):
+            data[i - j - 1] = (j * data[i - j - 2] + (i - j) * data[i - j - 1]) / (i - 1)
+        data[0] /= i - 1
+    for i in range(1, order - 1):
+        data[order - i - 1] = (i * data[order - i - 2] + (order - i) * data[order - i - 1]) / (order - 1)
+    data[0] /= order - 1
+    bsplines_data[1:order + 1] = data
+    out = []
+    for n in sizes:
+        scale = torch.tensor([2 * math.pi * i / n for i in range(n)], dtype=torch.float64).to(torch.float32)
+        arg = scale[:, None] * torch.arange(n).to(torch.float32)[None, :]
+        b = bsplines_data[:n]
+        sc = torch.sum(b * torch.cos(arg), dim=1)
+        ss = torch.sum(b * torch.sin(arg), dim=1)
+        m = sc * sc + ss * ss
+        for i in range(n):
+            if m[i] < 1e-7:
+                m[i] = (m[(i - 1 + n) % n] + m[(i + 1) % n]) * 0.5
+        out.append(m)
+    return out
+
+
+class PME:
+    """Particle-mesh Ewald for a periodic system of point charges; see the reference docstring (pme.py:5-51) for the physics."""
+
+    def __init__(self, gridx: int, gridy: int, gridz: int, order: int, alpha: float, coulomb: float, exclusions: Tensor):
+        if gridx < 1 or gridy < 1 or gridz < 1:
+            raise ValueError('The grid dimensions must be positive')
+        if order < 1:
+            raise ValueError('order must be positive')
+        if alpha <= 0:
+            raise ValueError('alpha must be positive')
+        if coulomb <= 0:
+            raise ValueError('coulomb must be positive')
+        if exclusions.dim() != 2:
+            raise ValueError('exclusions must be 2D')
+        self.gridx, self.gridy, self.gridz = gridx, gridy, gridz
+        self.order, self.alpha, self.coulomb = order, alpha, coulomb
+        self.exclusions, _ = torch.sort(exclusions.to(torch.int32), descending=True)
+        self.moduli = bspline_moduli(order, (gridx, gridy, gridz))
+
+    def _validate(self, positions, charges, box_vectors):
+        if positions.dim() != 2 or positions.shape[1] != 3:
+            raise ValueError('positions must have shape (atoms, 3)')
+        if charges.dim() != 1:
+            raise ValueError('charges must be 1D')
+        if positions.shape[0] != self.exclusions.shape[0] or charges.shape[0] != self.exclusions.shape[0]:
+            raise ValueError('positions, charges, and exclusions must all have the same length')
+        if box_vectors.dim() != 2 or box_vectors.shape[0] != 3 or box_vectors.shape[1] != 3:
+            raise ValueError('box_vectors must have shape (3, 3)')
+
+    def compute_direct(self, positions: Tensor, charges: Tensor, cutoff: float, box_vectors: Tensor, max_num_pairs: int = -1):
+        """Direct-space energy (pme.py:131-165): neighbour list + erfc sum + exclusion correction."""
+        self._validate(positions, charges, box_vectors)
+        if cutoff <= 0:
+            raise ValueError('cutoff must be positive')
+        neighbors, deltas, distances, _ = getNeighborPairs(positions, cutoff, max_num_pairs, box_vectors)
+        self.exclusions = self.exclusions.to(positions.device)
+        return pme_direct(positions, charges, neighbors, deltas, distances, self.exclusions, self.alpha, self.coulomb)
+
+    def compute_reciprocal(self, positions: Tensor, charges: Tensor, box_vectors: Tensor):
+        """Reciprocal-space energy including the self term (pme.py:167-196)."""
+        self._validate(positions, charges, box_vectors)
+        for i in range(3):
+            self.moduli[i] = self.moduli[i].to(positions.device)
+        self_energy = -torch.sum(charges ** 2) * self.coulomb * self.alpha / math.sqrt(math.pi)
+        return self_energy + pme_reciprocal(positions, charges, box_vectors, self.gridx, self.gridy, self.gridz, self.order, self.alpha,
+                                            self.coulomb, self.moduli[0], self.moduli[1], self.moduli[2])
