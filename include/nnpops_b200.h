@@ -146,6 +146,37 @@ NNPOPS_API int nnpops_pme_reciprocal_backward(const float* positions, const floa
                                               int gridy, int gridz, int order, float coulomb, const float* recip_grid, float* pos_deriv,
                                               float* charge_deriv, void* stream);
 
+/* --------------------------------------------------------------------------------------------------------------------
+ * SchNet CFConv.  Replaces classes CFConvNeighbors / CFConv (src/schnet/CFConv.h:37-85 and :109-217; CUDA implementations
+ * src/schnet/CudaCFConv.cu:132-188, :352-378, :484-528) which the torch Holders drive from src/pytorch/CFConvNeighbors.cpp:39-75
+ * and src/pytorch/CFConv.cpp:71-190.
+ *   CFConvNeighbors(numAtoms, cutoff, periodic) + build(positions, box)         -> nnpops_cfconv_neighbors_create / _build
+ *   CFConv(numAtoms, width, numGaussians, cutoff, periodic, gaussianWidth, activation, w1, b1, w2, b2)
+ *                                                                                -> nnpops_cfconv_create
+ *   compute(neighbors, positions, box, input, output)                           -> nnpops_cfconv_compute
+ *   backprop(neighbors, positions, box, input, outputDeriv, inputDeriv, positionDeriv) -> nnpops_cfconv_backprop
+ * w1: device float, indexed [width][num_gaussians] row-major exactly as the reference indexes the memory it is given
+ * (CpuCFConv.cpp:160-168; the torch Holder passes a [num_gaussians, width] tensor's storage unchanged, CFConv.cpp:131-132);
+ * w2: device [width][width]; b1, b2: device [width].  activation: 0 = shifted softplus, 1 = tanh (CFConv.h:111-120).
+ * Periodicity is decided per build() by box != NULL.  positions/box of compute/backprop are those given to build() (the
+ * list stores the sorted coordinates), so they are not passed again.  build() reads back one integer (the pair count) to size
+ * the list.  points_per_sigma: resolution of the radial filter table (0 = default 32).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct nnpops_cfconv_neighbors* nnpops_cfconv_neighbors_t;
+typedef struct nnpops_cfconv* nnpops_cfconv_t;
+NNPOPS_API int nnpops_cfconv_neighbors_create(nnpops_cfconv_neighbors_t* out, int num_atoms, float cutoff);
+NNPOPS_API void nnpops_cfconv_neighbors_destroy(nnpops_cfconv_neighbors_t h);
+NNPOPS_API int nnpops_cfconv_neighbors_build(nnpops_cfconv_neighbors_t h, const float* positions, const float* box, void* stream);
+NNPOPS_API int nnpops_cfconv_neighbors_num_pairs(nnpops_cfconv_neighbors_t h, long long* num_pairs);
+NNPOPS_API int nnpops_cfconv_create(nnpops_cfconv_t* out, int width, int num_gaussians, float cutoff, float gaussian_width, int activation,
+                                    const float* w1, const float* b1, const float* w2, const float* b2, int points_per_sigma);
+NNPOPS_API void nnpops_cfconv_destroy(nnpops_cfconv_t h);
+/* input, output: device float [num_atoms][width] */
+NNPOPS_API int nnpops_cfconv_compute(nnpops_cfconv_t h, nnpops_cfconv_neighbors_t neighbors, const float* input, float* output, void* stream);
+/* input_grad: device [num_atoms][width]; position_grad: device [num_atoms][3]; both overwritten */
+NNPOPS_API int nnpops_cfconv_backprop(nnpops_cfconv_t h, nnpops_cfconv_neighbors_t neighbors, const float* input, const float* output_grad,
+                                      float* input_grad, float* position_grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,16 @@ template <typename T>
 void neighbor_pairs(const T*, const T*, int, T, long long, int*, T*, T*, int*, cudaStream_t);
 template <typename T>
 void neighbor_pairs_backward(const int*, const T*, const T*, const T*, const T*, long long, int, T*, cudaStream_t);
+class CFConvNeighborList;
+class CFConvFilter;
+CFConvNeighborList* cfconv_neighbors_create(int, float);
+void cfconv_neighbors_destroy(CFConvNeighborList*);
+void cfconv_neighbors_build(CFConvNeighborList*, const float*, const float*, cudaStream_t);
+long long cfconv_neighbors_pairs(const CFConvNeighborList*);
+CFConvFilter* cfconv_create(int, int, float, float, int, const float*, const float*, const float*, const float*, int);
+void cfconv_destroy(CFConvFilter*);
+void cfconv_compute(const CFConvFilter*, const CFConvNeighborList*, const float*, float*, cudaStream_t);
+void cfconv_backprop(const CFConvFilter*, const CFConvNeighborList*, const float*, const float*, float*, float*, cudaStream_t);
 void pme_direct(const float*, const float*, const int*, const float*, const float*, const int*, int, long long, int, float, float, float*,
                 float*, float*, cudaStream_t);
 void pme_reciprocal_forward(const float*, const float*, const float*, int, int, int, int, int, float, float, const float*, const float*,
@@ -58,6 +68,13 @@ struct nnpops_ani_model {
     float* dGrad = nullptr;
     float* dEnergy = nullptr;
     int n = 0;
+};
+
+struct nnpops_cfconv_neighbors {
+    CFConvNeighborList* impl;
+};
+struct nnpops_cfconv {
+    CFConvFilter* impl;
 };
 
 extern "C" {
@@ -308,6 +325,64 @@ int nnpops_pme_reciprocal_backward(const float* positions, const float* charges,
         require_device();
         pme_reciprocal_backward(positions, charges, box, num_atoms, gridx, gridy, gridz, order, coulomb, recip_grid, pos_deriv, charge_deriv,
                                 (cudaStream_t)stream);
+    });
+}
+
+int nnpops_cfconv_neighbors_create(nnpops_cfconv_neighbors_t* out, int num_atoms, float cutoff) {
+    return guarded([&] {
+        require_device();
+        NNP_REQUIRE(out != nullptr, "out must not be NULL");
+        *out = new nnpops_cfconv_neighbors{cfconv_neighbors_create(num_atoms, cutoff)};
+    });
+}
+
+void nnpops_cfconv_neighbors_destroy(nnpops_cfconv_neighbors_t h) {
+    if (!h) return;
+    cfconv_neighbors_destroy(h->impl);
+    delete h;
+}
+
+int nnpops_cfconv_neighbors_build(nnpops_cfconv_neighbors_t h, const float* positions, const float* box, void* stream) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl, "invalid handle");
+        cfconv_neighbors_build(h->impl, positions, box, (cudaStream_t)stream);
+    });
+}
+
+int nnpops_cfconv_neighbors_num_pairs(nnpops_cfconv_neighbors_t h, long long* num_pairs) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl && num_pairs, "invalid argument");
+        *num_pairs = cfconv_neighbors_pairs(h->impl);
+    });
+}
+
+int nnpops_cfconv_create(nnpops_cfconv_t* out, int width, int num_gaussians, float cutoff, float gaussian_width, int activation,
+                         const float* w1, const float* b1, const float* w2, const float* b2, int points_per_sigma) {
+    return guarded([&] {
+        require_device();
+        NNP_REQUIRE(out != nullptr, "out must not be NULL");
+        *out = new nnpops_cfconv{cfconv_create(width, num_gaussians, cutoff, gaussian_width, activation, w1, b1, w2, b2, points_per_sigma)};
+    });
+}
+
+void nnpops_cfconv_destroy(nnpops_cfconv_t h) {
+    if (!h) return;
+    cfconv_destroy(h->impl);
+    delete h;
+}
+
+int nnpops_cfconv_compute(nnpops_cfconv_t h, nnpops_cfconv_neighbors_t neighbors, const float* input, float* output, void* stream) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl && neighbors && neighbors->impl, "invalid handle");
+        cfconv_compute(h->impl, neighbors->impl, input, output, (cudaStream_t)stream);
+    });
+}
+
+int nnpops_cfconv_backprop(nnpops_cfconv_t h, nnpops_cfconv_neighbors_t neighbors, const float* input, const float* output_grad,
+                           float* input_grad, float* position_grad, void* stream) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl && neighbors && neighbors->impl, "invalid handle");
+        cfconv_backprop(h->impl, neighbors->impl, input, output_grad, input_grad, position_grad, (cudaStream_t)stream);
     });
 }
 

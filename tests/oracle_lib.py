@@ -110,3 +110,34 @@ def ani_backward(pos, species, n_species, rcr, rca, radial_fn, angular_fn, radia
                                       pos.ctypes.data_as(C.c_void_p), boxp, rg.ctypes.data_as(C.c_void_p),
                                       ag.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
     return out
+
+
+def cfconv(pos, width, n_gauss, cutoff, sigma, activation, w1, b1, w2, b2, inp, box=None, out_grad=None, bits=32, impl="oracle"):
+    """-> output [n, W] or (output, input_grad, pos_grad, n_pairs) when out_grad is given."""
+    pos = np.ascontiguousarray(pos, np.float32)
+    n = pos.shape[0]
+    if impl == "ref":
+        bits = 32
+    dt = np.float32 if bits == 32 else np.float64
+    w1, b1, w2, b2 = (np.ascontiguousarray(a, np.float32) for a in (w1, b1, w2, b2))
+    inp = np.ascontiguousarray(inp, dt)
+    out = np.zeros((n, width), dt)
+    og = None if out_grad is None else np.ascontiguousarray(out_grad, dt)
+    ig = np.zeros((n, width), dt)
+    pg = np.zeros((n, 3), dt)
+    boxp = _opt(box, np.float32)
+    act = {"ssp": 0, "tanh": 1}[activation]
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    if impl == "ref":
+        npairs = C.c_longlong(0)
+        ref_lib().ref_cfconv(n, width, n_gauss, C.c_float(cutoff), C.c_float(sigma), act, p(w1), p(b1), p(w2), p(b2), p(pos), boxp, p(inp),
+                             p(out), p(og), p(ig), p(pg), C.byref(npairs))
+        pairs = npairs.value
+    else:
+        fn = lib(bits).oracle_cfconv
+        fn.restype = C.c_longlong
+        pairs = fn(n, width, n_gauss, C.c_float(cutoff), C.c_float(sigma), act, p(w1), p(b1), p(w2), p(b2), p(pos), boxp, p(inp), p(out),
+                   p(og), p(ig), p(pg))
+    if out_grad is None:
+        return out
+    return out, ig, pg, pairs
