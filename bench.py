@@ -84,6 +84,21 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def shard_conformers(total, rank, world):
+    """Conformer ids evaluated by `rank`: BASELINE config 3 deals conformer c to rank c mod world (independent conformers, no
+    collective on the data path)."""
+    return [c for c in range(total) if c % world == rank]
+
+
+def max_over_ranks(ms, dist, device):
+    """MAX over ranks of a per-rank duration (the slowest rank defines the job's throughput)."""
+    import torch
+    t = torch.tensor([float(ms)], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.cpu()[0])
+
+
 def make_conformer(n_atoms, c):
     from systems import lattice, cubic_box
     pos, L = lattice(n_atoms, 2.154, 0.3, 3000 + c)
@@ -111,7 +126,7 @@ def run_ours(args):
                      nets, mlp_impl=args.mlp, device="cuda:%d" % local)
     # pool of conformers per rank: conformer c of BASELINE config 3 goes to rank c mod world
     pool = 4
-    confs = [make_conformer(n, rank + world * i) for i in range(pool)]
+    confs = [make_conformer(n, c) for c in shard_conformers(pool * world, rank, world)]
     d_pos = [torch.tensor(p, device=dev) for p, _ in confs]
     d_box = [torch.tensor(b, device=dev) for _, b in confs]
     h_pos = [torch.tensor(p).pin_memory() for p, _ in confs]
@@ -148,13 +163,10 @@ def run_ours(args):
         model.energy_and_gradient(d_pos[i % pool], d_box[i % pool])
     t1.record()
     sync_all()
-    ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
     l1 = launches()
     stages, nrec = model.timing_end()
     clocks = sampler.stop() if rank == 0 else None
-    if dist is not None:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.cpu()[0])
+    ms_total = max_over_ranks(t0.elapsed_time(t1), dist, dev)
 
     # ---- end to end through the host-buffer C-ABI entry point (pinned host memory; H2D + D2H inside the timed region)
     for i in range(min(args.warmup, 3)):
@@ -166,10 +178,7 @@ def run_ours(args):
         model.energy_and_gradient_host(h_pos[i % pool].numpy(), h_box[i % pool].numpy(), h_e.numpy(), h_g.numpy())
     e1.record()
     sync_all()
-    ems = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if dist is not None:
-        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-    e2e_ms = float(ems.cpu()[0])
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1), dist, dev)
 
     if rank != 0:
         if dist is not None:

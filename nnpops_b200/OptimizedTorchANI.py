@@ -181,7 +181,8 @@ class OptimizedTorchANI(torch.nn.Module):
         super().__init__()
         conv = model.species_converter
         aev = model.aev_computer
-        species = conv((atomicNumbers, torch.empty(0))).species
+        conv_device = getattr(getattr(conv, "conv_tensor", None), "device", atomicNumbers.device)
+        species = conv((atomicNumbers.to(conv_device), torch.empty(0))).species
         self.register_buffer("species", species)
         nets = model.neural_networks
         ensemble = list(nets) if isinstance(nets, torch.nn.ModuleList) else [nets]
@@ -193,7 +194,7 @@ class OptimizedTorchANI(torch.nn.Module):
                               aev.ShfZ[0, 0, 0, :].tolist(), species[0].tolist(), networks, mlp_impl=mlp_impl,
                               device=str(atomicNumbers.device) if atomicNumbers.device.type == "cuda" else "cuda")
         # self energies are a constant (EnergyShifter.py:42-52)
-        self.register_buffer("self_energies", model.energy_shifter.sae(species))
+        self.register_buffer("self_energies", model.energy_shifter.sae(species.cpu()))
 
     def forward(self, species_coordinates: Tuple[Tensor, Tensor], cell: Optional[Tensor] = None,
                 pbc: Optional[Tensor] = None) -> SpeciesEnergies:
@@ -206,4 +207,4 @@ class OptimizedTorchANI(torch.nn.Module):
             if pbc.tolist() != [True, True, True]:
                 raise ValueError('Only fully periodic systems are supported, i.e. pbc = [True, True, True]')
         energies = self.fused(coordinates[0], cell)
-        return SpeciesEnergies(self.species, energies + self.self_energies.to(energies.device))
+        return SpeciesEnergies(self.species, energies.double() + self.self_energies.to(energies.device))

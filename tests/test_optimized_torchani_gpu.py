@@ -1,0 +1,49 @@
+"""The reference's module chain on a torchani stand-in: OptimizedTorchANI (fused) and the literal
+TorchANISymmetryFunctions + TorchANIBatchedNN path, both against oracle AEV + ATen MLP (cf. TestOptimizedTorchANI.py:59-100,
+TestBatchedNN.py:49-82 of the reference, which compare against torchani itself)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle_lib as O
+from fake_torchani import Model
+from mlp_ref import mlp_energy_and_grad
+from systems import ANI2X, lattice, rel_err
+
+pytestmark = pytest.mark.gpu
+HIDDEN = [(96, 64, 48), (80, 64, 48), (64, 48, 32), (64, 48, 32), (48, 32, 32), (48, 32, 32), (48, 32, 32)]
+
+
+def reference_values(model, pos, species):
+    rfn, afn = O.fn_tables(ANI2X["EtaR"], ANI2X["ShfR"], ANI2X["EtaA"], ANI2X["Zeta"], ANI2X["ShfA"], ANI2X["ShfZ"])
+    r0, a0 = O.ani_forward(pos, species, 7, 5.1, 3.5, rfn, afn, bits=64)
+    e0, dA = mlp_energy_and_grad(np.concatenate([r0, a0], 1), species, model.networks_numpy(), torch.float64)
+    g0 = O.ani_backward(pos, species, 7, 5.1, 3.5, rfn, afn, dA[:, :112], dA[:, 112:], bits=64)
+    sae = float(model.energy_shifter.sae(torch.tensor(species)[None])[0])
+    return e0 + sae, g0
+
+
+@pytest.mark.parametrize("path", ["fused", "literal"])
+def test_module_chain(path):
+    from nnpops_b200.OptimizedTorchANI import OptimizedTorchANI
+    from nnpops_b200.SymmetryFunctions import TorchANISymmetryFunctions
+    from nnpops_b200.BatchedNN import TorchANIBatchedNN
+    n = 46   # size of the reference's benchmark ligand 2iuz
+    pos, _ = lattice(n, 1.9, 0.3, 46)
+    species = np.random.default_rng(3).integers(0, 7, n)
+    numbers = torch.tensor([[Model(HIDDEN, 1, 0).species_converter.ELEMENTS[s] for s in species]])
+    model = Model(HIDDEN, 4, seed=11)
+    e_ref, g_ref = reference_values(model, pos, species)
+    p = torch.tensor(pos, device="cuda").unsqueeze(0).requires_grad_(True)
+    if path == "fused":
+        nnp = OptimizedTorchANI(model, numbers.cuda())
+        energy = nnp((numbers.cuda(), p)).energies
+    else:
+        aev = TorchANISymmetryFunctions(model.species_converter, model.aev_computer, numbers)
+        nn_ = TorchANIBatchedNN(model.species_converter, model.neural_networks, numbers).to("cuda")
+        sp = model.species_converter((numbers, torch.empty(0))).species.cuda()
+        energy = nn_(aev((sp, p))).energies + model.energy_shifter.sae(sp.cpu()).cuda()
+    energy.sum().backward()
+    e = float(energy.detach().cpu().double()[0])
+    assert abs(e - e_ref) < 5e-6 * abs(e_ref)
+    assert rel_err(p.grad.cpu().numpy()[0], g_ref) < 1e-5
