@@ -177,6 +177,10 @@ NNPOPS_API int nnpops_cfconv_compute(nnpops_cfconv_t h, nnpops_cfconv_neighbors_
 NNPOPS_API int nnpops_cfconv_backprop(nnpops_cfconv_t h, nnpops_cfconv_neighbors_t neighbors, const float* input, const float* output_grad,
                                       float* input_grad, float* position_grad, void* stream);
 
+/* development aid: mean milliseconds of one tcgen05 GEMM shape (C[m, batch*n] = A.B^T per batch member) on synthetic operands;
+ * mode = epilogue (0 fp32, 1 bias+CELU, 2 celu' mask, 3 last hidden layer); streaming != 0 disables the resident-B variant */
+NNPOPS_API int nnpops_debug_gemm_bench(int m, int n, int k, int batch, int mode, int streaming, int iters, double* ms);
+
 #ifdef __cplusplus
 }
 #endif

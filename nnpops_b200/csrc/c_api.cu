@@ -11,6 +11,8 @@ template <typename T>
 void neighbor_pairs(const T*, const T*, int, T, long long, int*, T*, T*, int*, cudaStream_t);
 template <typename T>
 void neighbor_pairs_backward(const int*, const T*, const T*, const T*, const T*, long long, int, T*, cudaStream_t);
+double gemm_tcgen05_bench(int, int, int, int, int, int);
+void gemm_tcgen05_set_streaming(bool);
 class CFConvNeighborList;
 class CFConvFilter;
 CFConvNeighborList* cfconv_neighbors_create(int, float);
@@ -383,6 +385,15 @@ int nnpops_cfconv_backprop(nnpops_cfconv_t h, nnpops_cfconv_neighbors_t neighbor
     return guarded([&] {
         NNP_REQUIRE(h && h->impl && neighbors && neighbors->impl, "invalid handle");
         cfconv_backprop(h->impl, neighbors->impl, input, output_grad, input_grad, position_grad, (cudaStream_t)stream);
+    });
+}
+
+int nnpops_debug_gemm_bench(int m, int n, int k, int batch, int mode, int streaming, int iters, double* ms) {
+    return guarded([&] {
+        require_device();
+        gemm_tcgen05_set_streaming(streaming != 0);
+        *ms = gemm_tcgen05_bench(m, n, k, batch, mode, iters);
+        gemm_tcgen05_set_streaming(false);
     });
 }
 

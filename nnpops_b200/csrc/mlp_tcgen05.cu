@@ -16,6 +16,7 @@
 // so the epilogue of tile i overlaps the main loop of tile i+1.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <tuple>
@@ -27,8 +28,12 @@ namespace {
 
 constexpr int TBM = 128, TBN = 128, TBK = 64, kStages = 3, kAccStages = 2;
 constexpr uint32_t kTileBytes = TBM * TBK * 2;        // 16 KB: 128 rows x 128 bytes
-constexpr uint32_t kStageBytes = 4 * kTileBytes;      // A hi, A lo, B hi, B lo
-constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr uint32_t kStageBytes = 4 * kTileBytes;      // streaming mode: A hi, A lo, B hi, B lo
+constexpr uint32_t kDataBytes = kStages * kStageBytes;
+constexpr uint32_t kStageWarpBytes = 32 * 64;         // per epilogue warp: 32 rows x 32 halves (XOR-swizzled), transposes to coalesced rows
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (4 + kEpiWarps) * 32;
+constexpr uint32_t kSmemBytes = kDataBytes + kEpiWarps * kStageWarpBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -71,6 +76,18 @@ __device__ __forceinline__ void umma_f16(uint32_t tmemD, uint64_t descA, uint64_
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// true in exactly one lane of a converged warp; ptxas recognises ELECT and keeps the leader's operands in uniform registers
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -99,7 +116,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ float celu_f(float x) { return x > 0.0f ? x : kCeluAlpha * (__expf(x * (1.0f / kCeluAlpha)) - 1.0f); }
+// celu(x) = max(x, 0) + min(0, alpha (exp(x / alpha) - 1)), branch-free: one ex2 per element whatever the sign
+__device__ __forceinline__ float celu_f(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(x, 0.0f) * (1.4426950408889634f / kCeluAlpha)));
+    return fmaxf(x, 0.0f) + fmaf(kCeluAlpha, e, -kCeluAlpha);
+}
 __device__ __forceinline__ float celu_grad_from_act_f(float a) { return a > 0.0f ? 1.0f : a * (1.0f / kCeluAlpha) + 1.0f; }
 
 __device__ __forceinline__ void split_f(float v, __half& hi, __half& lo) {
@@ -116,15 +138,185 @@ struct TcArgs {
     const __half* actHi; const __half* actLo; int ldact; int actBatchCols;
     float outScale;
     const float* w3; double* energyAcc; float seedScale;
+    int wide;                      // 1: issue Ahi.[Bhi;Blo] as one N = 256 MMA
 };
 
-__global__ void __launch_bounds__(256, 1)
+// ---- epilogue of one 128 x 64 slice: TMEM -> registers -> fused element-wise op -> shared-memory transpose -> coalesced global ----
+// A thread owns one row of the accumulator (TMEM lane), so direct stores would touch 32 different lines per instruction.  Every
+// 32 x 32 block is therefore transposed through a per-warp staging buffer: the thread writes its 64-byte row segment, then the
+// warp stores two full row segments per instruction (lanes 0-15 -> row r, lanes 16-31 -> row r + 1, 4 bytes per lane).
+// Staging layout: 32 rows x 64 bytes, no padding; 16-byte unit u of row r lives at unit (u ^ ((r >> 1) & 3)).  With that XOR both
+// access patterns are bank-conflict free: a thread writing/reading its own row (lanes = rows) and a quarter-warp moving two
+// complete rows (lanes = 16-byte units of consecutive rows).  Global accesses are 16 bytes per lane, 8 full rows per instruction.
+__device__ __forceinline__ uint32_t stage_off(int r, int u) { return (uint32_t)(r * 64 + ((u ^ ((r >> 1) & 3)) << 4)); }
+
+__device__ __forceinline__ void staged_store_half(unsigned char* stg, const uint32_t (&pk)[16], __half* gbase, size_t ld, int rowsValid, int lane) {
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        *reinterpret_cast<uint4*>(stg + stage_off(lane, i)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+    __syncwarp();
+    const int r0 = lane >> 2, u = lane & 3;
+    __half* dst = gbase + (size_t)r0 * ld + u * 8;
+    const size_t step = 8 * ld;
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+        const int r = it * 8 + r0;
+        const uint4 v = *reinterpret_cast<const uint4*>(stg + stage_off(r, u));
+        if (r < rowsValid) *reinterpret_cast<uint4*>(dst) = v;
+        dst += step;
+    }
+    __syncwarp();
+}
+
+// the reverse: coalesced load of a 32 x 32 block of halves, each thread ends up with its own row (16 packed registers)
+__device__ __forceinline__ void staged_load_half(unsigned char* stg, uint32_t (&pk)[16], const __half* gbase, size_t ld, int rowsValid, int lane) {
+    const int r0 = lane >> 2, u = lane & 3;
+    const __half* src = gbase + (size_t)r0 * ld + u * 8;
+    const size_t step = 8 * ld;
+    uint4 tmp[4];
+#pragma unroll
+    for (int it = 0; it < 4; it++) {      // all loads in flight before the first shared-memory store
+        tmp[it] = (it * 8 + r0 < rowsValid) ? __ldg(reinterpret_cast<const uint4*>(src)) : make_uint4(0u, 0u, 0u, 0u);
+        src += step;
+    }
+#pragma unroll
+    for (int it = 0; it < 4; it++) *reinterpret_cast<uint4*>(stg + stage_off(it * 8 + r0, u)) = tmp[it];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint4 t = *reinterpret_cast<const uint4*>(stg + stage_off(lane, i));
+        pk[4 * i] = t.x; pk[4 * i + 1] = t.y; pk[4 * i + 2] = t.z; pk[4 * i + 3] = t.w;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// warp (q = TMEM lane quarter, hsel = column half) handles rows q*32 + lane and columns [hsel*64, hsel*64 + 64) of the tile
+template <typename WAIT>
+__device__ __forceinline__ void epilogue_tile(const TcArgs& g, uint32_t tmemBase, int acc, int q, int hsel, int lane, int mt, int nt, int z,
+                                              unsigned char* stg, float& esum, WAIT&& waitAccumulator) {
+    const int mw = mt * TBM + q * 32;              // first row of this warp
+    const int m = mw + lane, n0 = nt * TBN;
+    const int rowsValid = min(32, g.M - mw);       // warp-uniform, may be <= 0
+    const uint32_t tbase = tmemBase + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * TBN);
+    bool waited = false;
+#pragma unroll 1
+    for (int c = hsel * 2; c < hsel * 2 + 2; c++) {
+        const int n = n0 + c * 32;
+        if (n >= g.N) break;                       // warp-uniform
+        uint32_t actH[16], actL[16];
+        if (g.mode == 2 && rowsValid > 0) {        // independent of the accumulator: for the first block this runs BEFORE the wait
+            const size_t ao = (size_t)mw * g.ldact + (size_t)z * g.actBatchCols + n;
+            staged_load_half(stg, actH, g.actHi + ao, g.ldact, rowsValid, lane);
+            staged_load_half(stg, actL, g.actLo + ao, g.ldact, rowsValid, lane);
+        }
+        if (!waited) { waitAccumulator(); waited = true; }
+        float4 bv[8];
+        if (g.mode == 1 || g.mode == 3) {          // bias row of this block, requested before the accumulator is read
+            const float4* bp = reinterpret_cast<const float4*>(g.bias + (size_t)z * g.biasBatch + n);
+#pragma unroll
+            for (int j = 0; j < 8; j++) bv[j] = __ldg(bp + j);
+        }
+        uint32_t r1[32], r2[32];
+        tmem_ld32(tbase + c * 32, r1);
+        tmem_ld32(tbase + TBN + c * 32, r2);
+        tmem_ld_wait();
+        if (rowsValid <= 0) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = fmaf(__uint_as_float(r2[j]), kLoInv, __uint_as_float(r1[j]));
+        if (g.mode == 0) {                         // fp32 result (dE/dAEV): the main loop is 24+ chunks long, direct stores stay hidden
+            if (m < g.M) {
+                float* dst = g.C32 + (size_t)m * g.ldc + (size_t)z * g.cBatchCols + n;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(dst + j) =
+                        make_float4(v[j] * g.outScale, v[j + 1] * g.outScale, v[j + 2] * g.outScale, v[j + 3] * g.outScale);
+            }
+            continue;
+        }
+        if (g.mode == 1 || g.mode == 3) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                v[4 * j] = celu_f(v[4 * j] + bv[j].x); v[4 * j + 1] = celu_f(v[4 * j + 1] + bv[j].y);
+                v[4 * j + 2] = celu_f(v[4 * j + 2] + bv[j].z); v[4 * j + 3] = celu_f(v[4 * j + 3] + bv[j].w);
+            }
+            if (g.mode == 3) {
+                const float4* wp = reinterpret_cast<const float4*>(g.w3 + (size_t)z * g.biasBatch + n);
+                const bool rowOk = m < g.M;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float4 wv = __ldg(wp + j);
+                    const float w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const float a = v[4 * j + i];
+                        if (rowOk) esum = fmaf(a, w4[i], esum);
+                        v[4 * j + i] = g.seedScale * w4[i] * celu_grad_from_act_f(a);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const float2 fh = unpack_h2(actH[i]), fl = unpack_h2(actL[i]);
+                v[2 * i] *= celu_grad_from_act_f(fmaf(fl.x, kLoInv, fh.x));
+                v[2 * i + 1] *= celu_grad_from_act_f(fmaf(fl.y, kLoInv, fh.y));
+            }
+        }
+        uint32_t ph[16], pl[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            const float2 f2 = __half22float2(h2);
+            ph[i] = *reinterpret_cast<const uint32_t*>(&h2);
+            pl[i] = pack_h2((v[2 * i] - f2.x) * kLoScale, (v[2 * i + 1] - f2.y) * kLoScale);
+        }
+        const size_t co = (size_t)mw * g.ldc + (size_t)z * g.cBatchCols + n;
+        staged_store_half(stg, ph, g.Chi + co, g.ldc, rowsValid, lane);
+        staged_store_half(stg, pl, g.Clo + co, g.ldc, rowsValid, lane);
+    }
+    if (!waited) waitAccumulator();                // tail tile with no columns for this warp: still consume the barrier phase
+}
+
+// One 64-wide K chunk: D1 += Ahi.Bhi, D2 += Ahi.Blo + Alo.Bhi.  The B hi and lo tiles are adjacent in shared memory (256 rows of
+// 128 bytes) and D1 | D2 are adjacent in TMEM, so for a full-width tile Ahi . [Bhi; Blo] is ONE N = 256 instruction producing D1
+// and the first half of D2 together: 8 instead of 12 tcgen05.mma per chunk.  descBits = all descriptor fields except the start
+// address (constant for the kernel); the start-address field counts 16-byte units, so stepping K by 16 halves adds 2.
+template <bool FULL>
+__device__ __forceinline__ void issue_chunk(uint32_t d1, uint64_t descBits, uint32_t stageAddr, uint32_t idescTile, bool firstChunk) {
+    const uint64_t aHi0 = descBits + (stageAddr >> 4);
+    constexpr uint32_t kTile16 = kTileBytes >> 4;
+    constexpr uint32_t idescWide = (1u << 4) | ((uint32_t)(2 * TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+    const uint32_t d2 = d1 + TBN;
+#pragma unroll
+    for (int k4 = 0; k4 < TBK / 16; k4++) {
+        const uint64_t aHi = aHi0 + 2 * k4, aLo = aHi + kTile16, bHi = aHi + 2 * kTile16, bLo = aHi + 3 * kTile16;
+        const uint32_t accum = (firstChunk && k4 == 0) ? 0u : 1u;
+        if (FULL) {
+            umma_f16(d1, aHi, bHi, idescWide, accum);          // N = 256: [D1 | D2] (+)= Ahi . [Bhi; Blo]
+        } else {
+            umma_f16(d1, aHi, bHi, idescTile, accum);
+            umma_f16(d2, aHi, bLo, idescTile, accum);
+        }
+        umma_f16(d2, aLo, bHi, idescTile, 1u);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                     const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, const TcArgs g) {
     extern __shared__ unsigned char smemRaw[];
-    const uint32_t base = (smem_u32(smemRaw) + 1023u) & ~1023u;
-    const uint32_t barBase = base + kStages * kStageBytes;
-    // barriers: full[kStages], empty[kStages], accFull[kAccStages], accEmpty[kAccStages]; then the TMEM base address slot
+    const uint32_t rawAddr = smem_u32(smemRaw);
+    const uint32_t base = (rawAddr + 1023u) & ~1023u;
+    unsigned char* const basePtr = smemRaw + (base - rawAddr);
+    const uint32_t barBase = base + kDataBytes + kEpiWarps * kStageWarpBytes;
+    // barriers: full[kStages], empty[kStages], accFull[kAccStages], accEmpty[kAccStages]; then the TMEM address slot
     auto fullBar = [&](int s) { return barBase + 8u * s; };
     auto emptyBar = [&](int s) { return barBase + 8u * (kStages + s); };
     auto accFullBar = [&](int s) { return barBase + 8u * (2 * kStages + s); };
@@ -140,7 +332,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; s++) { mbar_init(fullBar(s), 1); mbar_init(emptyBar(s), 1); }
-        for (int s = 0; s < kAccStages; s++) { mbar_init(accFullBar(s), 1); mbar_init(accEmptyBar(s), 4); }
+        for (int s = 0; s < kAccStages; s++) { mbar_init(accFullBar(s), 1); mbar_init(accEmptyBar(s), kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -154,140 +346,90 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmemBase) : "r"(tmemSlot));
 
     const int tilesM = (g.M + TBM - 1) / TBM, tilesN = (g.N + TBN - 1) / TBN;
-    const int numTiles = tilesM * tilesN * g.batch;
     const int kChunks = g.K / TBK;
+    const int numTiles = tilesM * tilesN * g.batch;
+    // Tile order: batch member fastest, then n-tile, then m-tile.  Concurrent CTAs then work on the same rows of A for all
+    // ensemble members at once (each row of the activation matrix is read as one contiguous run from HBM) and on few m-tiles.
+    auto decode = [&](int t, int& mt, int& nt, int& z) {
+        z = t % g.batch;
+        nt = (t / g.batch) % tilesN;
+        mt = t / (g.batch * tilesN);
+    };
 
+    // Producer and MMA warps stay converged: every lane runs the loops and the barrier waits (so all control values are
+    // warp-uniform), and the one lane picked by elect.sync issues the TMA / tcgen05 instructions.
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = blockIdx.x; t < numTiles; t += gridDim.x) {
-                const int nt = t % tilesN, mt = (t / tilesN) % tilesM, z = t / (tilesN * tilesM);
-                const int m0 = mt * TBM, n0 = nt * TBN;
-                for (int kc = 0; kc < kChunks; kc++) {
-                    mbar_wait(emptyBar(stage), phase ^ 1u);
+        const bool leader = elect_one();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = blockIdx.x; t < numTiles; t += gridDim.x) {
+            int mt, nt, z;
+            decode(t, mt, nt, z);
+            const int m0 = mt * TBM, yb = z * g.bBatchRows + nt * TBN;
+            for (int kc = 0; kc < kChunks; kc++) {
+                mbar_wait(emptyBar(stage), phase ^ 1u);
+                if (leader) {
                     const uint32_t sb = base + stage * kStageBytes;
                     mbar_expect_tx(fullBar(stage), kStageBytes);
-                    const int xa = z * g.aBatchCols + kc * TBK, xb = kc * TBK, yb = z * g.bBatchRows + n0;
+                    const int xa = z * g.aBatchCols + kc * TBK;
                     tma_load_2d(sb, &mapAhi, fullBar(stage), xa, m0);
                     tma_load_2d(sb + kTileBytes, &mapAlo, fullBar(stage), xa, m0);
-                    tma_load_2d(sb + 2 * kTileBytes, &mapBhi, fullBar(stage), xb, yb);
-                    tma_load_2d(sb + 3 * kTileBytes, &mapBlo, fullBar(stage), xb, yb);
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    tma_load_2d(sb + 2 * kTileBytes, &mapBhi, fullBar(stage), kc * TBK, yb);
+                    tma_load_2d(sb + 3 * kTileBytes, &mapBlo, fullBar(stage), kc * TBK, yb);
                 }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, accPhase = 0;
-            for (int t = blockIdx.x; t < numTiles; t += gridDim.x) {
-                const int nt = t % tilesN;
-                const int nTile = min(TBN, g.N - nt * TBN);   // 64 or 128 (N is a multiple of 64)
-                const uint32_t idesc = (1u << 4) | ((uint32_t)(nTile >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-                mbar_wait(accEmptyBar(acc), accPhase ^ 1u);
+        const bool leader = elect_one();
+        const uint64_t descBits = make_desc(0);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, accPhase = 0;
+        for (int t = blockIdx.x; t < numTiles; t += gridDim.x) {
+            int mt, nt, z;
+            decode(t, mt, nt, z);
+            const int nTile = min(TBN, g.N - nt * TBN);   // 64 or 128 (N is a multiple of 64)
+            const uint32_t idescTile = (1u << 4) | ((uint32_t)(nTile >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+            mbar_wait(accEmptyBar(acc), accPhase ^ 1u);
+            tc_fence_after();
+            const uint32_t d1 = tmemBase + (uint32_t)(acc * 2 * TBN);
+            for (int kc = 0; kc < kChunks; kc++) {
+                mbar_wait(fullBar(stage), phase);
                 tc_fence_after();
-                const uint32_t d1 = tmemBase + (uint32_t)(acc * 2 * TBN), d2 = d1 + TBN;
-                for (int kc = 0; kc < kChunks; kc++) {
-                    mbar_wait(fullBar(stage), phase);
-                    tc_fence_after();
+                if (leader) {
                     const uint32_t sb = base + stage * kStageBytes;
-#pragma unroll
-                    for (int k4 = 0; k4 < TBK / 16; k4++) {
-                        const uint64_t aHi = make_desc(sb + k4 * 32), aLo = make_desc(sb + kTileBytes + k4 * 32);
-                        const uint64_t bHi = make_desc(sb + 2 * kTileBytes + k4 * 32), bLo = make_desc(sb + 3 * kTileBytes + k4 * 32);
-                        const uint32_t first = (kc | k4) ? 1u : 0u;
-                        umma_f16(d1, aHi, bHi, idesc, first);
-                        umma_f16(d2, aHi, bLo, idesc, first);
-                        umma_f16(d2, aLo, bHi, idesc, 1u);
-                    }
+                    if (nTile == TBN) issue_chunk<true>(d1, descBits, sb, idescTile, kc == 0);
+                    else issue_chunk<false>(d1, descBits, sb, idescTile, kc == 0);
                     umma_commit(emptyBar(stage));          // frees the smem stage once these MMAs have read it
                     if (kc == kChunks - 1) umma_commit(accFullBar(acc));
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
-                if (++acc == kAccStages) { acc = 0; accPhase ^= 1u; }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
+            if (++acc == kAccStages) { acc = 0; accPhase ^= 1u; }
         }
     } else if (warp >= 4) {
-        const int q = warp & 3;   // TMEM lane quarter owned by this warp
+        const int q = warp & 3;              // TMEM lane quarter this warp may access (warp id mod 4)
+        const int hsel = (warp - 4) >> 2;    // which 64-column half of the tile
+        unsigned char* const stg = basePtr + kDataBytes + (warp - 4) * kStageWarpBytes;
         int acc = 0;
         uint32_t accPhase = 0;
         for (int t = blockIdx.x; t < numTiles; t += gridDim.x) {
-            const int nt = t % tilesN, mt = (t / tilesN) % tilesM, z = t / (tilesN * tilesM);
-            const int m = mt * TBM + q * 32 + lane, n0 = nt * TBN;
+            int mt, nt, z;
+            decode(t, mt, nt, z);
             float esum = 0.0f;
-            mbar_wait(accFullBar(acc), accPhase);
-            tc_fence_after();
-            const uint32_t tbase = tmemBase + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * TBN);
-#pragma unroll 1
-            for (int c = 0; c < TBN / 32; c++) {
-                const int n = n0 + c * 32;
-                if (n >= g.N) break;                       // warp-uniform
-                uint32_t r1[32], r2[32];
-                tmem_ld32(tbase + c * 32, r1);
-                tmem_ld32(tbase + TBN + c * 32, r2);
-                tmem_ld_wait();
-                if (m < g.M) {
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = fmaf(__uint_as_float(r2[j]), kLoInv, __uint_as_float(r1[j]));
-                    if (g.mode == 0) {
-                        float* dst = g.C32 + (size_t)m * g.ldc + (size_t)z * g.cBatchCols + n;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(dst + j) =
-                                make_float4(v[j] * g.outScale, v[j + 1] * g.outScale, v[j + 2] * g.outScale, v[j + 3] * g.outScale);
-                    } else {
-                        if (g.mode == 1) {
-                            const float* bp = g.bias + (size_t)z * g.biasBatch + n;
-#pragma unroll
-                            for (int j = 0; j < 32; j++) v[j] = celu_f(v[j] + __ldg(bp + j));
-                        } else if (g.mode == 3) {
-                            const float* bp = g.bias + (size_t)z * g.biasBatch + n;
-                            const float* wp = g.w3 + (size_t)z * g.biasBatch + n;
-#pragma unroll
-                            for (int j = 0; j < 32; j++) {
-                                const float a = celu_f(v[j] + __ldg(bp + j));
-                                const float wv = __ldg(wp + j);
-                                esum = fmaf(a, wv, esum);
-                                v[j] = g.seedScale * wv * celu_grad_from_act_f(a);
-                            }
-                        } else {
-                            const size_t ao = (size_t)m * g.ldact + (size_t)z * g.actBatchCols + n;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                const uint4 ah = *reinterpret_cast<const uint4*>(g.actHi + ao + j);
-                                const uint4 al = *reinterpret_cast<const uint4*>(g.actLo + ao + j);
-                                const __half* hh = reinterpret_cast<const __half*>(&ah);
-                                const __half* hl = reinterpret_cast<const __half*>(&al);
-#pragma unroll
-                                for (int i = 0; i < 8; i++) {
-                                    const float a = fmaf(__half2float(hl[i]), kLoInv, __half2float(hh[i]));
-                                    v[j + i] *= celu_grad_from_act_f(a);
-                                }
-                            }
-                        }
-                        const size_t co = (size_t)m * g.ldc + (size_t)z * g.cBatchCols + n;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint4 ph, pl;
-                            __half* hh = reinterpret_cast<__half*>(&ph);
-                            __half* hl = reinterpret_cast<__half*>(&pl);
-#pragma unroll
-                            for (int i = 0; i < 8; i++) split_f(v[j + i], hh[i], hl[i]);
-                            *reinterpret_cast<uint4*>(g.Chi + co + j) = ph;
-                            *reinterpret_cast<uint4*>(g.Clo + co + j) = pl;
-                        }
-                    }
-                }
-            }
+            epilogue_tile(g, tmemBase, acc, q, hsel, lane, mt, nt, z, stg, esum, [&]() {
+                mbar_wait(accFullBar(acc), accPhase);
+                tc_fence_after();
+            });
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(accEmptyBar(acc));
             if (g.mode == 3) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
-                if (lane == 0) atomicAdd(g.energyAcc, (double)esum);
+                if (lane == 0 && esum != 0.0f) atomicAdd(g.energyAcc, (double)esum);
             }
             if (++acc == kAccStages) { acc = 0; accPhase ^= 1u; }
         }
@@ -333,6 +475,8 @@ CUtensorMap make_map(const __half* ptr, long long rows, long long cols, long lon
     return m;
 }
 
+bool g_forceStreaming = std::getenv("NNPOPS_GEMM_STREAMING") != nullptr;   // A/B switch for measurements
+
 int num_sms() {
     static int n = 0;
     if (!n) {
@@ -344,6 +488,8 @@ int num_sms() {
 }
 
 }  // namespace
+
+void gemm_tcgen05_set_streaming(bool on) { g_forceStreaming = on; }
 
 void launch_gemm_tcgen05(const GemmArgsH& a, cudaStream_t stream) {
     if (a.M <= 0 || a.N <= 0) return;
@@ -364,10 +510,50 @@ void launch_gemm_tcgen05(const GemmArgsH& a, cudaStream_t stream) {
     g.Chi = a.Chi; g.Clo = a.Clo; g.C32 = a.C32; g.ldc = a.ldc; g.cBatchCols = a.cBatchCols; g.bias = a.bias; g.biasBatch = a.biasBatch;
     g.actHi = a.actHi; g.actLo = a.actLo; g.ldact = a.ldact; g.actBatchCols = a.actBatchCols; g.outScale = a.outScale;
     g.w3 = a.w3; g.energyAcc = a.energyAcc; g.seedScale = a.seedScale;
+    g.wide = 1;
     const int tiles = ((a.M + TBM - 1) / TBM) * ((a.N + TBN - 1) / TBN) * a.batch;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    gemm_tcgen05_kernel<<<grid, 256, kSmemBytes, stream>>>(mAhi, mAlo, mBhi, mBlo, g);
+    gemm_tcgen05_kernel<<<grid, kThreads, kSmemBytes, stream>>>(mAhi, mAlo, mBhi, mBlo, g);
     count_launch();
+}
+
+// Micro-benchmark of one GEMM shape on synthetic operands (development aid behind nnpops_debug_gemm_bench): mean milliseconds.
+double gemm_tcgen05_bench(int M, int N, int K, int batch, int mode, int iters) {
+    const int lda = batch > 1 ? batch * K : K, ldc = batch * N;
+    __half *Ahi, *Alo, *Bhi, *Blo, *Chi, *Clo, *actHi, *actLo;
+    float *C32, *bias, *w3;
+    double* eacc;
+    const size_t na = (size_t)M * lda, nb = (size_t)batch * N * K, nc = (size_t)M * ldc;
+    NNP_CUDA_CHECK(cudaMalloc(&Ahi, 2 * na)); NNP_CUDA_CHECK(cudaMalloc(&Alo, 2 * na));
+    NNP_CUDA_CHECK(cudaMalloc(&Bhi, 2 * nb)); NNP_CUDA_CHECK(cudaMalloc(&Blo, 2 * nb));
+    NNP_CUDA_CHECK(cudaMalloc(&Chi, 2 * nc)); NNP_CUDA_CHECK(cudaMalloc(&Clo, 2 * nc));
+    NNP_CUDA_CHECK(cudaMalloc(&actHi, 2 * nc)); NNP_CUDA_CHECK(cudaMalloc(&actLo, 2 * nc));
+    NNP_CUDA_CHECK(cudaMalloc(&C32, 4 * nc)); NNP_CUDA_CHECK(cudaMalloc(&bias, 4 * (size_t)ldc)); NNP_CUDA_CHECK(cudaMalloc(&w3, 4 * (size_t)ldc));
+    NNP_CUDA_CHECK(cudaMalloc(&eacc, 8));
+    cudaMemset(Ahi, 0x2c, 2 * na); cudaMemset(Alo, 0x2c, 2 * na); cudaMemset(Bhi, 0x2c, 2 * nb); cudaMemset(Blo, 0x2c, 2 * nb);
+    cudaMemset(actHi, 0x2c, 2 * nc); cudaMemset(actLo, 0x2c, 2 * nc); cudaMemset(bias, 0, 4 * (size_t)ldc); cudaMemset(w3, 0, 4 * (size_t)ldc);
+    cudaMemset(eacc, 0, 8);
+    GemmArgsH g;
+    std::memset(&g, 0, sizeof(g));
+    g.Ahi = Ahi; g.Alo = Alo; g.lda = lda; g.aCols = lda; g.aBatchCols = batch > 1 ? K : 0;
+    g.Bhi = Bhi; g.Blo = Blo; g.ldb = K; g.bRows = batch * N; g.bBatchRows = batch > 1 ? N : 0;
+    g.Chi = Chi; g.Clo = Clo; g.C32 = C32; g.ldc = ldc; g.cBatchCols = batch > 1 ? N : 0; g.bias = bias; g.biasBatch = batch > 1 ? N : 0;
+    g.actHi = actHi; g.actLo = actLo; g.ldact = ldc; g.actBatchCols = batch > 1 ? N : 0; g.outScale = 1.0f; g.w3 = w3; g.energyAcc = eacc;
+    g.seedScale = 1.0f; g.M = M; g.N = N; g.K = K; g.batch = batch; g.epilogue = mode;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 2; i++) launch_gemm_tcgen05(g, nullptr);
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; i++) launch_gemm_tcgen05(g, nullptr);
+    cudaEventRecord(e1);
+    NNP_CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    for (void* p : {(void*)Ahi, (void*)Alo, (void*)Bhi, (void*)Blo, (void*)Chi, (void*)Clo, (void*)actHi, (void*)actLo, (void*)C32, (void*)bias,
+                    (void*)w3, (void*)eacc})
+        cudaFree(p);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return ms / iters;
 }
 
 }  // namespace nnpops
