@@ -39,6 +39,27 @@ __device__ __forceinline__ void store_aev(const AevOut& o, size_t idx, float v) 
     }
 }
 
+// zero `count` consecutive AEV elements starting at idx (warp-cooperative); 16-byte stores when the range allows it
+__device__ __forceinline__ void zero_aev_range(const AevOut& o, size_t idx, int count, int lane) {
+    if (o.hi) {
+        if ((count & 7) == 0 && (idx & 7) == 0) {
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = lane * 8; i < count; i += 256) {
+                *reinterpret_cast<uint4*>(o.hi + idx + i) = z;
+                *reinterpret_cast<uint4*>(o.lo + idx + i) = z;
+            }
+        } else {
+            for (int i = lane; i < count; i += 32) { o.hi[idx + i] = __float2half_rn(0.0f); o.lo[idx + i] = __float2half_rn(0.0f); }
+        }
+    } else {
+        if ((count & 3) == 0 && (idx & 3) == 0) {
+            for (int i = lane * 4; i < count; i += 128) *reinterpret_cast<float4*>(o.f32 + idx + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            for (int i = lane; i < count; i += 32) o.f32[idx + i] = 0.0f;
+        }
+    }
+}
+
 __device__ __forceinline__ int pair_index(int S, int s, int t) {   // CpuANISymmetryFunctions.cpp:39-43
     int lo = min(s, t), hi = max(s, t);
     return lo * S - (lo * (lo - 1)) / 2 + (hi - lo);
@@ -270,18 +291,28 @@ ani_angular_fwd_kernel(int n, const float4* __restrict__ sorted, const int* __re
     const float cosScale = tab->cosScale;
     const float fEtaL2 = tab->fEtaL2, fZeta = tab->fZeta, fScale = tab->fScale;
 
+    // species offsets of this centre live in registers (lane s holds segment s) and are broadcast by shuffle; species without
+    // angular neighbours are skipped wholesale and their output blocks zero-filled with wide stores
+    const int myB = lane < S ? min(off[lane], capA) : 0;
+    const int myN = (lane < S ? min(off[lane + 1], capA) : 0) - myB;
     for (int m0 = 0; m0 < nA; m0 += 32) {
         int pIdx = 0;
         for (int s = 0; s < S; s++) {
-            const int bs = off[s], ns = min(off[s + 1], capA) - bs;
+            const int bs = __shfl_sync(kFull, myB, s), ns = __shfl_sync(kFull, myN, s);
+            if (ns == 0) {   // every pair (s, t >= s) is empty
+                if (m0 == 0) zero_aev_range(out, orow + (size_t)pIdx * nA, (S - s) * nA, lane);
+                pIdx += S - s;
+                continue;
+            }
             for (int t = s; t < S; t++, pIdx++) {
-                const int bt = off[t], nt = min(off[t + 1], capA) - bt;
+                const int bt = __shfl_sync(kFull, myB, t), nt = __shfl_sync(kFull, myN, t);
                 const int ntrip = (s == t) ? (ns * (ns - 1)) / 2 : ns * nt;
-                const size_t dst = orow + pIdx * nA + m0;
+                const size_t dst = orow + (size_t)pIdx * nA + m0;
                 if (ntrip <= 0) {
-                    if (m0 + lane < nA) store_aev(out, dst + lane, 0.0f);
+                    if (m0 == 0) zero_aev_range(out, orow + (size_t)pIdx * nA, nA, lane);
                     continue;
                 }
+                const float invNt = 1.0f / (float)nt;
                 float acc[32];
 #pragma unroll
                 for (int i = 0; i < 32; i++) acc[i] = 0.0f;
@@ -296,7 +327,7 @@ ani_angular_fwd_kernel(int n, const float4* __restrict__ sorted, const int* __re
                         while ((b * (b + 1)) / 2 <= qq) b++;
                         ia = bs + qq - (b * (b - 1)) / 2; ib = bs + b;
                     } else {
-                        const int a = (int)(((float)qq + 0.5f) / (float)nt);
+                        const int a = (int)(((float)qq + 0.5f) * invNt);   // exact: the quotient is >= 0.5/nt away from an integer
                         ia = bs + a; ib = bt + qq - a * nt;
                     }
                     const float ax = sdx[ia], ay = sdy[ia], az = sdz[ia], bx = sdx[ib], by = sdy[ib], bz = sdz[ib];
@@ -355,6 +386,9 @@ __global__ void __launch_bounds__(kWPB * 32)
 ani_radial_bwd_kernel(int n, const float4* __restrict__ sorted, const int* __restrict__ sortedOrig, const Geom* __restrict__ geom,
                       const AniTables* __restrict__ tab, const int* __restrict__ rowRad, const int* __restrict__ offRad, int capR,
                       const int* __restrict__ rowMap, const float* __restrict__ grad, int stride, float* __restrict__ posGrad) {
+    // lane <-> neighbour: every lane evaluates all radial functions of its own pair, with the neighbour's gradient row segment
+    // (nR consecutive floats) fetched by 16-byte loads that are all in flight before the first use; the centre's own gradient
+    // row is staged once per warp in shared memory (indexed by the neighbour's species).  One warp reduction per centre.
     extern __shared__ unsigned char smemRaw[];
     __shared__ Geom g;
     __shared__ float sEtaL2[kAniMaxRadial], sEta[kAniMaxRadial], sShf[kAniMaxRadial];
@@ -365,52 +399,61 @@ ani_radial_bwd_kernel(int n, const float4* __restrict__ sorted, const int* __res
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = blockIdx.x * kWPB + w;
     if (p >= n) return;
-    float* sux = reinterpret_cast<float*>(smemRaw) + (size_t)w * 7 * capR;
-    float *suy = sux + capR, *suz = suy + capR, *sr = suz + capR, *sfc = sr + capR, *sdfc = sfc + capR;
-    int* srow = reinterpret_cast<int*>(sdfc + capR);
-    const int* off = offRad + (size_t)p * (S + 1);
-    const int cnt = min(off[S], capR);
+    float* sGi = reinterpret_cast<float*>(smemRaw) + (size_t)w * S * nR;
+    const int cnt = min(offRad[(size_t)p * (S + 1) + S], capR);
     const float4 ci = sorted[p];
     const int sp = __float_as_int(ci.w);
+    const int orig = sortedOrig[p];
+    {
+        const float* gi = grad + (size_t)(rowMap ? rowMap[orig] : orig) * stride;
+        for (int i = lane; i < S * nR; i += 32) sGi[i] = gi[i];
+    }
+    __syncwarp();
     const float rcr = tab->rcr, kf = kPi / rcr;
+    const bool vec = (nR & 3) == 0 && (stride & 3) == 0 && ((reinterpret_cast<uintptr_t>(grad) & 15) == 0);
+    float fx = 0.0f, fy = 0.0f, fz = 0.0f;
     for (int q = lane; q < cnt; q += 32) {
         const int j = rowRad[(size_t)p * capR + q];
         const float4 cj = sorted[j];
+        const int oj = sortedOrig[j];
+        const float* gj = grad + (size_t)(rowMap ? rowMap[oj] : oj) * stride + sp * nR;
         float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
         const float r = sqrtf(min_image_mul(g, dx, dy, dz));
         const float ir = 1.0f / r;
         float sn, cs;
         sincosf(r * kf, &sn, &cs);
-        sux[q] = dx * ir; suy[q] = dy * ir; suz[q] = dz * ir; sr[q] = r;
-        sfc[q] = 0.5f * cs + 0.5f;
-        sdfc[q] = -0.5f * kf * sn;
-        const int oj = sortedOrig[j];
-        srow[q] = rowMap ? rowMap[oj] : oj;
-    }
-    __syncwarp();
-    const int orig = sortedOrig[p];
-    const float* gi = grad + (size_t)(rowMap ? rowMap[orig] : orig) * stride;
-    float fx = 0.0f, fy = 0.0f, fz = 0.0f;
-    for (int k0 = 0; k0 < nR; k0 += 32) {
-        const int kk = min(nR - k0, 32);
-        int KP = 1;
-        while (KP < kk) KP <<= 1;
-        const int H = 32 / KP, k = lane % KP, h = lane / KP;
-        const bool kval = k < kk;
-        const float eta2 = kval ? sEtaL2[k0 + k] : 0.0f, eta = kval ? sEta[k0 + k] : 0.0f, shf = kval ? sShf[k0 + k] : 0.0f;
-        for (int s = 0; s < S; s++) {
-            const int b = off[s], e = min(off[s + 1], capR);
-            if (b >= e) continue;
-            const float gc = kval ? gi[s * nR + k0 + k] : 0.0f;
-            for (int q = b + h; q < e; q += H) {
-                const float t = sr[q] - shf;
-                const float ex = ex2a(-eta2 * t * t);
-                const float dv = ex * (sdfc[q] - 2.0f * eta * t * sfc[q]);
-                const float gj = kval ? grad[(size_t)srow[q] * stride + sp * nR + k0 + k] : 0.0f;
-                const float wgt = (gc + gj) * dv;
-                fx = fmaf(wgt, sux[q], fx); fy = fmaf(wgt, suy[q], fy); fz = fmaf(wgt, suz[q], fz);
+        const float fc = 0.5f * cs + 0.5f, dfc = -0.5f * kf * sn;
+        const float* gi = sGi + __float_as_int(cj.w) * nR;
+        float wsum = 0.0f;
+        if (vec) {
+            for (int k0 = 0; k0 < nR; k0 += 16) {
+                float4 gv[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    gv[u] = (k0 + 4 * u < nR) ? __ldg(reinterpret_cast<const float4*>(gj + k0 + 4 * u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const float gq[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int k = k0 + 4 * u + e;
+                        if (k < nR) {
+                            const float t = r - sShf[k];
+                            const float ex = ex2a(-sEtaL2[k] * t * t);
+                            wsum = fmaf(gi[k] + gq[e], ex * (dfc - 2.0f * sEta[k] * t * fc), wsum);
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int k = 0; k < nR; k++) {
+                const float t = r - sShf[k];
+                const float ex = ex2a(-sEtaL2[k] * t * t);
+                wsum = fmaf(gi[k] + gj[k], ex * (dfc - 2.0f * sEta[k] * t * fc), wsum);
             }
         }
+        const float wr = wsum * ir;
+        fx = fmaf(wr, dx, fx); fy = fmaf(wr, dy, fy); fz = fmaf(wr, dz, fz);
     }
     fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
     if (lane == 0) {
@@ -752,7 +795,7 @@ void AniAev::backward(const float* radialGrad, int radialStride, const float* an
     NNP_REQUIRE(haveForward_, "backward() called before forward()");
     const int grid = (n_ + kWPB - 1) / kWPB;
     if (tabHost_.nRadial > 0) {
-        const size_t smem = (size_t)kWPB * 7 * capR_ * sizeof(float);
+        const size_t smem = (size_t)kWPB * tabHost_.nSpecies * tabHost_.nRadial * sizeof(float);
         set_smem(ani_radial_bwd_kernel, smem);
         ani_radial_bwd_kernel<<<grid, kWPB * 32, smem, stream>>>(n_, cells_.sorted, cells_.sortedOrig, cells_.geom, tab_, rowRad_, offRad_,
                                                                  capR_, rowMap_, radialGrad, radialStride, positionGrad);
