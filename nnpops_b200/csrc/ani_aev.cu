@@ -256,7 +256,7 @@ __device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
 }
 
 template <int MODE, int NSA, int NSZ, bool TORCHANI>
-__global__ void __launch_bounds__(kWPB * 32)
+__global__ void __launch_bounds__(kWPB * 32, 3)
 ani_angular_fwd_kernel(int n, const float4* __restrict__ sorted, const int* __restrict__ sortedOrig, const Geom* __restrict__ geom,
                        const AniTables* __restrict__ tab, const int* __restrict__ rowAng, const int* __restrict__ offAng, int capA,
                        const int* __restrict__ rowMap, AevOut out, int stride) {
@@ -379,8 +379,7 @@ ani_angular_fwd_kernel(int n, const float4* __restrict__ sorted, const int* __re
 // ------------------------------------------------------------------------------------------------------------------
 // Radial backward, gather-only: dE/dx_i = -sum_j w_ij delta_ij / r_ij with
 // w_ij = scale * sum_k (G[i][s_j][k] + G[j][s_i][k]) * exp(..)(fc' - 2 eta (r - Rs_k) fc)   (CpuANISymmetryFunctions.cpp:228-263).
-// Every directed pair is evaluated by its centre, so there are no atomics and the result is a plain store that also
-// initialises positionGrad for the angular kernel that follows on the same stream.
+// Every directed pair is evaluated by its centre: no atomics inside the pair loop, one accumulate per centre at the end.
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWPB * 32)
 ani_radial_bwd_kernel(int n, const float4* __restrict__ sorted, const int* __restrict__ sortedOrig, const Geom* __restrict__ geom,
@@ -456,9 +455,10 @@ ani_radial_bwd_kernel(int n, const float4* __restrict__ sorted, const int* __res
         fx = fmaf(wr, dx, fx); fy = fmaf(wr, dy, fy); fz = fmaf(wr, dz, fz);
     }
     fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
-    if (lane == 0) {
+    if (lane == 0) {   // accumulated (not stored): the angular kernel adds into the same zero-initialised array concurrently
         const float sc = -tab->radialScale;
-        posGrad[3 * (size_t)orig] = sc * fx; posGrad[3 * (size_t)orig + 1] = sc * fy; posGrad[3 * (size_t)orig + 2] = sc * fz;
+        atomicAdd(posGrad + 3 * (size_t)orig, sc * fx); atomicAdd(posGrad + 3 * (size_t)orig + 1, sc * fy);
+        atomicAdd(posGrad + 3 * (size_t)orig + 2, sc * fz);
     }
 }
 
@@ -732,11 +732,17 @@ AniAev::AniAev(int numAtoms, int numSpecies, float rcr, float rca, const int* at
     NNP_CUDA_CHECK(cudaMalloc(&flag_, sizeof(int)));
     NNP_CUDA_CHECK(cudaMemset(flag_, 0, sizeof(int)));
     NNP_CUDA_CHECK(cudaMalloc(&counters_, 2 * sizeof(unsigned long long)));
+    NNP_CUDA_CHECK(cudaStreamCreateWithFlags(&aux_, cudaStreamNonBlocking));
+    NNP_CUDA_CHECK(cudaEventCreateWithFlags(&evFork_, cudaEventDisableTiming));
+    NNP_CUDA_CHECK(cudaEventCreateWithFlags(&evJoin_, cudaEventDisableTiming));
 }
 
 AniAev::~AniAev() {
     cudaFree(tab_); cudaFree(species_); cudaFree(rowRad_); cudaFree(rowAng_); cudaFree(offRad_); cudaFree(offAng_);
     cudaFree(flag_); cudaFree(counters_);
+    if (aux_) cudaStreamDestroy(aux_);
+    if (evFork_) cudaEventDestroy(evFork_);
+    if (evJoin_) cudaEventDestroy(evJoin_);
     cells_.release();
 }
 
@@ -771,13 +777,22 @@ void AniAev::forward(const float* positions, const float* box, float* radial, in
         count_launch();
     }
     if (ev) cudaEventRecord(ev[0], stream);
+    // The radial and angular kernels are independent (disjoint outputs) and individually latency-bound: fork the radial kernel
+    // onto the auxiliary stream so the two run concurrently, join before returning.
+    const bool fork = tabHost_.nRadial > 0 && tabHost_.nAngular > 0;
+    cudaStream_t rs = fork ? aux_ : stream;
+    if (fork) {
+        NNP_CUDA_CHECK(cudaEventRecord(evFork_, stream));
+        NNP_CUDA_CHECK(cudaStreamWaitEvent(aux_, evFork_, 0));
+    }
     if (tabHost_.nRadial > 0) {
         const size_t smem = (size_t)kWPB * 2 * capR_ * sizeof(float);
         set_smem(ani_radial_fwd_kernel, smem);
-        ani_radial_fwd_kernel<<<grid, kWPB * 32, smem, stream>>>(n_, cells_.sorted, cells_.sortedOrig, cells_.geom, tab_, rowRad_, offRad_,
-                                                                 capR_, rowMap_, radialOut, radialStride);
+        ani_radial_fwd_kernel<<<grid, kWPB * 32, smem, rs>>>(n_, cells_.sorted, cells_.sortedOrig, cells_.geom, tab_, rowRad_, offRad_,
+                                                             capR_, rowMap_, radialOut, radialStride);
         count_launch();
     }
+    if (fork) NNP_CUDA_CHECK(cudaEventRecord(evJoin_, aux_));
     if (ev) cudaEventRecord(ev[1], stream);
     if (tabHost_.nAngular > 0) {
         const size_t smem = (size_t)kWPB * 6 * capA_ * sizeof(float);
@@ -785,6 +800,7 @@ void AniAev::forward(const float* positions, const float* box, float* radial, in
                      angularOut, angularStride);
         count_launch();
     }
+    if (fork) NNP_CUDA_CHECK(cudaStreamWaitEvent(stream, evJoin_, 0));
     NNP_CUDA_CHECK(cudaGetLastError());
     haveForward_ = true;
 }
@@ -794,15 +810,21 @@ void AniAev::backward(const float* radialGrad, int radialStride, const float* an
     if (n_ == 0) return;
     NNP_REQUIRE(haveForward_, "backward() called before forward()");
     const int grid = (n_ + kWPB - 1) / kWPB;
+    NNP_CUDA_CHECK(cudaMemsetAsync(positionGrad, 0, sizeof(float) * 3 * n_, stream));
+    const bool fork = tabHost_.nRadial > 0 && tabHost_.nAngular > 0;
+    cudaStream_t rs = fork ? aux_ : stream;
+    if (fork) {
+        NNP_CUDA_CHECK(cudaEventRecord(evFork_, stream));
+        NNP_CUDA_CHECK(cudaStreamWaitEvent(aux_, evFork_, 0));
+    }
     if (tabHost_.nRadial > 0) {
         const size_t smem = (size_t)kWPB * tabHost_.nSpecies * tabHost_.nRadial * sizeof(float);
         set_smem(ani_radial_bwd_kernel, smem);
-        ani_radial_bwd_kernel<<<grid, kWPB * 32, smem, stream>>>(n_, cells_.sorted, cells_.sortedOrig, cells_.geom, tab_, rowRad_, offRad_,
-                                                                 capR_, rowMap_, radialGrad, radialStride, positionGrad);
+        ani_radial_bwd_kernel<<<grid, kWPB * 32, smem, rs>>>(n_, cells_.sorted, cells_.sortedOrig, cells_.geom, tab_, rowRad_, offRad_,
+                                                             capR_, rowMap_, radialGrad, radialStride, positionGrad);
         count_launch();
-    } else {
-        NNP_CUDA_CHECK(cudaMemsetAsync(positionGrad, 0, sizeof(float) * 3 * n_, stream));
     }
+    if (fork) NNP_CUDA_CHECK(cudaEventRecord(evJoin_, aux_));
     if (ev) cudaEventRecord(ev[0], stream);
     if (tabHost_.nAngular > 0) {
         const int gPitch = tabHost_.nAngular + 1;
@@ -812,6 +834,7 @@ void AniAev::backward(const float* radialGrad, int radialStride, const float* an
                      angularGrad, angularStride, positionGrad, gPitch);
         count_launch();
     }
+    if (fork) NNP_CUDA_CHECK(cudaStreamWaitEvent(stream, evJoin_, 0));
     NNP_CUDA_CHECK(cudaGetLastError());
 }
 

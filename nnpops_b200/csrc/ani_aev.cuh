@@ -79,6 +79,8 @@ private:
     unsigned long long* counters_ = nullptr;   // [2] scratch for countTriples / countRadialPairs
     const int* rowMap_ = nullptr;
     bool haveForward_ = false;
+    cudaStream_t aux_ = nullptr;            // radial kernels run here, concurrently with the angular kernels on the caller's stream
+    cudaEvent_t evFork_ = nullptr, evJoin_ = nullptr;
 };
 
 }  // namespace nnpops

@@ -7,8 +7,9 @@
 //     order z, y, x (getNeighborPairsCPU.cpp:65-69), inclusive cutoff  distance <= cutoff (:73,81);
 //   * max_num_pairs == -1: output length N(N-1)/2, slot = row(row-1)/2 + col, misses are -1 / NaN;
 //   * max_num_pairs  >  0: compacted list padded with -1 / NaN, pairs beyond the capacity dropped.
-// Unlike the reference CUDA path the compacted list is deterministic: pass 1 counts the pairs each row atom owns, an exclusive
-// scan gives its offset, pass 2 writes them (ballot compaction inside the warp), so the order depends only on the input.
+// Unlike the reference CUDA path the compacted list is deterministic: pass 1 counts the pairs each atom owns (the atom with the
+// smaller cell-sorted index owns the pair), an exclusive scan gives its offset, pass 2 writes them (ballot compaction inside the
+// warp), so the order depends only on the input.
 // num_found always holds the number of pairs inside the cutoff (the reference CUDA path leaves it 0 in all-pairs mode).
 #include <map>
 #include <mutex>
@@ -81,21 +82,29 @@ pairs_kernel(int n, const T* __restrict__ pos, const T* __restrict__ boxPtr, con
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = blockIdx.x * kWPB + w;
     if (p >= n) return;
-    const int row = sortedOrig[p];
-    const T pr[3] = {pos[3 * (size_t)row], pos[3 * (size_t)row + 1], pos[3 * (size_t)row + 2]};
+    // Half shell in sorted order: the unordered pair {p, q} is handled by the atom with the smaller sorted index, so every pair is
+    // tested once.  A cheap fp32 pre-test on the sorted coordinates (multiply-by-reciprocal minimum image, 1 % margin) discards
+    // the ~85 % of candidates that are clearly outside the cutoff before the exact reference arithmetic (divisions) runs.
+    const int op = sortedOrig[p];
+    const float4 cp = sorted[p];
+    const T pp[3] = {pos[3 * (size_t)op], pos[3 * (size_t)op + 1], pos[3 * (size_t)op + 2]};
+    const float pre2 = (float)cutoff * (float)cutoff * 1.0201f;
     long long cursor = (MODE == 1) ? offsets[p] : 0;
     int mine = 0;
     for_each_candidate_run(g, cellStart, sortedCell[p], [&](int b, int e) {
-        for (int q0 = b; q0 < e; q0 += 32) {
+        for (int q0 = max(b, p + 1); q0 < e; q0 += 32) {
             const int q = q0 + lane;
             bool ok = false;
-            int col = -1;
+            int row = -1, col = -1;
             T dx = 0, dy = 0, dz = 0, d = 0;
-            if (q < e) {
-                col = sortedOrig[q];
-                if (col < row) {
-                    const T pc[3] = {pos[3 * (size_t)col], pos[3 * (size_t)col + 1], pos[3 * (size_t)col + 2]};
-                    d = pair_delta<T>(bx, pr, pc, dx, dy, dz);
+            if (q < e && q > p) {
+                const float4 cq = sorted[q];
+                float ax = cq.x - cp.x, ay = cq.y - cp.y, az = cq.z - cp.z;
+                if (min_image_mul(g, ax, ay, az) <= pre2) {
+                    const int oq = sortedOrig[q];
+                    const T pq[3] = {pos[3 * (size_t)oq], pos[3 * (size_t)oq + 1], pos[3 * (size_t)oq + 2]};
+                    if (oq > op) { row = oq; col = op; d = pair_delta<T>(bx, pq, pp, dx, dy, dz); }
+                    else         { row = op; col = oq; d = pair_delta<T>(bx, pp, pq, dx, dy, dz); }
                     ok = d <= cutoff;
                 }
             }
