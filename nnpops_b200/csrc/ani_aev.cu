@@ -42,20 +42,22 @@ __device__ __forceinline__ void store_aev(const AevOut& o, size_t idx, float v) 
 // zero `count` consecutive AEV elements starting at idx (warp-cooperative); 16-byte stores when the range allows it
 __device__ __forceinline__ void zero_aev_range(const AevOut& o, size_t idx, int count, int lane) {
     if (o.hi) {
-        if ((count & 7) == 0 && (idx & 7) == 0) {
+        __half* hi = o.hi + idx;
+        __half* lo = o.lo + idx;
+        if ((count & 7) == 0 && ((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0) {
             const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-            for (int i = lane * 8; i < count; i += 256) {
-                *reinterpret_cast<uint4*>(o.hi + idx + i) = z;
-                *reinterpret_cast<uint4*>(o.lo + idx + i) = z;
-            }
+            const int units = count >> 3;                      // 16-byte units per array
+            for (int u = lane; u < units; u += 32) { reinterpret_cast<uint4*>(hi)[u] = z; reinterpret_cast<uint4*>(lo)[u] = z; }
         } else {
-            for (int i = lane; i < count; i += 32) { o.hi[idx + i] = __float2half_rn(0.0f); o.lo[idx + i] = __float2half_rn(0.0f); }
+            for (int i = lane; i < count; i += 32) { hi[i] = __float2half_rn(0.0f); lo[i] = __float2half_rn(0.0f); }
         }
     } else {
-        if ((count & 3) == 0 && (idx & 3) == 0) {
-            for (int i = lane * 4; i < count; i += 128) *reinterpret_cast<float4*>(o.f32 + idx + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* f = o.f32 + idx;
+        if ((count & 3) == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0) {
+            const int units = count >> 2;
+            for (int u = lane; u < units; u += 32) reinterpret_cast<float4*>(f)[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
-            for (int i = lane; i < count; i += 32) o.f32[idx + i] = 0.0f;
+            for (int i = lane; i < count; i += 32) f[i] = 0.0f;
         }
     }
 }
@@ -322,10 +324,11 @@ ani_angular_fwd_kernel(int n, const float4* __restrict__ sorted, const int* __re
                     const int qq = valid ? q : 0;
                     int ia, ib;
                     if (s == t) {   // unordered pairs a < b inside one segment: qq = b(b-1)/2 + a
-                        int b = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)qq)) * 0.5f);
-                        while ((b * (b - 1)) / 2 > qq) b--;
-                        while ((b * (b + 1)) / 2 <= qq) b++;
-                        ia = bs + qq - (b * (b - 1)) / 2; ib = bs + b;
+                        // b = floor((1 + sqrt(1 + 8 q)) / 2) from an approximate root, fixed by one exact integer comparison each way
+                        int b = (int)fmaf(__fsqrt_rn(fmaf(8.0f, (float)qq, 1.0f)), 0.5f, 0.5f);
+                        b -= ((b * (b - 1)) >> 1) > qq ? 1 : 0;
+                        b += ((b * (b + 1)) >> 1) <= qq ? 1 : 0;
+                        ia = bs + qq - ((b * (b - 1)) >> 1); ib = bs + b;
                     } else {
                         const int a = (int)(((float)qq + 0.5f) * invNt);   // exact: the quotient is >= 0.5/nt away from an integer
                         ia = bs + a; ib = bt + qq - a * nt;

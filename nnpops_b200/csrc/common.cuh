@@ -41,22 +41,25 @@ struct Geom {
 // Minimum-image displacement, "multiply by reciprocal" flavour used by ANI and CFConv
 // (CpuANISymmetryFunctions.cpp:355-379, CpuCFConv.cpp:30-55).  Explicit round-to-nearest intrinsics keep nvcc from
 // contracting into FMAs, so r2 is bit-identical to the reference CPU arithmetic and cutoff decisions cannot differ.
+// rintf (one FRND) replaces the reference's round(): the two differ only on exact ties |delta * inv| = k + 0.5, where both
+// images have the same |delta| (= half the box), hence the same r2; such a pair can only be inside the cutoff when the box is
+// narrower than two cutoffs, which the reference excludes.
 __device__ __forceinline__ float min_image_mul(const Geom& g, float& dx, float& dy, float& dz) {
     if (g.periodic) {
         if (g.triclinic) {
-            float s3 = roundf(__fmul_rn(dz, g.inv[2]));
+            float s3 = rintf(__fmul_rn(dz, g.inv[2]));
             dx = __fsub_rn(dx, __fmul_rn(s3, g.box[6]));
             dy = __fsub_rn(dy, __fmul_rn(s3, g.box[7]));
             dz = __fsub_rn(dz, __fmul_rn(s3, g.box[8]));
-            float s2 = roundf(__fmul_rn(dy, g.inv[1]));
+            float s2 = rintf(__fmul_rn(dy, g.inv[1]));
             dx = __fsub_rn(dx, __fmul_rn(s2, g.box[3]));
             dy = __fsub_rn(dy, __fmul_rn(s2, g.box[4]));
-            float s1 = roundf(__fmul_rn(dx, g.inv[0]));
+            float s1 = rintf(__fmul_rn(dx, g.inv[0]));
             dx = __fsub_rn(dx, __fmul_rn(s1, g.box[0]));
         } else {
-            dx = __fsub_rn(dx, __fmul_rn(roundf(__fmul_rn(dx, g.inv[0])), g.box[0]));
-            dy = __fsub_rn(dy, __fmul_rn(roundf(__fmul_rn(dy, g.inv[1])), g.box[4]));
-            dz = __fsub_rn(dz, __fmul_rn(roundf(__fmul_rn(dz, g.inv[2])), g.box[8]));
+            dx = __fsub_rn(dx, __fmul_rn(rintf(__fmul_rn(dx, g.inv[0])), g.box[0]));
+            dy = __fsub_rn(dy, __fmul_rn(rintf(__fmul_rn(dy, g.inv[1])), g.box[4]));
+            dz = __fsub_rn(dz, __fmul_rn(rintf(__fmul_rn(dz, g.inv[2])), g.box[8]));
         }
     }
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
