@@ -62,6 +62,33 @@ __device__ __forceinline__ void zero_aev_range(const AevOut& o, size_t idx, int 
     }
 }
 
+// zero the blocks [p*nA, (p+1)*nA) of one AEV row for every pair p whose bit is set in emptyMask (nPairs <= 32): one pass of
+// 16-byte stores over the row instead of one call per empty block
+__device__ __forceinline__ void zero_aev_blocks(const AevOut& o, size_t rowIdx, int nA, int nPairs, unsigned emptyMask, int lane) {
+    const int total = nPairs * nA;
+    if (o.hi) {
+        __half* hi = o.hi + rowIdx;
+        __half* lo = o.lo + rowIdx;
+        if ((nA & 7) == 0 && ((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0) {
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            for (int u = lane; u < (total >> 3); u += 32)
+                if ((emptyMask >> ((u << 3) / nA)) & 1u) { reinterpret_cast<uint4*>(hi)[u] = z; reinterpret_cast<uint4*>(lo)[u] = z; }
+        } else {
+            for (int i = lane; i < total; i += 32)
+                if ((emptyMask >> (i / nA)) & 1u) { hi[i] = __float2half_rn(0.0f); lo[i] = __float2half_rn(0.0f); }
+        }
+    } else {
+        float* f = o.f32 + rowIdx;
+        if ((nA & 3) == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0) {
+            for (int u = lane; u < (total >> 2); u += 32)
+                if ((emptyMask >> ((u << 2) / nA)) & 1u) reinterpret_cast<float4*>(f)[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            for (int i = lane; i < total; i += 32)
+                if ((emptyMask >> (i / nA)) & 1u) f[i] = 0.0f;
+        }
+    }
+}
+
 __device__ __forceinline__ int pair_index(int S, int s, int t) {   // CpuANISymmetryFunctions.cpp:39-43
     int lo = min(s, t), hi = max(s, t);
     return lo * S - (lo * (lo - 1)) / 2 + (hi - lo);
@@ -297,12 +324,15 @@ ani_angular_fwd_kernel(int n, const float4* __restrict__ sorted, const int* __re
     // angular neighbours are skipped wholesale and their output blocks zero-filled with wide stores
     const int myB = lane < S ? min(off[lane], capA) : 0;
     const int myN = (lane < S ? min(off[lane + 1], capA) : 0) - myB;
+    const int nPairs = tab->nPairs;
+    const bool maskZero = nPairs <= 32;      // empty blocks are collected in a bit mask and zero-filled in one pass at the end
+    unsigned nonEmpty = 0u;
     for (int m0 = 0; m0 < nA; m0 += 32) {
         int pIdx = 0;
         for (int s = 0; s < S; s++) {
             const int bs = __shfl_sync(kFull, myB, s), ns = __shfl_sync(kFull, myN, s);
             if (ns == 0) {   // every pair (s, t >= s) is empty
-                if (m0 == 0) zero_aev_range(out, orow + (size_t)pIdx * nA, (S - s) * nA, lane);
+                if (m0 == 0 && !maskZero) zero_aev_range(out, orow + (size_t)pIdx * nA, (S - s) * nA, lane);
                 pIdx += S - s;
                 continue;
             }
@@ -311,9 +341,10 @@ ani_angular_fwd_kernel(int n, const float4* __restrict__ sorted, const int* __re
                 const int ntrip = (s == t) ? (ns * (ns - 1)) / 2 : ns * nt;
                 const size_t dst = orow + (size_t)pIdx * nA + m0;
                 if (ntrip <= 0) {
-                    if (m0 == 0) zero_aev_range(out, orow + (size_t)pIdx * nA, nA, lane);
+                    if (m0 == 0 && !maskZero) zero_aev_range(out, orow + (size_t)pIdx * nA, nA, lane);
                     continue;
                 }
+                if (maskZero) nonEmpty |= 1u << pIdx;
                 const float invNt = 1.0f / (float)nt;
                 float acc[32];
 #pragma unroll
@@ -377,6 +408,7 @@ ani_angular_fwd_kernel(int n, const float4* __restrict__ sorted, const int* __re
             }
         }
     }
+    if (maskZero) zero_aev_blocks(out, orow, nA, nPairs, ~nonEmpty, lane);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
