@@ -91,39 +91,62 @@ pairs_kernel(int n, const T* __restrict__ pos, const T* __restrict__ boxPtr, con
     const float pre2 = (float)cutoff * (float)cutoff * 1.0201f;
     long long cursor = (MODE == 1) ? offsets[p] : 0;
     int mine = 0;
+    // Survivors of the pre-test are queued (ballot compaction, scan order preserved) and the exact test runs on full batches of
+    // 32, so the divisions of the reference arithmetic execute on dense lanes instead of the ~15 % that survive each sweep.
+    __shared__ int queueAll[kWPB][64];
+    int* queue = queueAll[w];
+    int queued = 0;
+    auto drain = [&](int count) {   // exact test + output for queue[0 .. count)
+        bool ok = false;
+        int row = -1, col = -1;
+        T dx = 0, dy = 0, dz = 0, d = 0;
+        if (lane < count) {
+            const int oq = sortedOrig[queue[lane]];
+            const T pq[3] = {pos[3 * (size_t)oq], pos[3 * (size_t)oq + 1], pos[3 * (size_t)oq + 2]};
+            if (oq > op) { row = oq; col = op; d = pair_delta<T>(bx, pq, pp, dx, dy, dz); }
+            else         { row = op; col = oq; d = pair_delta<T>(bx, pp, pq, dx, dy, dz); }
+            ok = d <= cutoff;
+        }
+        const unsigned m = __ballot_sync(kFull, ok);
+        if (MODE != 0 && ok) {
+            long long slot;
+            if (MODE == 1) slot = cursor + __popc(m & ((1u << lane) - 1u));
+            else slot = (long long)row * (row - 1) / 2 + col;
+            if (slot < capacity) {
+                neighbors[slot] = row;
+                neighbors[capacity + slot] = col;
+                deltas[3 * slot] = dx; deltas[3 * slot + 1] = dy; deltas[3 * slot + 2] = dz;
+                distances[slot] = d;
+            }
+        }
+        cursor += __popc(m);
+        mine += __popc(m);
+    };
     for_each_candidate_run(g, cellStart, sortedCell[p], [&](int b, int e) {
         for (int q0 = max(b, p + 1); q0 < e; q0 += 32) {
             const int q = q0 + lane;
-            bool ok = false;
-            int row = -1, col = -1;
-            T dx = 0, dy = 0, dz = 0, d = 0;
-            if (q < e && q > p) {
+            bool keep = false;
+            if (q < e) {
                 const float4 cq = sorted[q];
                 float ax = cq.x - cp.x, ay = cq.y - cp.y, az = cq.z - cp.z;
-                if (min_image_mul(g, ax, ay, az) <= pre2) {
-                    const int oq = sortedOrig[q];
-                    const T pq[3] = {pos[3 * (size_t)oq], pos[3 * (size_t)oq + 1], pos[3 * (size_t)oq + 2]};
-                    if (oq > op) { row = oq; col = op; d = pair_delta<T>(bx, pq, pp, dx, dy, dz); }
-                    else         { row = op; col = oq; d = pair_delta<T>(bx, pp, pq, dx, dy, dz); }
-                    ok = d <= cutoff;
-                }
+                keep = min_image_mul(g, ax, ay, az) <= pre2;
             }
-            const unsigned m = __ballot_sync(kFull, ok);
-            if (MODE != 0 && ok) {
-                long long slot;
-                if (MODE == 1) slot = cursor + __popc(m & ((1u << lane) - 1u));
-                else slot = (long long)row * (row - 1) / 2 + col;
-                if (slot < capacity) {
-                    neighbors[slot] = row;
-                    neighbors[capacity + slot] = col;
-                    deltas[3 * slot] = dx; deltas[3 * slot + 1] = dy; deltas[3 * slot + 2] = dz;
-                    distances[slot] = d;
-                }
+            const unsigned m = __ballot_sync(kFull, keep);
+            if (keep) queue[queued + __popc(m & ((1u << lane) - 1u))] = q;
+            queued += __popc(m);
+            __syncwarp();
+            if (queued >= 32) {
+                drain(32);
+                __syncwarp();
+                const int carry = (lane < queued - 32) ? queue[32 + lane] : 0;
+                __syncwarp();
+                if (lane < queued - 32) queue[lane] = carry;
+                queued -= 32;
+                __syncwarp();
             }
-            cursor += __popc(m);
-            mine += __popc(m);
         }
     });
+    if (queued > 0) drain(queued);
     if (lane == 0) {
         if (MODE == 0) counts[p] = mine;
         if (MODE == 2 && mine) atomicAdd(found, (unsigned long long)mine);
