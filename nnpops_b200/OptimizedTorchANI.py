@@ -208,3 +208,24 @@ class OptimizedTorchANI(torch.nn.Module):
                 raise ValueError('Only fully periodic systems are supported, i.e. pbc = [True, True, True]')
         energies = self.fused(coordinates[0], cell)
         return SpeciesEnergies(self.species, energies.double() + self.self_energies.to(energies.device))
+
+
+class ScriptableFusedANI(torch.nn.Module):
+    """TorchScript-able form of FusedANI: the same fused pipeline behind the custom class ``NNPOpsFusedANI::Holder`` and the autograd
+    op ``NNPOpsFusedANI::operation`` of libNNPOpsPyTorch.so, so a scripted / saved module (e.g. for openmm-torch's TorchForce) runs the
+    species-grouped tensor-core path.  ``forward(positions[N, 3], cell[3, 3] or None) -> energy[1]``; forces by autograd."""
+
+    def __init__(self, num_species: int, Rcr: float, Rca: float, EtaR, ShfR, EtaA, Zeta, ShfA, ShfZ, species: Sequence[int], networks,
+                 mlp_impl: str = "tcgen05"):
+        super().__init__()
+        from . import torch_ops
+        torch_ops.load()
+        dims, params = pack_network_params(networks)
+        self.holder = torch.classes.NNPOpsFusedANI.Holder(int(num_species), float(Rcr), float(Rca), [float(x) for x in EtaR],
+                                                          [float(x) for x in ShfR], [float(x) for x in EtaA], [float(x) for x in Zeta],
+                                                          [float(x) for x in ShfA], [float(x) for x in ShfZ], [int(x) for x in species],
+                                                          len(networks[0]), [int(x) for x in dims.reshape(-1)], torch.from_numpy(params),
+                                                          {"simt": 0, "tcgen05": 1}[mlp_impl])
+
+    def forward(self, positions: Tensor, cell: Optional[Tensor] = None) -> Tensor:
+        return torch.ops.NNPOpsFusedANI.operation(self.holder, positions, cell)

@@ -398,7 +398,111 @@ public:
     }
 };
 
+// ---------------------------------------------------------------------------------------------- fused ANI model (extension)
+// Not part of the reference surface: the scalable sibling of OptimizedTorchANI (SURVEY.md section 8b "mismatch list" / 8f.2) as a
+// TorchScript-able custom class, so that a scripted module (e.g. for openmm-torch) can use the species-grouped tensor-core path.
+class FusedAniHolder : public torch::CustomClassHolder {
+public:
+    FusedAniHolder(int64_t numSpecies, double Rcr, double Rca, const std::vector<double>& EtaR, const std::vector<double>& ShfR,
+                   const std::vector<double>& EtaA, const std::vector<double>& Zeta, const std::vector<double>& ShfA,
+                   const std::vector<double>& ShfZ, const std::vector<int64_t>& atomSpecies, int64_t ensembleSize,
+                   const std::vector<int64_t>& dims, const Tensor& params, int64_t mlpImpl)
+        : numSpecies(numSpecies), Rcr(Rcr), Rca(Rca), EtaR(EtaR), ShfR(ShfR), EtaA(EtaA), Zeta(Zeta), ShfA(ShfA), ShfZ(ShfZ),
+          atomSpecies(atomSpecies), ensembleSize(ensembleSize), dims(dims), params(params.detach().to(torch::kCPU, torch::kFloat32).contiguous()),
+          mlpImpl(mlpImpl) {
+        TORCH_CHECK(numSpecies > 0 && dims.size() % (size_t)numSpecies == 0 && dims.size() / numSpecies >= 3,
+                    "dims must hold numSpecies rows of numLayers+1 layer sizes");
+    }
+    ~FusedAniHolder() override { nnpops_ani_model_destroy(impl); }
+
+    // -> {energy [1], dE/dpositions [N, 3]}
+    tensor_list evaluate(const Tensor& positions, const c10::optional<Tensor>& cellOpt) {
+        if (positions.scalar_type() != torch::kFloat32) throw std::runtime_error("The type of \"positions\" has to be float32");
+        if (positions.dim() != 2 || positions.size(0) != (int64_t)atomSpecies.size() || positions.size(1) != 3)
+            throw std::runtime_error("The shape of \"positions\" has to be (" + std::to_string(atomSpecies.size()) + ", 3)");
+        require_cuda(positions, "positions");
+        c10::cuda::CUDAGuard guard(positions.device());
+        Tensor cell;
+        if (cellOpt) {
+            cell = cellOpt->to(positions.options()).contiguous();
+            TORCH_CHECK(cell.dim() == 2 && cell.size(0) == 3 && cell.size(1) == 3, "The shape of \"cell\" has to be (3, 3)");
+        }
+        if (!impl) {
+            device = positions.device();
+            std::vector<float> radialFn, angularFn;
+            for (const float eta : EtaR)
+                for (const float rs : ShfR) { radialFn.push_back(eta); radialFn.push_back(rs); }
+            for (const float eta : EtaA)
+                for (const float zeta : Zeta)
+                    for (const float rs : ShfA)
+                        for (const float thetas : ShfZ) { angularFn.push_back(eta); angularFn.push_back(rs); angularFn.push_back(zeta); angularFn.push_back(thetas); }
+            std::vector<int> species(atomSpecies.begin(), atomSpecies.end()), d(dims.begin(), dims.end());
+            const int numLayers = (int)(dims.size() / numSpecies) - 1;
+            check(nnpops_ani_model_create(&impl, (int)species.size(), (int)numSpecies, (float)Rcr, (float)Rca, species.data(), (int)radialFn.size() / 2,
+                                          radialFn.data(), (int)angularFn.size() / 4, angularFn.data(), (int)ensembleSize, numLayers, d.data(),
+                                          params.data_ptr<float>(), (int)mlpImpl, 0, 0));
+        }
+        if (positions.device() != device) throw std::runtime_error("The device of \"positions\" has changed");
+        const Tensor pos = positions.contiguous();
+        Tensor energy = torch::empty({1}, pos.options()), grad = torch::empty_like(pos);
+        check(nnpops_ani_model_energy_grad(impl, pos.data_ptr<float>(), cellOpt ? cell.data_ptr<float>() : nullptr, energy.data_ptr<float>(),
+                                           grad.data_ptr<float>(), stream_of(pos)));
+        return {energy, grad};
+    }
+
+    using State = std::tuple<int64_t, double, double, std::vector<double>, std::vector<double>, std::vector<double>, std::vector<double>,
+                             std::vector<double>, std::vector<double>, std::vector<int64_t>, int64_t, std::vector<int64_t>, Tensor, int64_t>;
+    State state() const {
+        return State(numSpecies, Rcr, Rca, EtaR, ShfR, EtaA, Zeta, ShfA, ShfZ, atomSpecies, ensembleSize, dims, params, mlpImpl);
+    }
+
+private:
+    int64_t numSpecies;
+    double Rcr, Rca;
+    std::vector<double> EtaR, ShfR, EtaA, Zeta, ShfA, ShfZ;
+    std::vector<int64_t> atomSpecies;
+    int64_t ensembleSize;
+    std::vector<int64_t> dims;
+    Tensor params;
+    int64_t mlpImpl;
+    torch::Device device = torch::kCPU;
+    nnpops_ani_model_t impl = nullptr;
+};
+
+class FusedAniFunction : public torch::autograd::Function<FusedAniFunction> {
+public:
+    static Tensor forward(AutogradContext* ctx, const c10::intrusive_ptr<FusedAniHolder>& holder, const Tensor& positions,
+                          const c10::optional<Tensor>& cell) {
+        const tensor_list r = holder->evaluate(positions, cell);
+        ctx->save_for_backward({r[1]});
+        return r[0];
+    }
+    static tensor_list backward(AutogradContext* ctx, const tensor_list& grads) {
+        const Tensor g = ctx->get_saved_variables()[0];
+        return {Tensor(), g * grads[0], Tensor()};
+    }
+};
+Tensor fused_ani_operation(const c10::optional<c10::intrusive_ptr<FusedAniHolder>>& holder, const Tensor& positions,
+                           const c10::optional<Tensor>& cell) {
+    return FusedAniFunction::apply(*holder, positions, cell);
+}
+
 }  // namespace
+
+TORCH_LIBRARY(NNPOpsFusedANI, m) {
+    m.class_<FusedAniHolder>("Holder")
+        .def(torch::init<int64_t, double, double, const std::vector<double>&, const std::vector<double>&, const std::vector<double>&,
+                         const std::vector<double>&, const std::vector<double>&, const std::vector<double>&, const std::vector<int64_t>&, int64_t,
+                         const std::vector<int64_t>&, const Tensor&, int64_t>())
+        .def("evaluate", &FusedAniHolder::evaluate)
+        .def_pickle([](const c10::intrusive_ptr<FusedAniHolder>& self) -> FusedAniHolder::State { return self->state(); },
+                    [](FusedAniHolder::State st) -> c10::intrusive_ptr<FusedAniHolder> {
+                        return c10::make_intrusive<FusedAniHolder>(std::get<0>(st), std::get<1>(st), std::get<2>(st), std::get<3>(st), std::get<4>(st),
+                                                                   std::get<5>(st), std::get<6>(st), std::get<7>(st), std::get<8>(st), std::get<9>(st),
+                                                                   std::get<10>(st), std::get<11>(st), std::get<12>(st), std::get<13>(st));
+                    });
+    m.def("operation", fused_ani_operation);
+}
 
 TORCH_LIBRARY(NNPOpsANISymmetryFunctions, m) {
     m.class_<AniHolder>("Holder")

@@ -167,3 +167,28 @@ def test_neighbor_and_pme_ops():
     assert np.allclose(np.array(G["expected_ddirect"]) + np.array(G["expected_drecip"]), pos.grad.cpu().numpy(), rtol=1e-4, atol=1e-3)
     with pytest.raises(RuntimeError):
         torch.ops.neighbors.getNeighborPairs(torch.zeros((4, 3), device="cuda"), 1.0, 1, torch.empty((0, 0), device="cuda"), True)
+
+
+@pytest.mark.gpu
+def test_scriptable_fused_ani_roundtrip_matches_ctypes_path():
+    """The fused model as a TorchScript custom class: script -> save -> load -> energy + autograd forces equal the ctypes FusedANI."""
+    from mlp_ref import random_networks
+    from nnpops_b200.OptimizedTorchANI import FusedANI, ScriptableFusedANI
+    n = 500
+    pos, L = lattice(n, 2.154, 0.3, 3000)
+    species = water_species(n)
+    box = cubic_box(L)
+    nets = random_networks(7, [(64, 64, 32)] * 7, 2, 1008, seed=3)
+    args = (7, 5.2, 3.5, ANI2X["EtaR"], ANI2X["ShfR"], ANI2X["EtaA"], ANI2X["Zeta"], ANI2X["ShfA"], ANI2X["ShfZ"], species, nets)
+    mod = torch.jit.script(ScriptableFusedANI(*args))
+    with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+        mod.save(f.name)
+        mod = torch.jit.load(f.name)
+    p = torch.tensor(pos, device="cuda", requires_grad=True)
+    b = torch.tensor(box, device="cuda")
+    e = mod(p, b)
+    e.sum().backward()
+    ref = FusedANI(*args)
+    e0, g0 = ref.energy_and_gradient(torch.tensor(pos, device="cuda"), b)
+    assert abs(float(e) - float(e0)) <= 1e-6 * abs(float(e0))
+    assert rel_err(p.grad.cpu().numpy(), g0.cpu().numpy()) < 1e-6
