@@ -73,6 +73,7 @@ CASES = {
     "blob1000": (1000, False, "protein", 5.1),
     "box1000": (1000, True, "water", 5.2),
     "box3000_7sp": (3000, True, "all7", 5.1),
+    "protein5000": (5000, False, "protein", 5.1),   # BASELINE config 2 geometry
 }
 
 
@@ -229,3 +230,37 @@ def test_translation_and_linearity_properties_at_scale():
     fa = h.backward(ga).cpu().numpy(); fb = h.backward(gb).cpu().numpy()
     fab = h.backward([ga[0] + 2 * gb[0], ga[1] + 2 * gb[1]]).cpu().numpy()
     assert rel_err(fab, fa + 2 * fb) < 2e-5
+
+
+def test_full_size_box_rows_match_oracle_on_local_clusters():
+    """BASELINE config 3 size (50 000 atoms, periodic, Rcr 5.2): the O(N^2) oracle is too slow for the whole box, but an AEV row only
+    depends on the atoms within Rcr of its centre.  For 48 sampled centres the neighbourhood (explicit periodic images from a
+    KD-tree) is handed to the oracle as a small non-periodic cluster and its centre row compared with the GPU row."""
+    from scipy.spatial import cKDTree
+    from nnpops_b200.SymmetryFunctions import Holder
+    n = 50000
+    pos, L = lattice(n, 2.154, 0.3, 3000)
+    species = water_species(n)
+    box = cubic_box(L)
+    rfn, afn = ani2x_tables()
+    h = Holder.from_function_lists(7, 5.2, 3.5, rfn, afn, list(species))
+    radial, angular = h.forward(dev(pos), dev(box))
+    assert h.overflowed() == 0
+    triples, pairs = h.work()
+    aev = np.concatenate([radial.cpu().numpy(), angular.cpu().numpy()], 1)
+    wrapped = np.mod(pos.astype(np.float64), L)
+    tree = cKDTree(wrapped, boxsize=L)
+    assert abs(tree.count_neighbors(tree, 5.2) - n - 2 * pairs) <= 20      # pair count of the cell list vs an independent KD-tree
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for i in rng.choice(n, 48, replace=False):
+        nb = [j for j in tree.query_ball_point(wrapped[i], 5.6) if j != i]
+        d = wrapped[nb] - wrapped[i]
+        d -= np.round(d / L) * L                                           # explicit minimum images around the centre
+        cluster = np.vstack([np.zeros((1, 3)), d]).astype(np.float32)
+        sp = np.concatenate([[species[i]], species[nb]]).astype(np.int32)
+        r0, a0 = O.ani_forward(cluster, sp, 7, 5.2, 3.5, rfn, afn)
+        row0 = np.concatenate([r0[0], a0[0]])
+        worst = max(worst, np.abs(aev[i] - row0).max() / np.abs(row0).max())
+    print("full-size AEV rows vs oracle clusters: worst rel err %.2e, triples %d, pairs %d" % (worst, triples, pairs))
+    assert worst < 2e-5   # the cluster uses re-centred coordinates, so deltas differ from the box arithmetic by fp32 round-off
