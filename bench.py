@@ -210,8 +210,10 @@ def run_ours(args):
     kern("cell_list+ani_rows_kernel", stages["cells+rows"], n, 64.0 + 4.0 * 2 * prs / max(n, 1), "hbm", pk["hbm_gbs"], "GB/s")
     mlp_ach = mlp_flops / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
     traffic, tensor_active = None, None
-    prof = os.path.join(ROOT, "profiles", "r02_summary.json")   # ncu --set full capture of the 12 GEMM launches of one step
-    if os.path.exists(prof) and args.mlp == "tcgen05" and n == 50000:
+    import glob
+    profs = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_summary.json")))   # ncu --set full capture of the GEMM launches of one step
+    prof = profs[-1] if profs else ""
+    if prof and args.mlp == "tcgen05" and n == 50000:
         tot = json.load(open(prof)).get("gemm_step_totals", {})
         traffic, tensor_active = tot.get("dram_bytes"), tot.get("tensor_pipe_active_pct_time_weighted")
     gemm_name = "gemm_tcgen05_kernel" if args.mlp == "tcgen05" else "gemm_tn_simt_kernel"
@@ -219,10 +221,15 @@ def run_ours(args):
                 "achieved": round(mlp_ach, 3), "peak": mlp_peak, "unit": "TFLOP/s", "frac": round(mlp_ach / mlp_peak, 4), "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % pk["source"],
                 "algorithmic_flops_per_step": mlp_flops, "ms_per_step": round(mlp_ms, 4),
-                "traffic_note": "dram__bytes_read+write summed over the 12 GEMM launches of one step (profiles/r02_summary.json); "
-                                "tensor pipe active %s %% time-weighted in the same capture" % tensor_active,
-                "note": "fp32-accurate GEMM; achieved counts algorithmic fp32 flops (2*M*N*K un-padded): every product is executed as 3 "
-                        "fp16 tensor-core MMAs (hi*hi, hi*lo, lo*hi), i.e. 3x this figure on the tensor pipe"}
+                "executed_flops_per_step": 2.0 * work["mlp_flops_forward_executed"],
+                "frac_executed": round(2.0 * work["mlp_flops_forward_executed"] / (mlp_ms * 1e-3) / 1e12 / mlp_peak, 4) if mlp_ms > 0 else None,
+                "active_features": "%d of %d AEV columns (the others belong to species absent from the system and are identically zero: "
+                                   "the first layer skips those 0*w products, results unchanged)" % (work["active_features"], work["aev_length"]),
+                "traffic_note": "dram__bytes_read+write summed over the GEMM launches of one step (%s); "
+                                "tensor pipe active %s %% time-weighted in the same capture" % (os.path.relpath(prof, ROOT) if prof else None, tensor_active),
+                "note": "fp32-accurate GEMM; achieved counts algorithmic fp32 flops (SURVEY 8d: 2*M*N*K un-padded on the full 1008-column AEV); "
+                        "frac_executed counts only the flops issued after dropping the structurally-zero AEV columns; every product is "
+                        "executed as 3 fp16 tensor-core MMAs (hi*hi, hi*lo, lo*hi), i.e. 3x that figure on the tensor pipe"}
     out = {
         "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -231,7 +238,7 @@ def run_ours(args):
                                "8-member ensemble with random ANI-2x-shaped weights, one conformer per step per GPU, "
                                "conformers split across GPUs with no collective" % n,
                    "atoms": n, "conformers_per_rank_pool": pool, "mlp_impl": args.mlp,
-                   "l2": "per-step working set (AEV 205 MB + activations > 2 GB) exceeds the 126 MB L2; positions rotate through %d conformers" % pool,
+                   "l2": "per-step working set (MLP activations and gradients, > 1 GB) exceeds the 126 MB L2; positions rotate through %d conformers" % pool,
                    "triples_per_step": tri, "radial_pairs_per_step": prs},
         "e2e": {"value": round(world * args.steps / (e2e_ms / 1e3), 4), "unit": UNIT, "h2d_bytes_per_step": n * 12 + 36,
                 "d2h_bytes_per_step": n * 12 + 4, "api": "nnpops_ani_model_energy_grad_host (C ABI, pinned host buffers)"},

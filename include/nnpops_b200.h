@@ -77,13 +77,17 @@ NNPOPS_API int nnpops_ani_model_energy_grad(nnpops_ani_model_t h, const float* p
 /* same call with HOST buffers (pinned or pageable): copies in, evaluates, copies energy and gradient out, synchronises */
 NNPOPS_API int nnpops_ani_model_energy_grad_host(nnpops_ani_model_t h, const float* positions_host, const float* box_host, float* energy_host,
                                       float* position_grad_host, void* stream);
-/* introspection for tests and benchmarks: device pointers to the species-sorted AEV matrix and its gradient, the row stride in
- * floats, and (host, num_atoms ints) the row of each atom */
+/* introspection for tests and benchmarks: device pointers to the species-sorted AEV matrix (active columns only) and its gradient, the row
+ * stride in floats, and (host, num_atoms ints) the row of each atom */
 NNPOPS_API int nnpops_ani_model_buffers(nnpops_ani_model_t h, float** features, float** feature_grad, int* stride, int* row_of_atom);
 /* copy the AEV matrix (which = 0) or its gradient (which = 1) of the last evaluation into out: device float [num_atoms][aev_length],
- * ATOM order */
+ * ATOM order, full AEV layout; columns of species absent from the system read 0 (their gradient is not formed) */
 NNPOPS_API int nnpops_ani_model_read_features(nnpops_ani_model_t h, int which, float* out, void* stream);
 NNPOPS_API int nnpops_ani_model_work(nnpops_ani_model_t h, long long* triples, long long* radial_pairs, double* mlp_flops_forward, void* stream);
+/* mlp_flops_forward above counts the network on the model's full AEV length (the algorithmic figure).  The fused model evaluates
+ * the AEV and the first layer only on the columns whose neighbour species occur in the system (the others are identically zero):
+ * aev_length = full length, active_features = columns kept, mlp_flops_forward_executed = flops actually issued per forward. */
+NNPOPS_API int nnpops_ani_model_info(nnpops_ani_model_t h, int* aev_length, int* active_features, double* mlp_flops_forward_executed);
 NNPOPS_API int nnpops_ani_model_overflowed(nnpops_ani_model_t h, int* flags);
 /* CUDA-event timing of the pipeline stages on the launching stream, for benchmarks: after timing_begin the next max_steps
  * evaluations record events; timing_end synchronises and returns the summed milliseconds of the 7 stages

@@ -142,7 +142,10 @@ class FusedANI(torch.nn.Module):
     def work(self):
         t, p, fl = C.c_longlong(0), C.c_longlong(0), C.c_double(0)
         check(lib.nnpops_ani_model_work(self._h, C.byref(t), C.byref(p), C.byref(fl), current_stream(self.device_)))
-        return {"triples": t.value, "radial_pairs": p.value, "mlp_flops_forward": fl.value}
+        full, active, ex = C.c_int(0), C.c_int(0), C.c_double(0)
+        check(lib.nnpops_ani_model_info(self._h, C.byref(full), C.byref(active), C.byref(ex)))
+        return {"triples": t.value, "radial_pairs": p.value, "mlp_flops_forward": fl.value, "aev_length": full.value,
+                "active_features": active.value, "mlp_flops_forward_executed": ex.value}
 
     STAGES = ("cells+rows", "radial_fwd", "angular_fwd", "mlp_fwd", "mlp_bwd", "radial_bwd", "angular_bwd")
 

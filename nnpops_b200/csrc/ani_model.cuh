@@ -12,7 +12,7 @@ class AniModel {
 public:
     AniModel(int numAtoms, int numSpecies, float rcr, float rca, const int* atomSpecies, int nRadial, const float* radialFn,
              int nAngular, const float* angularFn, int ensemble, int numLayers, const int* dims, const float* params,
-             int maxRadialNeighbors, int maxAngularNeighbors);
+             int maxRadialNeighbors, int maxAngularNeighbors, bool compact = true);
     ~AniModel();
     // energy: device float[1]; positionGrad: device [n][3] = dE/dx (forces = -positionGrad)
     void energyAndGradient(const float* positions, const float* box, float* energy, float* positionGrad, cudaStream_t stream);
@@ -23,7 +23,9 @@ public:
     void timingBegin(int maxSteps);
     int timingEnd(float* stageMs);
     void readFeatures(int which, float* out, cudaStream_t stream);   // atom order, [n][aevLength]
-    int aevLength() const { return nFeat_; }
+    int aevLength() const { return nFeatFull_; }        // the model's full AEV length (readFeatures layout)
+    int activeFeatures() const { return nFeat_; }      // columns that can be non-zero for this system's species
+    double denseFlopsForward() const { return denseFlopsFwd_; }   // MLP forward flops counted on the full AEV length
     AniAev& aev() { return *aev_; }
     SpeciesMlp& mlp() { return *mlp_; }
     float* features() { return feat_; }          // [n][featureStride], species-sorted rows
@@ -34,7 +36,9 @@ public:
 private:
     std::unique_ptr<AniAev> aev_;
     std::unique_ptr<SpeciesMlp> mlp_;
-    int n_, stride_, nFeat_;
+    int n_, stride_, nFeat_, nFeatFull_;
+    double denseFlopsFwd_ = 0;
+    int* colOfFull_ = nullptr;   // device [nFeatFull]: compact column or -1
     float* feat_ = nullptr;
     float* featGrad_ = nullptr;
     int* rowMap_ = nullptr;

@@ -217,7 +217,16 @@ int nnpops_ani_model_work(nnpops_ani_model_t h, long long* triples, long long* r
         NNP_REQUIRE(h && h->impl, "invalid handle");
         if (triples) *triples = h->impl->aev().countTriples((cudaStream_t)stream);
         if (radial_pairs) *radial_pairs = h->impl->aev().countRadialPairs((cudaStream_t)stream);
-        if (mlp_flops_forward) *mlp_flops_forward = h->impl->mlp().flopsForward();
+        if (mlp_flops_forward) *mlp_flops_forward = h->impl->denseFlopsForward();
+    });
+}
+
+int nnpops_ani_model_info(nnpops_ani_model_t h, int* aev_length, int* active_features, double* mlp_flops_forward_executed) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl, "invalid handle");
+        if (aev_length) *aev_length = h->impl->aevLength();
+        if (active_features) *active_features = h->impl->activeFeatures();
+        if (mlp_flops_forward_executed) *mlp_flops_forward_executed = h->impl->mlp().flopsForward();
     });
 }
 

@@ -162,6 +162,17 @@ def test_autograd_module_matches_reference_interface():
         mod.holder.forward(dev(pos).double(), None)
 
 
+def active_columns(species, S, nR, nA):
+    """Boolean mask over the full AEV layout: radial block s / angular block (s, t) is active iff its species occur in the system."""
+    present = np.zeros(S, bool)
+    present[np.unique(species)] = True
+    mask = [np.repeat(present, nR)]
+    for s in range(S):
+        for t in range(s, S):
+            mask.append(np.full(nA, present[s] and present[t]))
+    return np.concatenate(mask)
+
+
 def fused(pos, species, box, rcr, impl, hidden=ANI2X_HIDDEN, ensemble=8, seed=42):
     from nnpops_b200.OptimizedTorchANI import FusedANI
     nets = random_networks(7, hidden, ensemble, 1008, seed)
@@ -191,6 +202,12 @@ def test_fused_energy_forces(name, impl):
     g0 = O.ani_backward(pos, species, 7, rcr, 3.5, rfn, afn, dA[:, :112], dA[:, 112:], box=box, bits=64)
     aev = m.features().cpu().numpy()
     dAg = m.feature_grad().cpu().numpy()
+    # the fused model keeps only the AEV columns whose neighbour species occur in the system: the others are identically zero in
+    # the oracle too, and the gradient with respect to them (position-independent) is not formed
+    act = active_columns(species, 7, 16, 32)
+    assert m.work()["active_features"] == int(act.sum())
+    assert not aev0[:, ~act].any() and not aev[:, ~act].any() and not dAg[:, ~act].any()
+    dA = np.where(act[None, :], dA, 0.0)
     errs = dict(aev=rel_err(aev, aev0), dA=rel_err(dAg, dA), energy=abs(e - e0) / max(abs(e0), 1e-30), forces=rel_err(g, g0))
     print(name, impl, errs, "forces max|delta| = %.3e" % np.abs(g - g0).max())
     assert errs["aev"] < TOL and errs["dA"] < TOL and errs["forces"] < TOL and errs["energy"] < TOL
