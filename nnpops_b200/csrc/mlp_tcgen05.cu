@@ -31,8 +31,9 @@ constexpr uint32_t kTileBytes = TBM * TBK * 2;        // 16 KB: 128 rows x 128 b
 constexpr uint32_t kStageBytes = 4 * kTileBytes;      // streaming mode: A hi, A lo, B hi, B lo
 constexpr uint32_t kDataBytes = kStages * kStageBytes;
 constexpr uint32_t kStageWarpBytes = 32 * 64;         // per epilogue warp: 32 rows x 32 halves (XOR-swizzled), transposes to coalesced rows
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = (4 + kEpiWarps) * 32;
+constexpr int kEpiWarps = 16;          // 4 TMEM lane quarters x 4 column blocks of 32: one 32 x 32 block per warp per tile
+constexpr int kFirstEpiWarp = 2;     // warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer
+constexpr int kThreads = (kFirstEpiWarp + kEpiWarps) * 32;   // 576 threads -> up to 112 registers each
 constexpr uint32_t kSmemBytes = kDataBytes + kEpiWarps * kStageWarpBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
 
@@ -114,6 +115,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // celu(x) = max(x, 0) + min(0, alpha (exp(x / alpha) - 1)), branch-free: one ex2 per element whatever the sign
@@ -139,6 +148,7 @@ struct TcArgs {
     float outScale;
     const float* w3; double* energyAcc; float seedScale;
     int wide;                      // 1: issue Ahi.[Bhi;Blo] as one N = 256 MMA
+    int dbg;                       // development switches (NNPOPS_GEMM_DBG bit mask), 0 in production
 };
 
 // ---- epilogue of one 128 x 64 slice: TMEM -> registers -> fused element-wise op -> shared-memory transpose -> coalesced global ----
@@ -196,8 +206,9 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// warp (q = TMEM lane quarter, hsel = column half) handles rows q*32 + lane and columns [hsel*64, hsel*64 + 64) of the tile
-template <typename WAIT>
+// warp (q = TMEM lane quarter, hsel = column block) handles rows q*32 + lane and columns [hsel*32, hsel*32 + 32) of the tile.  Four
+// epilogue warps per scheduler: the latencies of one warp's chain (bias / activation loads, TMEM load, staging) hide behind the others
+template <int MODE, typename WAIT>
 __device__ __forceinline__ void epilogue_tile(const TcArgs& g, uint32_t tmemBase, int acc, int q, int hsel, int lane, int mt, int nt, int z,
                                               unsigned char* stg, float& esum, WAIT&& waitAccumulator) {
     const int mw = mt * TBM + q * 32;              // first row of this warp
@@ -205,81 +216,88 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& g, uint32_t tmemBase
     const int rowsValid = min(32, g.M - mw);       // warp-uniform, may be <= 0
     const uint32_t tbase = tmemBase + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * TBN);
     bool waited = false;
-#pragma unroll 1
-    for (int c = hsel * 2; c < hsel * 2 + 2; c++) {
-        const int n = n0 + c * 32;
-        if (n >= g.N) break;                       // warp-uniform
+    const int c = hsel;
+    const int n = n0 + c * 32;
+    if (n < g.N) {                                  // warp-uniform
         uint32_t actH[16], actL[16];
-        if (g.mode == 2 && rowsValid > 0) {        // independent of the accumulator: for the first block this runs BEFORE the wait
+        if (MODE == 2 && rowsValid > 0 && !(g.dbg & 2)) {   // independent of the accumulator: issued BEFORE the wait
             const size_t ao = (size_t)mw * g.ldact + (size_t)z * g.actBatchCols + n;
             staged_load_half(stg, actH, g.actHi + ao, g.ldact, rowsValid, lane);
             staged_load_half(stg, actL, g.actLo + ao, g.ldact, rowsValid, lane);
         }
-        if (!waited) { waitAccumulator(); waited = true; }
-        float4 bv[8];
-        if (g.mode == 1 || g.mode == 3) {          // bias row of this block, requested before the accumulator is read
-            const float4* bp = reinterpret_cast<const float4*>(g.bias + (size_t)z * g.biasBatch + n);
+        waitAccumulator(); waited = true;
+        uint32_t ph[16], pl[16];
+        const bool rowOk = m < g.M;
 #pragma unroll
-            for (int j = 0; j < 8; j++) bv[j] = __ldg(bp + j);
-        }
-        uint32_t r1[32], r2[32];
-        tmem_ld32(tbase + c * 32, r1);
-        tmem_ld32(tbase + TBN + c * 32, r2);
-        tmem_ld_wait();
-        if (rowsValid <= 0) continue;
-        float v[32];
+        for (int h = 0; h < 2; h++) {               // two 16-column halves keep the register footprint small
+            float4 bv[4], wv[4];
+            if (MODE == 1 || MODE == 3) {       // bias (and last-layer weights), requested before the accumulator is read
+                const float4* bp = reinterpret_cast<const float4*>(g.bias + (size_t)z * g.biasBatch + n + 16 * h);
 #pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = fmaf(__uint_as_float(r2[j]), kLoInv, __uint_as_float(r1[j]));
-        if (g.mode == 0) {                         // fp32 result (dE/dAEV): the main loop is 24+ chunks long, direct stores stay hidden
-            if (m < g.M) {
-                float* dst = g.C32 + (size_t)m * g.ldc + (size_t)z * g.cBatchCols + n;
+                for (int j = 0; j < 4; j++) bv[j] = __ldg(bp + j);
+                if (MODE == 3) {
+                    const float4* wp = reinterpret_cast<const float4*>(g.w3 + (size_t)z * g.biasBatch + n + 16 * h);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(dst + j) =
-                        make_float4(v[j] * g.outScale, v[j + 1] * g.outScale, v[j + 2] * g.outScale, v[j + 3] * g.outScale);
-            }
-            continue;
-        }
-        if (g.mode == 1 || g.mode == 3) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                v[4 * j] = celu_f(v[4 * j] + bv[j].x); v[4 * j + 1] = celu_f(v[4 * j + 1] + bv[j].y);
-                v[4 * j + 2] = celu_f(v[4 * j + 2] + bv[j].z); v[4 * j + 3] = celu_f(v[4 * j + 3] + bv[j].w);
-            }
-            if (g.mode == 3) {
-                const float4* wp = reinterpret_cast<const float4*>(g.w3 + (size_t)z * g.biasBatch + n);
-                const bool rowOk = m < g.M;
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const float4 wv = __ldg(wp + j);
-                    const float w4[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const float a = v[4 * j + i];
-                        if (rowOk) esum = fmaf(a, w4[i], esum);
-                        v[4 * j + i] = g.seedScale * w4[i] * celu_grad_from_act_f(a);
-                    }
+                    for (int j = 0; j < 4; j++) wv[j] = __ldg(wp + j);
                 }
             }
-        } else {
+            uint32_t r1[16], r2[16];
+            tmem_ld16(tbase + c * 32 + 16 * h, r1);
+            tmem_ld16(tbase + TBN + c * 32 + 16 * h, r2);
+            tmem_ld_wait();
+            if (rowsValid <= 0 || (g.dbg & 4)) continue;
+            float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const float2 fh = unpack_h2(actH[i]), fl = unpack_h2(actL[i]);
-                v[2 * i] *= celu_grad_from_act_f(fmaf(fl.x, kLoInv, fh.x));
-                v[2 * i + 1] *= celu_grad_from_act_f(fmaf(fl.y, kLoInv, fh.y));
+            for (int j = 0; j < 16; j++) v[j] = fmaf(__uint_as_float(r2[j]), kLoInv, __uint_as_float(r1[j]));
+            if (MODE == 0) {                      // fp32 result (dE/dAEV): the main loop is long, direct stores stay hidden
+                if (rowOk) {
+                    float* dst = g.C32 + (size_t)m * g.ldc + (size_t)z * g.cBatchCols + n + 16 * h;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(dst + j) =
+                            make_float4(v[j] * g.outScale, v[j + 1] * g.outScale, v[j + 2] * g.outScale, v[j + 3] * g.outScale);
+                }
+                continue;
+            }
+            if (MODE == 1 || MODE == 3) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    v[4 * j] = celu_f(v[4 * j] + bv[j].x); v[4 * j + 1] = celu_f(v[4 * j + 1] + bv[j].y);
+                    v[4 * j + 2] = celu_f(v[4 * j + 2] + bv[j].z); v[4 * j + 3] = celu_f(v[4 * j + 3] + bv[j].w);
+                }
+                if (MODE == 3) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const float w4[4] = {wv[j].x, wv[j].y, wv[j].z, wv[j].w};
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const float a = v[4 * j + i];
+                            if (rowOk) esum = fmaf(a, w4[i], esum);
+                            v[4 * j + i] = g.seedScale * w4[i] * celu_grad_from_act_f(a);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const float2 fh = unpack_h2(actH[8 * h + i]), fl = unpack_h2(actL[8 * h + i]);
+                    v[2 * i] *= celu_grad_from_act_f(fmaf(fl.x, kLoInv, fh.x));
+                    v[2 * i + 1] *= celu_grad_from_act_f(fmaf(fl.y, kLoInv, fh.y));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                const float2 f2 = __half22float2(h2);
+                ph[8 * h + i] = *reinterpret_cast<const uint32_t*>(&h2);
+                pl[8 * h + i] = pack_h2((v[2 * i] - f2.x) * kLoScale, (v[2 * i + 1] - f2.y) * kLoScale);
             }
         }
-        uint32_t ph[16], pl[16];
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-            const float2 f2 = __half22float2(h2);
-            ph[i] = *reinterpret_cast<const uint32_t*>(&h2);
-            pl[i] = pack_h2((v[2 * i] - f2.x) * kLoScale, (v[2 * i + 1] - f2.y) * kLoScale);
+        if (MODE != 0 && rowsValid > 0 && !(g.dbg & 5)) {
+            const size_t co = (size_t)mw * g.ldc + (size_t)z * g.cBatchCols + n;
+            staged_store_half(stg, ph, g.Chi + co, g.ldc, rowsValid, lane);
+            staged_store_half(stg, pl, g.Clo + co, g.ldc, rowsValid, lane);
         }
-        const size_t co = (size_t)mw * g.ldc + (size_t)z * g.cBatchCols + n;
-        staged_store_half(stg, ph, g.Chi + co, g.ldc, rowsValid, lane);
-        staged_store_half(stg, pl, g.Clo + co, g.ldc, rowsValid, lane);
     }
     if (!waited) waitAccumulator();                // tail tile with no columns for this warp: still consume the barrier phase
 }
@@ -308,6 +326,7 @@ __device__ __forceinline__ void issue_chunk(uint32_t d1, uint64_t descBits, uint
     }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                     const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo, const TcArgs g) {
@@ -335,7 +354,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
         for (int s = 0; s < kAccStages; s++) { mbar_init(accFullBar(s), 1); mbar_init(accEmptyBar(s), kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {
+    __syncwarp();
+    if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmemSlot), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -370,10 +390,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
                 mbar_wait(emptyBar(stage), phase ^ 1u);
                 if (leader) {
                     const uint32_t sb = base + stage * kStageBytes;
-                    mbar_expect_tx(fullBar(stage), kStageBytes);
+                    mbar_expect_tx(fullBar(stage), (g.dbg & 8) ? kStageBytes - 2 * kTileBytes : kStageBytes);
                     const int xa = z * g.aBatchCols + kc * TBK;
+                    if (!(g.dbg & 8)) {
                     tma_load_2d(sb, &mapAhi, fullBar(stage), xa, m0);
                     tma_load_2d(sb + kTileBytes, &mapAlo, fullBar(stage), xa, m0);
+                    }
                     tma_load_2d(sb + 2 * kTileBytes, &mapBhi, fullBar(stage), kc * TBK, yb);
                     tma_load_2d(sb + 3 * kTileBytes, &mapBlo, fullBar(stage), kc * TBK, yb);
                 }
@@ -399,7 +421,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
                 tc_fence_after();
                 if (leader) {
                     const uint32_t sb = base + stage * kStageBytes;
-                    if (nTile == TBN) issue_chunk<true>(d1, descBits, sb, idescTile, kc == 0);
+                    if (g.dbg & 16) {}
+                    else if (nTile == TBN) issue_chunk<true>(d1, descBits, sb, idescTile, kc == 0);
                     else issue_chunk<false>(d1, descBits, sb, idescTile, kc == 0);
                     umma_commit(emptyBar(stage));          // frees the smem stage once these MMAs have read it
                     if (kc == kChunks - 1) umma_commit(accFullBar(acc));
@@ -409,24 +432,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
             }
             if (++acc == kAccStages) { acc = 0; accPhase ^= 1u; }
         }
-    } else if (warp >= 4) {
-        const int q = warp & 3;              // TMEM lane quarter this warp may access (warp id mod 4)
-        const int hsel = (warp - 4) >> 2;    // which 64-column half of the tile
-        unsigned char* const stg = basePtr + kDataBytes + (warp - 4) * kStageWarpBytes;
+    } else if (warp >= kFirstEpiWarp) {
+        const int q = warp & 3;                          // TMEM lane quarter this warp may access (warp id mod 4)
+        const int hsel = (warp - kFirstEpiWarp) >> 2;    // which 32-column block of the tile (distinct among the 4 warps of a quarter)
+        unsigned char* const stg = basePtr + kDataBytes + (warp - kFirstEpiWarp) * kStageWarpBytes;
         int acc = 0;
         uint32_t accPhase = 0;
         for (int t = blockIdx.x; t < numTiles; t += gridDim.x) {
             int mt, nt, z;
             decode(t, mt, nt, z);
             float esum = 0.0f;
-            epilogue_tile(g, tmemBase, acc, q, hsel, lane, mt, nt, z, stg, esum, [&]() {
+            epilogue_tile<MODE>(g, tmemBase, acc, q, hsel, lane, mt, nt, z, stg, esum, [&]() {
                 mbar_wait(accFullBar(acc), accPhase);
                 tc_fence_after();
             });
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(accEmptyBar(acc));
-            if (g.mode == 3) {
+            if (MODE == 3) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
                 if (lane == 0 && esum != 0.0f) atomicAdd(g.energyAcc, (double)esum);
@@ -436,7 +459,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(512u) : "memory");
     }
@@ -499,7 +522,10 @@ void launch_gemm_tcgen05(const GemmArgsH& a, cudaStream_t stream) {
                 "tcgen05 GEMM: output leading dimensions must be multiples of 8");
     static bool attrSet = false;
     if (!attrSet) {
-        NNP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        NNP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        NNP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        NNP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        NNP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
         attrSet = true;
     }
     const CUtensorMap mAhi = make_map(a.Ahi, a.M, a.aCols, a.lda), mAlo = make_map(a.Alo, a.M, a.aCols, a.lda);
@@ -511,9 +537,16 @@ void launch_gemm_tcgen05(const GemmArgsH& a, cudaStream_t stream) {
     g.actHi = a.actHi; g.actLo = a.actLo; g.ldact = a.ldact; g.actBatchCols = a.actBatchCols; g.outScale = a.outScale;
     g.w3 = a.w3; g.energyAcc = a.energyAcc; g.seedScale = a.seedScale;
     g.wide = 1;
+    { const char* e = std::getenv("NNPOPS_GEMM_DBG"); g.dbg = e ? std::atoi(e) : 0; }
     const int tiles = ((a.M + TBM - 1) / TBM) * ((a.N + TBN - 1) / TBN) * a.batch;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    gemm_tcgen05_kernel<<<grid, kThreads, kSmemBytes, stream>>>(mAhi, mAlo, mBhi, mBlo, g);
+    switch (g.mode) {
+        case 0: gemm_tcgen05_kernel<0><<<grid, kThreads, kSmemBytes, stream>>>(mAhi, mAlo, mBhi, mBlo, g); break;
+        case 1: gemm_tcgen05_kernel<1><<<grid, kThreads, kSmemBytes, stream>>>(mAhi, mAlo, mBhi, mBlo, g); break;
+        case 2: gemm_tcgen05_kernel<2><<<grid, kThreads, kSmemBytes, stream>>>(mAhi, mAlo, mBhi, mBlo, g); break;
+        case 3: gemm_tcgen05_kernel<3><<<grid, kThreads, kSmemBytes, stream>>>(mAhi, mAlo, mBhi, mBlo, g); break;
+        default: NNP_REQUIRE(false, "tcgen05 GEMM: unknown epilogue mode");
+    }
     count_launch();
 }
 

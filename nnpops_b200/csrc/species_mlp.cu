@@ -313,61 +313,99 @@ void SpeciesMlp::forwardTc(const float* features, float* energy, cudaStream_t st
         split_rows_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>(features, n8, featHi_, featLo_);
         count_launch();
     }
+    if (slabRows_ > 0 && graphExec_ && !capturing_) {
+        NNP_CUDA_CHECK(cudaGraphLaunch(graphExec_, stream));
+        return;
+    }
+    if (slabRows_ > 0 && !capturing_ && std::getenv("NNPOPS_MLP_GRAPH") && ++eagerCalls_ > 1) {
+        capturing_ = true;
+        cudaGraph_t graph;
+        cudaStream_t cap;
+        NNP_CUDA_CHECK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+        NNP_CUDA_CHECK(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+        forwardTc(features, energy, cap);
+        NNP_CUDA_CHECK(cudaStreamEndCapture(cap, &graph));
+        cudaStreamDestroy(cap);
+        NNP_CUDA_CHECK(cudaGraphInstantiate(&graphExec_, graph, 0));
+        cudaGraphDestroy(graph);
+        capturing_ = false;
+        NNP_CUDA_CHECK(cudaGraphLaunch(graphExec_, stream));
+        return;
+    }
+    if (slabRows_ > 0) {
+        // L2 blocking: the whole forward + backward chain runs slab by slab on scratch buffers that every slab reuses, so the
+        // activations and gradients between the layers live in the 126 MB L2 instead of making a round trip through HBM
+        for (int s = 0; s < S_; s++)
+            for (int r0 = rowStart_[s]; r0 < rowStart_[s + 1]; r0 += slabRows_) {
+                const int nr = std::min(slabRows_, rowStart_[s + 1] - r0);
+                forwardRowsTc(s, r0, nr, 0, stream);
+                backwardRowsTc(s, r0, nr, 0, slabGrad_, stream);
+            }
+        return;
+    }
     for (int s = 0; s < S_; s++) {
         const int r0 = rowStart_[s], nr = rowStart_[s + 1] - r0;
-        if (nr == 0) continue;
-        for (int l = 0; l < L_ - 1; l++) {
-            const Layer& ly = layers_[s][l];
-            GemmArgsH g;
-            std::memset(&g, 0, sizeof(g));
-            g.M = nr; g.epilogue = 1; g.bias = ly.b; g.K = ly.inP; g.outScale = 1.0f;
-            g.Bhi = ly.Whi; g.Blo = ly.Wlo; g.ldb = ly.inP; g.bRows = M_ * ly.outP;
-            g.Chi = actHi_[l] + (size_t)r0 * width_[l]; g.Clo = actLo_[l] + (size_t)r0 * width_[l]; g.ldc = width_[l];
-            if (l == L_ - 2) {   // last hidden layer: energy and the backward seed come straight out of the epilogue
-                g.epilogue = 3; g.w3 = layers_[s][L_ - 1].W; g.energyAcc = energyAcc_; g.seedScale = kGradScale / M_;
-                g.Chi = dzHi_[l] + (size_t)r0 * width_[l]; g.Clo = dzLo_[l] + (size_t)r0 * width_[l];
-            }
-            if (l == 0) {
-                g.Ahi = featHi_ + (size_t)r0 * featStride_; g.Alo = featLo_ + (size_t)r0 * featStride_; g.lda = featStride_;
-                g.aCols = featStride_; g.aBatchCols = 0; g.bBatchRows = 0; g.N = M_ * ly.outP; g.batch = 1; g.cBatchCols = 0; g.biasBatch = 0;
-            } else {
-                g.Ahi = actHi_[l - 1] + (size_t)r0 * width_[l - 1]; g.Alo = actLo_[l - 1] + (size_t)r0 * width_[l - 1];
-                g.lda = width_[l - 1]; g.aCols = width_[l - 1]; g.aBatchCols = ly.inP; g.bBatchRows = ly.outP; g.N = ly.outP; g.batch = M_;
-                g.cBatchCols = ly.outP; g.biasBatch = ly.outP;
-            }
-            launch_gemm_tcgen05(g, stream);
+        if (nr > 0) forwardRowsTc(s, r0, nr, r0, stream);
+    }
+}
+
+// rows [r0, r0 + nr) of species s; activations go to rows [w0, w0 + nr) of the work buffers
+void SpeciesMlp::forwardRowsTc(int s, int r0, int nr, int w0, cudaStream_t stream) {
+    for (int l = 0; l < L_ - 1; l++) {
+        const Layer& ly = layers_[s][l];
+        GemmArgsH g;
+        std::memset(&g, 0, sizeof(g));
+        g.M = nr; g.epilogue = 1; g.bias = ly.b; g.K = ly.inP; g.outScale = 1.0f;
+        g.Bhi = ly.Whi; g.Blo = ly.Wlo; g.ldb = ly.inP; g.bRows = M_ * ly.outP;
+        g.Chi = actHi_[l] + (size_t)w0 * width_[l]; g.Clo = actLo_[l] + (size_t)w0 * width_[l]; g.ldc = width_[l];
+        if (l == L_ - 2) {   // last hidden layer: energy and the backward seed come straight out of the epilogue
+            g.epilogue = 3; g.w3 = layers_[s][L_ - 1].W; g.energyAcc = energyAcc_; g.seedScale = kGradScale / M_;
+            g.Chi = dzHi_[l] + (size_t)w0 * width_[l]; g.Clo = dzLo_[l] + (size_t)w0 * width_[l];
         }
+        if (l == 0) {
+            g.Ahi = featHi_ + (size_t)r0 * featStride_; g.Alo = featLo_ + (size_t)r0 * featStride_; g.lda = featStride_;
+            g.aCols = featStride_; g.aBatchCols = 0; g.bBatchRows = 0; g.N = M_ * ly.outP; g.batch = 1; g.cBatchCols = 0; g.biasBatch = 0;
+        } else {
+            g.Ahi = actHi_[l - 1] + (size_t)w0 * width_[l - 1]; g.Alo = actLo_[l - 1] + (size_t)w0 * width_[l - 1];
+            g.lda = width_[l - 1]; g.aCols = width_[l - 1]; g.aBatchCols = ly.inP; g.bBatchRows = ly.outP; g.N = ly.outP; g.batch = M_;
+            g.cBatchCols = ly.outP; g.biasBatch = ly.outP;
+        }
+        launch_gemm_tcgen05(g, stream);
     }
 }
 
 void SpeciesMlp::backwardTc(float* featureGrad, cudaStream_t stream) {
+    if (slabRows_ > 0) return;   // already done slab by slab inside forwardTc (slabGrad_)
     for (int s = 0; s < S_; s++) {
         const int r0 = rowStart_[s], nr = rowStart_[s + 1] - r0;
-        if (nr == 0) continue;
-        for (int l = L_ - 2; l >= 1; l--) {
-            const Layer& ly = layers_[s][l];
-            GemmArgsH g;
-            std::memset(&g, 0, sizeof(g));
-            g.M = nr; g.N = ly.inP; g.K = ly.outP; g.batch = M_; g.epilogue = 2; g.outScale = 1.0f;
-            g.Ahi = dzHi_[l] + (size_t)r0 * width_[l]; g.Alo = dzLo_[l] + (size_t)r0 * width_[l]; g.lda = width_[l]; g.aCols = width_[l];
-            g.aBatchCols = ly.outP;
-            g.Bhi = ly.Wthi; g.Blo = ly.Wtlo; g.ldb = ly.outP; g.bRows = M_ * ly.inP; g.bBatchRows = ly.inP;
-            g.Chi = dzHi_[l - 1] + (size_t)r0 * width_[l - 1]; g.Clo = dzLo_[l - 1] + (size_t)r0 * width_[l - 1]; g.ldc = width_[l - 1];
-            g.cBatchCols = ly.inP;
-            g.actHi = actHi_[l - 1] + (size_t)r0 * width_[l - 1]; g.actLo = actLo_[l - 1] + (size_t)r0 * width_[l - 1];
-            g.ldact = width_[l - 1]; g.actBatchCols = ly.inP;
-            launch_gemm_tcgen05(g, stream);
-        }
-        {
-            const Layer& ly = layers_[s][0];
-            GemmArgsH g;
-            std::memset(&g, 0, sizeof(g));
-            g.M = nr; g.N = ly.inP; g.K = M_ * ly.outP; g.batch = 1; g.epilogue = 0; g.outScale = 1.0f / kGradScale;
-            g.Ahi = dzHi_[0] + (size_t)r0 * width_[0]; g.Alo = dzLo_[0] + (size_t)r0 * width_[0]; g.lda = width_[0]; g.aCols = width_[0];
-            g.Bhi = ly.Wthi; g.Blo = ly.Wtlo; g.ldb = M_ * ly.outP; g.bRows = ly.inP;
-            g.C32 = featureGrad + (size_t)r0 * featStride_; g.ldc = featStride_;
-            launch_gemm_tcgen05(g, stream);
-        }
+        if (nr > 0) backwardRowsTc(s, r0, nr, r0, featureGrad, stream);
+    }
+}
+
+void SpeciesMlp::backwardRowsTc(int s, int r0, int nr, int w0, float* featureGrad, cudaStream_t stream) {
+    for (int l = L_ - 2; l >= 1; l--) {
+        const Layer& ly = layers_[s][l];
+        GemmArgsH g;
+        std::memset(&g, 0, sizeof(g));
+        g.M = nr; g.N = ly.inP; g.K = ly.outP; g.batch = M_; g.epilogue = 2; g.outScale = 1.0f;
+        g.Ahi = dzHi_[l] + (size_t)w0 * width_[l]; g.Alo = dzLo_[l] + (size_t)w0 * width_[l]; g.lda = width_[l]; g.aCols = width_[l];
+        g.aBatchCols = ly.outP;
+        g.Bhi = ly.Wthi; g.Blo = ly.Wtlo; g.ldb = ly.outP; g.bRows = M_ * ly.inP; g.bBatchRows = ly.inP;
+        g.Chi = dzHi_[l - 1] + (size_t)w0 * width_[l - 1]; g.Clo = dzLo_[l - 1] + (size_t)w0 * width_[l - 1]; g.ldc = width_[l - 1];
+        g.cBatchCols = ly.inP;
+        g.actHi = actHi_[l - 1] + (size_t)w0 * width_[l - 1]; g.actLo = actLo_[l - 1] + (size_t)w0 * width_[l - 1];
+        g.ldact = width_[l - 1]; g.actBatchCols = ly.inP;
+        launch_gemm_tcgen05(g, stream);
+    }
+    {
+        const Layer& ly = layers_[s][0];
+        GemmArgsH g;
+        std::memset(&g, 0, sizeof(g));
+        g.M = nr; g.N = ly.inP; g.K = M_ * ly.outP; g.batch = 1; g.epilogue = 0; g.outScale = 1.0f / kGradScale;
+        g.Ahi = dzHi_[0] + (size_t)w0 * width_[0]; g.Alo = dzLo_[0] + (size_t)w0 * width_[0]; g.lda = width_[0]; g.aCols = width_[0];
+        g.Bhi = ly.Wthi; g.Blo = ly.Wtlo; g.ldb = M_ * ly.outP; g.bRows = ly.inP;
+        g.C32 = featureGrad + (size_t)r0 * featStride_; g.ldc = featStride_;
+        launch_gemm_tcgen05(g, stream);
     }
 }
 
