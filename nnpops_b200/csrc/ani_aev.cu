@@ -11,6 +11,7 @@
 #include "ani_aev.cuh"
 #include <cuda_fp16.h>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace nnpops {
@@ -412,6 +413,164 @@ ani_angular_fwd_kernel(int n, const float4* __restrict__ sorted, const int* __re
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Angular forward, grouped form (factorised tables, <= 32 species pairs): G lanes per centre, 32 / G centres per warp.
+// A liquid-density centre has ~140 triples spread over a few species-pair blocks of 15-70 triples; with a whole warp per
+// centre the last iteration of every block runs mostly empty lanes and the 32-lane transpose-reduce is paid per block.
+// Groups of G = 8 lanes fill their iterations (ceil(ntrip / 8) * 8 slots) and run the reduction of 4 centres at once
+// (3 butterfly levels instead of 5); lane gl of a group ends with channels [gl * 32 / G, (gl + 1) * 32 / G) and stores them
+// as one vector.  The block loop is warp-uniform (all groups visit the same species pair; the trip count is the warp maximum).
+// ------------------------------------------------------------------------------------------------------------------
+template <int G, int NSA, int NSZ, bool TORCHANI>
+__global__ void __launch_bounds__(kWPB * 32)
+ani_angular_fwd_grouped_kernel(int n, const float4* __restrict__ sorted, const int* __restrict__ sortedOrig, const Geom* __restrict__ geom,
+                               const AniTables* __restrict__ tab, const int* __restrict__ rowAng, const int* __restrict__ offAng, int capA,
+                               const int* __restrict__ rowMap, AevOut out, int stride) {
+    static_assert(NSA * NSZ == 32, "the grouped kernel assumes 32 angular channels");
+    constexpr int CPW = 32 / G;   // centres per warp
+    constexpr int R = 32 / G;     // channels per lane after the in-group reduction
+    extern __shared__ unsigned char smemRaw[];
+    __shared__ Geom g;
+    __shared__ float fShfA[kAniMaxShf], fCos[kAniMaxShf], fSin[kAniMaxShf];
+    if (threadIdx.x == 0) g = *geom;
+    if (threadIdx.x < kAniMaxShf) { fShfA[threadIdx.x] = tab->fShfA[threadIdx.x]; fCos[threadIdx.x] = tab->fCos[threadIdx.x]; fSin[threadIdx.x] = tab->fSin[threadIdx.x]; }
+    __syncthreads();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane / G, gl = lane % G;
+    const int p0 = (blockIdx.x * kWPB + w) * CPW;
+    if (p0 >= n) return;                       // warp-uniform
+    const int p = p0 + sub;
+    const bool centre = p < n;
+    const int S = tab->nSpecies, nA = 32, nPairs = tab->nPairs;
+    const size_t perCentre = (size_t)6 * capA + (kAniMaxSpecies + 1);
+    float* sdx = reinterpret_cast<float*>(smemRaw) + ((size_t)w * CPW + sub) * perCentre;
+    float *sdy = sdx + capA, *sdz = sdy + capA, *sr = sdz + capA, *sir = sr + capA, *sfc = sir + capA;
+    int* sOff = reinterpret_cast<int*>(sfc + capA);
+    const int pc = centre ? p : p0;            // lanes of a missing centre mirror the first one with zero neighbours
+    const int* off = offAng + (size_t)pc * (S + 1);
+    const int cnt = centre ? min(off[S], capA) : 0;
+    for (int i = gl; i <= S; i += G) sOff[i] = centre ? min(off[i], capA) : 0;
+    const float4 ci = sorted[pc];
+    const float kf = kPi / tab->rca;
+    for (int q = gl; q < cnt; q += G) {
+        const float4 cj = sorted[rowAng[(size_t)p * capA + q]];
+        float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
+        const float r = sqrtf(min_image_mul(g, dx, dy, dz));
+        sdx[q] = dx; sdy[q] = dy; sdz[q] = dz; sr[q] = r; sir[q] = 1.0f / r;
+        sfc[q] = 0.5f * cosf(r * kf) + 0.5f;
+    }
+    __syncwarp();
+    const int orig = sortedOrig[pc];
+    const size_t orow = (size_t)(rowMap ? rowMap[orig] : orig) * stride;
+    const float cosScale = tab->cosScale;
+    const float fEtaL2 = tab->fEtaL2, fZeta = tab->fZeta, fScale = tab->fScale;
+    unsigned written = 0u;                     // warp-uniform: species pairs stored by every centre of the warp
+    int pIdx = 0;
+    for (int s = 0; s < S; s++) {
+        const int bs = sOff[s], ns = sOff[s + 1] - bs;
+        for (int t = s; t < S; t++, pIdx++) {
+            const int bt = sOff[t], nt = sOff[t + 1] - bt;
+            const int ntrip = (s == t) ? (ns * (ns - 1)) / 2 : ns * nt;
+            const int maxTrip = __reduce_max_sync(kFull, ntrip);
+            if (maxTrip <= 0) continue;
+            written |= 1u << pIdx;
+            const float invNt = 1.0f / (float)max(nt, 1);
+            float acc[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) acc[i] = 0.0f;
+            for (int q0 = 0; q0 < maxTrip; q0 += G) {
+                const int q = q0 + gl;
+                const bool valid = q < ntrip;
+                const int qq = valid ? q : 0;
+                int ia, ib;
+                if (s == t) {   // unordered pairs a < b inside one segment: qq = b(b-1)/2 + a
+                    int b = (int)fmaf(__fsqrt_rn(fmaf(8.0f, (float)qq, 1.0f)), 0.5f, 0.5f);
+                    b -= ((b * (b - 1)) >> 1) > qq ? 1 : 0;
+                    b += ((b * (b + 1)) >> 1) <= qq ? 1 : 0;
+                    ia = bs + qq - ((b * (b - 1)) >> 1); ib = bs + b;
+                } else {
+                    const int a = (int)(((float)qq + 0.5f) * invNt);
+                    ia = bs + a; ib = bt + qq - a * nt;
+                }
+                if (!valid) { ia = 0; ib = 0; }
+                const float ax = sdx[ia], ay = sdy[ia], az = sdz[ia], bx = sdx[ib], by = sdy[ib], bz = sdz[ib];
+                const float dot = ax * bx + ay * by + az * bz;
+                const float ipr = sir[ia] * sir[ib];
+                const float c = cosScale * dot * ipr;
+                float sn;
+                if (TORCHANI) {
+                    sn = sqrtf(fmaxf(1.0f - c * c, 0.0f));
+                } else {
+                    const float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+                    sn = sqrtf(cx * cx + cy * cy + cz * cz) * ipr;
+                }
+                const float rm = 0.5f * (sr[ia] + sr[ib]);
+                const float F = valid ? sfc[ia] * sfc[ib] : 0.0f;
+                float P[NSZ];
+#pragma unroll
+                for (int z = 0; z < NSZ; z++) {
+                    const float base = fmaxf(1.0f + c * fCos[z] + sn * fSin[z], 0.0f);
+                    P[z] = F * ex2a(fZeta * lg2a(base));
+                }
+#pragma unroll
+                for (int a = 0; a < NSA; a++) {
+                    const float tt = rm - fShfA[a];
+                    const float E = ex2a(-fEtaL2 * tt * tt);
+#pragma unroll
+                    for (int z = 0; z < NSZ; z++) acc[a * NSZ + z] = fmaf(P[z], E, acc[a * NSZ + z]);
+                }
+            }
+            // in-group transpose-reduce: log2(G) levels; lane gl keeps channels [gl * R, gl * R + R)
+#pragma unroll
+            for (int o = G / 2, c2 = 16; o >= 1; o >>= 1, c2 >>= 1) {
+                const bool up = (gl & o) != 0;
+#pragma unroll
+                for (int i = 0; i < c2; i++) {
+                    const float send = up ? acc[i] : acc[i + c2];
+                    const float keep = up ? acc[i + c2] : acc[i];
+                    acc[i] = keep + __shfl_xor_sync(kFull, send, o);
+                }
+            }
+            if (centre) {
+                const size_t dst = orow + (size_t)pIdx * nA + gl * R;
+                if (out.hi) {
+                    uint32_t wh[(R + 1) / 2], wl[(R + 1) / 2];
+#pragma unroll
+                    for (int i = 0; i < R; i += 2) {
+                        const float v0 = acc[i] * fScale, v1 = (i + 1 < R) ? acc[i + 1] * fScale : 0.0f;
+                        const __half2 h2 = __floats2half2_rn(v0, v1);
+                        const float2 f2 = __half22float2(h2);
+                        const __half2 l2 = __floats2half2_rn((v0 - f2.x) * 2048.0f, (v1 - f2.y) * 2048.0f);
+                        wh[i / 2] = *reinterpret_cast<const uint32_t*>(&h2);
+                        wl[i / 2] = *reinterpret_cast<const uint32_t*>(&l2);
+                    }
+                    if (R == 4) {
+                        *reinterpret_cast<uint2*>(out.hi + dst) = make_uint2(wh[0], wh[R > 2 ? 1 : 0]);
+                        *reinterpret_cast<uint2*>(out.lo + dst) = make_uint2(wl[0], wl[R > 2 ? 1 : 0]);
+                    } else if (R == 2) {
+                        *reinterpret_cast<uint32_t*>(out.hi + dst) = wh[0];
+                        *reinterpret_cast<uint32_t*>(out.lo + dst) = wl[0];
+                    } else {
+                        out.hi[dst] = __ushort_as_half((unsigned short)(wh[0] & 0xffffu));
+                        out.lo[dst] = __ushort_as_half((unsigned short)(wl[0] & 0xffffu));
+                    }
+                } else {
+                    if (R == 4) *reinterpret_cast<float4*>(out.f32 + dst) = make_float4(acc[0] * fScale, acc[1] * fScale, acc[2] * fScale, acc[3] * fScale);
+                    else if (R == 2) *reinterpret_cast<float2*>(out.f32 + dst) = make_float2(acc[0] * fScale, acc[1] * fScale);
+                    else out.f32[dst] = acc[0] * fScale;
+                }
+            }
+        }
+    }
+    // species pairs that no centre of this warp populated: zero-fill, one centre at a time with the whole warp
+    if (written != (nPairs >= 32 ? 0xffffffffu : (1u << nPairs) - 1u)) {
+        for (int cidx = 0; cidx < CPW; cidx++) {
+            if (p0 + cidx >= n) break;
+            const size_t rowC = __shfl_sync(kFull, (unsigned long long)orow, cidx * G);
+            zero_aev_blocks(out, rowC, nA, nPairs, ~written, lane);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Radial backward, gather-only: dE/dx_i = -sum_j w_ij delta_ij / r_ij with
 // w_ij = scale * sum_k (G[i][s_j][k] + G[j][s_i][k]) * exp(..)(fc' - 2 eta (r - Rs_k) fc)   (CpuANISymmetryFunctions.cpp:228-263).
 // Every directed pair is evaluated by its centre: no atomics inside the pair loop, one accumulate per centre at the end.
@@ -498,10 +657,9 @@ ani_radial_bwd_kernel(int n, const float4* __restrict__ sorted, const int* __res
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Angular backward (CpuANISymmetryFunctions.cpp:265-353).  lane <-> neighbour a of the centre.  In step d lane a evaluates
-// the triple (a, b = a + d mod n): it keeps the force on a, and the force on b travels to lane b by one shuffle (a rotation,
-// so all targets are distinct) -- no shared or global atomics inside the triple loop.  Rows longer than 32 fall back to
-// ordered pairs (each triple evaluated from both ends, still no communication).
+// Angular backward (CpuANISymmetryFunctions.cpp:265-353).  One warp per centre, lane <-> triple: the triples of the centre are
+// enumerated flat in rotation order (see the loop), the forces on the two neighbours of a triple are accumulated in per-warp
+// shared-memory arrays (collision-poor by construction) and flushed with one red.add per neighbour component at the end.
 // ------------------------------------------------------------------------------------------------------------------
 struct TripleForce {
     float ax, ay, az, bx, by, bz;
@@ -593,10 +751,11 @@ ani_angular_bwd_kernel(int n, const float4* __restrict__ sorted, const int* __re
     const int p = blockIdx.x * kWPB + w;
     if (p >= n) return;
     const int S = tab->nSpecies, nA = tab->nAngular, nPairs = tab->nPairs;
-    const size_t perWarp = (size_t)9 * capA + (size_t)nPairs * gPitch;
+    const size_t perWarp = (size_t)12 * capA + (size_t)nPairs * gPitch;
     float* sdx = reinterpret_cast<float*>(smemRaw) + (size_t)w * perWarp;
     float *sdy = sdx + capA, *sdz = sdy + capA, *sr = sdz + capA, *sir = sr + capA, *sfc = sir + capA, *sdfc = sfc + capA;
-    int* ssp = reinterpret_cast<int*>(sdfc + capA);
+    float *sfx = sdfc + capA, *sfy = sfx + capA, *sfz = sfy + capA;   // force accumulators of the neighbours
+    int* ssp = reinterpret_cast<int*>(sfz + capA);
     int* sorig = ssp + capA;
     float* sG = reinterpret_cast<float*>(sorig + capA);
     const int* off = offAng + (size_t)p * (S + 1);
@@ -616,6 +775,7 @@ ani_angular_bwd_kernel(int n, const float4* __restrict__ sorted, const int* __re
         sfc[q] = 0.5f * cs + 0.5f; sdfc[q] = -0.5f * kf * sn;
         ssp[q] = __float_as_int(cj.w);
         sorig[q] = sortedOrig[j];
+        sfx[q] = 0.0f; sfy[q] = 0.0f; sfz[q] = 0.0f;
     }
     {   // stage the centre's gradient row [nPairs][nA] with a pitch that spreads species pairs over banks
         const float* gi = grad + (size_t)(rowMap ? rowMap[orig] : orig) * stride;
@@ -631,40 +791,30 @@ ani_angular_bwd_kernel(int n, const float4* __restrict__ sorted, const int* __re
                                                          sr[b], sir[b], sfc[b], sdfc[b], gp, 0, nA, T, fShfA, fCos, fSin, cosScale, fEta,
                                                          fEtaL2, fZeta, fScale);
     };
-    if (cnt <= 32) {
-        const bool va = lane < cnt;
-        float fx = 0.0f, fy = 0.0f, fz = 0.0f;
-        for (int d = 1; 2 * d <= cnt; d++) {
-            const bool act = va && (2 * d < cnt || lane < d);
-            TripleForce f = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-            if (act) {
-                int b = lane + d;
+    // Flat enumeration of the cnt (cnt - 1) / 2 triples in rotation order: entry q is the pair (a, a + d mod cnt) with d = q / cnt + 1,
+    // a = q mod cnt (the antipodal step of an even row lists only a < cnt / 2, which is exactly where q runs out).  Lanes of one
+    // iteration hold consecutive a (all distinct, at most two values of d), so the shared-memory force accumulators see at most
+    // two-way address collisions; every iteration has 32 busy lanes whatever the row length.
+    {
+        const int total = (cnt * (cnt - 1)) >> 1;
+        const float invCnt = 1.0f / (float)cnt;
+        for (int q0 = 0; q0 < total; q0 += 32) {
+            const int q = q0 + lane;
+            if (q < total) {
+                const int d1 = (int)(((float)q + 0.5f) * invCnt);
+                const int a = q - d1 * cnt;
+                int b = a + d1 + 1;
                 if (b >= cnt) b -= cnt;
-                f = eval(lane, b);
-                fx += f.ax; fy += f.ay; fz += f.az;
+                const TripleForce f = eval(a, b);
+                atomicAdd(&sfx[a], f.ax); atomicAdd(&sfy[a], f.ay); atomicAdd(&sfz[a], f.az);
+                atomicAdd(&sfx[b], f.bx); atomicAdd(&sfy[b], f.by); atomicAdd(&sfz[b], f.bz);
                 cxs -= f.ax + f.bx; cys -= f.ay + f.by; czs -= f.az + f.bz;
             }
-            int src = lane - d;
-            if (src < 0) src += cnt;
-            src &= 31;
-            const float rx = __shfl_sync(kFull, f.bx, src), ry = __shfl_sync(kFull, f.by, src), rz = __shfl_sync(kFull, f.bz, src);
-            if (va) { fx += rx; fy += ry; fz += rz; }
         }
-        if (va) {
-            float* dst = posGrad + 3 * (size_t)sorig[lane];
-            atomicAdd(dst, fx); atomicAdd(dst + 1, fy); atomicAdd(dst + 2, fz);
-        }
-    } else {
+        __syncwarp();
         for (int a = lane; a < cnt; a += 32) {
-            float fx = 0.0f, fy = 0.0f, fz = 0.0f;
-            for (int b = 0; b < cnt; b++) {
-                if (b == a) continue;
-                const TripleForce f = eval(a, b);
-                fx += f.ax; fy += f.ay; fz += f.az;
-            }
-            cxs -= fx; cys -= fy; czs -= fz;
             float* dst = posGrad + 3 * (size_t)sorig[a];
-            atomicAdd(dst, fx); atomicAdd(dst + 1, fy); atomicAdd(dst + 2, fz);
+            atomicAdd(dst, sfx[a]); atomicAdd(dst + 1, sfy[a]); atomicAdd(dst + 2, sfz[a]);
         }
     }
     cxs = warp_sum(cxs); cys = warp_sum(cys); czs = warp_sum(czs);
@@ -830,9 +980,30 @@ void AniAev::forward(const float* positions, const float* box, float* radial, in
     if (fork) NNP_CUDA_CHECK(cudaEventRecord(evJoin_, aux_));
     if (ev) cudaEventRecord(ev[1], stream);
     if (tabHost_.nAngular > 0) {
-        const size_t smem = (size_t)kWPB * 6 * capA_ * sizeof(float);
-        ANI_DISPATCH(ani_angular_fwd_kernel, n_, cells_.sorted, cells_.sortedOrig, cells_.geom, tab_, rowAng_, offAng_, capA_, rowMap_,
-                     angularOut, angularStride);
+        static const int groupLanes = std::getenv("NNPOPS_ANGULAR_GROUP") ? std::atoi(std::getenv("NNPOPS_ANGULAR_GROUP")) : 8;
+        const bool aligned = ((angularStride | radialWidth()) & 3) == 0 &&
+                             ((reinterpret_cast<uintptr_t>(angular) | reinterpret_cast<uintptr_t>(splitHi) | reinterpret_cast<uintptr_t>(splitLo)) & 15) == 0;
+        if (tabHost_.fast && tabHost_.nShfA == 8 && tabHost_.nShfZ == 4 && tabHost_.torchani && tabHost_.nPairs <= 32 && aligned &&
+            (groupLanes == 8 || groupLanes == 16)) {
+            const int cpw = 32 / groupLanes;
+            const size_t smem = (size_t)kWPB * cpw * ((size_t)6 * capA_ + kAniMaxSpecies + 1) * sizeof(float);
+            const int gridG = (n_ + kWPB * cpw - 1) / (kWPB * cpw);
+            if (groupLanes == 8) {
+                auto k = ani_angular_fwd_grouped_kernel<8, 8, 4, true>;
+                set_smem(k, smem);
+                k<<<gridG, kWPB * 32, smem, stream>>>(n_, cells_.sorted, cells_.sortedOrig, cells_.geom, tab_, rowAng_, offAng_, capA_, rowMap_,
+                                                     angularOut, angularStride);
+            } else {
+                auto k = ani_angular_fwd_grouped_kernel<16, 8, 4, true>;
+                set_smem(k, smem);
+                k<<<gridG, kWPB * 32, smem, stream>>>(n_, cells_.sorted, cells_.sortedOrig, cells_.geom, tab_, rowAng_, offAng_, capA_, rowMap_,
+                                                     angularOut, angularStride);
+            }
+        } else {
+            const size_t smem = (size_t)kWPB * 6 * capA_ * sizeof(float);
+            ANI_DISPATCH(ani_angular_fwd_kernel, n_, cells_.sorted, cells_.sortedOrig, cells_.geom, tab_, rowAng_, offAng_, capA_, rowMap_,
+                         angularOut, angularStride);
+        }
         count_launch();
     }
     if (fork) NNP_CUDA_CHECK(cudaStreamWaitEvent(stream, evJoin_, 0));
@@ -863,7 +1034,7 @@ void AniAev::backward(const float* radialGrad, int radialStride, const float* an
     if (ev) cudaEventRecord(ev[0], stream);
     if (tabHost_.nAngular > 0) {
         const int gPitch = tabHost_.nAngular + 1;
-        const size_t smem = (size_t)kWPB * ((size_t)9 * capA_ + (size_t)tabHost_.nPairs * gPitch) * sizeof(float);
+        const size_t smem = (size_t)kWPB * ((size_t)12 * capA_ + (size_t)tabHost_.nPairs * gPitch) * sizeof(float);
         NNP_REQUIRE(smem <= 200 * 1024, "angular gradient row does not fit in shared memory (numSpecies^2 * numAngular too large)");
         ANI_DISPATCH(ani_angular_bwd_kernel, n_, cells_.sorted, cells_.sortedOrig, cells_.geom, tab_, rowAng_, offAng_, capA_, rowMap_,
                      angularGrad, angularStride, positionGrad, gPitch);

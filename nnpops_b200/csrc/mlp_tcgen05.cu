@@ -26,15 +26,20 @@ namespace nnpops {
 
 namespace {
 
-constexpr int TBM = 128, TBN = 128, TBK = 64, kStages = 3, kAccStages = 2;
+constexpr int TBM = 128, TBN = 128, TBK = 64, kAccStages = 2;
+// Operand ring depth: 3 stages; the celu'-mask epilogue (mode 2) gives one stage up for per-warp activation prefetch buffers.
+__host__ __device__ constexpr int stages_of(int mode) { return mode == 2 ? 2 : 3; }
 constexpr uint32_t kTileBytes = TBM * TBK * 2;        // 16 KB: 128 rows x 128 bytes
 constexpr uint32_t kStageBytes = 4 * kTileBytes;      // streaming mode: A hi, A lo, B hi, B lo
-constexpr uint32_t kDataBytes = kStages * kStageBytes;
 constexpr uint32_t kStageWarpBytes = 32 * 64;         // per epilogue warp: 32 rows x 32 halves (XOR-swizzled), transposes to coalesced rows
+// mode 2 adds two more such blocks per warp: the activation hi / lo block of the warp's NEXT tile, filled by cp.async
+__host__ __device__ constexpr uint32_t warp_bytes_of(int mode) { return mode == 2 ? 3 * kStageWarpBytes : kStageWarpBytes; }
 constexpr int kEpiWarps = 16;          // 4 TMEM lane quarters x 4 column blocks of 32: one 32 x 32 block per warp per tile
 constexpr int kFirstEpiWarp = 2;     // warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer
 constexpr int kThreads = (kFirstEpiWarp + kEpiWarps) * 32;   // 576 threads -> up to 112 registers each
-constexpr uint32_t kSmemBytes = kDataBytes + kEpiWarps * kStageWarpBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+__host__ __device__ constexpr uint32_t smem_bytes_of(int mode) {
+    return stages_of(mode) * kStageBytes + kEpiWarps * warp_bytes_of(mode) + 1024 /*alignment slack*/ + 256 /*barriers*/;
+}
 constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -210,7 +215,8 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // epilogue warps per scheduler: the latencies of one warp's chain (bias / activation loads, TMEM load, staging) hide behind the others
 template <int MODE, typename WAIT>
 __device__ __forceinline__ void epilogue_tile(const TcArgs& g, uint32_t tmemBase, int acc, int q, int hsel, int lane, int mt, int nt, int z,
-                                              unsigned char* stg, float& esum, WAIT&& waitAccumulator) {
+                                              unsigned char* stg, float& esum, const uint32_t (&actH)[16], const uint32_t (&actL)[16],
+                                              WAIT&& waitAccumulator) {
     const int mw = mt * TBM + q * 32;              // first row of this warp
     const int m = mw + lane, n0 = nt * TBN;
     const int rowsValid = min(32, g.M - mw);       // warp-uniform, may be <= 0
@@ -219,12 +225,6 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& g, uint32_t tmemBase
     const int c = hsel;
     const int n = n0 + c * 32;
     if (n < g.N) {                                  // warp-uniform
-        uint32_t actH[16], actL[16];
-        if (MODE == 2 && rowsValid > 0 && !(g.dbg & 2)) {   // independent of the accumulator: issued BEFORE the wait
-            const size_t ao = (size_t)mw * g.ldact + (size_t)z * g.actBatchCols + n;
-            staged_load_half(stg, actH, g.actHi + ao, g.ldact, rowsValid, lane);
-            staged_load_half(stg, actL, g.actLo + ao, g.ldact, rowsValid, lane);
-        }
         waitAccumulator(); waited = true;
         uint32_t ph[16], pl[16];
         const bool rowOk = m < g.M;
@@ -334,7 +334,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
     const uint32_t rawAddr = smem_u32(smemRaw);
     const uint32_t base = (rawAddr + 1023u) & ~1023u;
     unsigned char* const basePtr = smemRaw + (base - rawAddr);
-    const uint32_t barBase = base + kDataBytes + kEpiWarps * kStageWarpBytes;
+    constexpr int kStages = stages_of(MODE);
+    constexpr uint32_t kDataBytes = kStages * kStageBytes;
+    const uint32_t barBase = base + kDataBytes + kEpiWarps * warp_bytes_of(MODE);
     // barriers: full[kStages], empty[kStages], accFull[kAccStages], accEmpty[kAccStages]; then the TMEM address slot
     auto fullBar = [&](int s) { return barBase + 8u * s; };
     auto emptyBar = [&](int s) { return barBase + 8u * (kStages + s); };
@@ -435,14 +437,50 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
     } else if (warp >= kFirstEpiWarp) {
         const int q = warp & 3;                          // TMEM lane quarter this warp may access (warp id mod 4)
         const int hsel = (warp - kFirstEpiWarp) >> 2;    // which 32-column block of the tile (distinct among the 4 warps of a quarter)
-        unsigned char* const stg = basePtr + kDataBytes + (warp - kFirstEpiWarp) * kStageWarpBytes;
+        unsigned char* const stg = basePtr + kDataBytes + (warp - kFirstEpiWarp) * warp_bytes_of(MODE);
         int acc = 0;
         uint32_t accPhase = 0;
+        // mode 2: the activation block (hi, lo) this warp needs for celu' is fetched with cp.async one tile ahead into the warp's
+        // own shared-memory blocks (same swizzled layout as the store staging), so its HBM latency is off the critical path
+        unsigned char* const actBuf = stg + kStageWarpBytes;
+        auto prefetch_act = [&](int t) {
+            int mt, nt, z;
+            decode(t, mt, nt, z);
+            const int mw = mt * TBM + q * 32, n = nt * TBN + hsel * 32;
+            const int rowsValid = (n < g.N) ? min(32, g.M - mw) : 0;
+            const int r0 = lane >> 2, u = lane & 3;
+            const size_t ao = (size_t)max(min(mw, g.M - 1), 0) * g.ldact + (size_t)z * g.actBatchCols + min(n, g.N - 32) + u * 8;
+#pragma unroll
+            for (int it = 0; it < 4; it++) {
+                const int r = it * 8 + r0;
+                const uint32_t bytes = r < rowsValid ? 16u : 0u;
+                const size_t o = ao + (bytes ? (size_t)r * g.ldact : 0);
+                const uint32_t dst = smem_u32(actBuf + stage_off(r, u));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(g.actHi + o), "r"(bytes) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + kStageWarpBytes), "l"(g.actLo + o), "r"(bytes) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        if (MODE == 2 && !(g.dbg & 2) && (int)blockIdx.x < numTiles) prefetch_act(blockIdx.x);
         for (int t = blockIdx.x; t < numTiles; t += gridDim.x) {
             int mt, nt, z;
             decode(t, mt, nt, z);
             float esum = 0.0f;
-            epilogue_tile<MODE>(g, tmemBase, acc, q, hsel, lane, mt, nt, z, stg, esum, [&]() {
+            uint32_t actH[16], actL[16];
+            if (MODE == 2 && !(g.dbg & 2)) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint4 th = *reinterpret_cast<const uint4*>(actBuf + stage_off(lane, i));
+                    const uint4 tl = *reinterpret_cast<const uint4*>(actBuf + kStageWarpBytes + stage_off(lane, i));
+                    actH[4 * i] = th.x; actH[4 * i + 1] = th.y; actH[4 * i + 2] = th.z; actH[4 * i + 3] = th.w;
+                    actL[4 * i] = tl.x; actL[4 * i + 1] = tl.y; actL[4 * i + 2] = tl.z; actL[4 * i + 3] = tl.w;
+                }
+                __syncwarp();
+                if (t + (int)gridDim.x < numTiles) prefetch_act(t + gridDim.x);
+            }
+            epilogue_tile<MODE>(g, tmemBase, acc, q, hsel, lane, mt, nt, z, stg, esum, actH, actL, [&]() {
                 mbar_wait(accFullBar(acc), accPhase);
                 tc_fence_after();
             });
@@ -522,10 +560,10 @@ void launch_gemm_tcgen05(const GemmArgsH& a, cudaStream_t stream) {
                 "tcgen05 GEMM: output leading dimensions must be multiples of 8");
     static bool attrSet = false;
     if (!attrSet) {
-        NNP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        NNP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        NNP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        NNP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        NNP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_of(0)));
+        NNP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_of(1)));
+        NNP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_of(2)));
+        NNP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_of(3)));
         attrSet = true;
     }
     const CUtensorMap mAhi = make_map(a.Ahi, a.M, a.aCols, a.lda), mAlo = make_map(a.Alo, a.M, a.aCols, a.lda);
@@ -541,10 +579,10 @@ void launch_gemm_tcgen05(const GemmArgsH& a, cudaStream_t stream) {
     const int tiles = ((a.M + TBM - 1) / TBM) * ((a.N + TBN - 1) / TBN) * a.batch;
     const int grid = tiles < num_sms() ? tiles : num_sms();
     switch (g.mode) {
-        case 0: gemm_tcgen05_kernel<0><<<grid, kThreads, kSmemBytes, stream>>>(mAhi, mAlo, mBhi, mBlo, g); break;
-        case 1: gemm_tcgen05_kernel<1><<<grid, kThreads, kSmemBytes, stream>>>(mAhi, mAlo, mBhi, mBlo, g); break;
-        case 2: gemm_tcgen05_kernel<2><<<grid, kThreads, kSmemBytes, stream>>>(mAhi, mAlo, mBhi, mBlo, g); break;
-        case 3: gemm_tcgen05_kernel<3><<<grid, kThreads, kSmemBytes, stream>>>(mAhi, mAlo, mBhi, mBlo, g); break;
+        case 0: gemm_tcgen05_kernel<0><<<grid, kThreads, smem_bytes_of(0), stream>>>(mAhi, mAlo, mBhi, mBlo, g); break;
+        case 1: gemm_tcgen05_kernel<1><<<grid, kThreads, smem_bytes_of(1), stream>>>(mAhi, mAlo, mBhi, mBlo, g); break;
+        case 2: gemm_tcgen05_kernel<2><<<grid, kThreads, smem_bytes_of(2), stream>>>(mAhi, mAlo, mBhi, mBlo, g); break;
+        case 3: gemm_tcgen05_kernel<3><<<grid, kThreads, smem_bytes_of(3), stream>>>(mAhi, mAlo, mBhi, mBlo, g); break;
         default: NNP_REQUIRE(false, "tcgen05 GEMM: unknown epilogue mode");
     }
     count_launch();
