@@ -69,17 +69,19 @@ __global__ void geom_kernel(const T* __restrict__ pos, int n, const T* __restric
         }
     }
     g.ncells = g.nc[0] * g.nc[1] * g.nc[2];
+    g.anyOutside = 0;
     if (threadIdx.x == 0) *out = g;
 }
 
 template <typename T>
-__device__ __forceinline__ int cell_of(const Geom& g, T px, T py, T pz) {
+__device__ __forceinline__ int cell_of(const Geom& g, T px, T py, T pz, bool* outside = nullptr) {
     int ix, iy, iz;
     if (g.periodic) {
         // fractional coordinates in the lower-triangular box, wrapped into [0, 1)
         float fz = (float)pz * g.inv[2];
         float fy = ((float)py - fz * g.box[7]) * g.inv[1];
         float fx = ((float)px - fy * g.box[3] - fz * g.box[6]) * g.inv[0];
+        if (outside) *outside = !(fx >= 0.0f && fx < 1.0f && fy >= 0.0f && fy < 1.0f && fz >= 0.0f && fz < 1.0f);
         fx -= floorf(fx); fy -= floorf(fy); fz -= floorf(fz);
         ix = (int)(fx * g.nc[0]); iy = (int)(fy * g.nc[1]); iz = (int)(fz * g.nc[2]);
     } else {
@@ -92,14 +94,16 @@ __device__ __forceinline__ int cell_of(const Geom& g, T px, T py, T pz) {
 }
 
 template <typename T>
-__global__ void count_kernel(const T* __restrict__ pos, int n, const Geom* __restrict__ geom, int* __restrict__ cellCount,
+__global__ void count_kernel(const T* __restrict__ pos, int n, Geom* __restrict__ geom, int* __restrict__ cellCount,
                              int* __restrict__ cellOf, int* __restrict__ slot) {
     __shared__ Geom g;
     if (threadIdx.x == 0) g = *geom;
     __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int c = cell_of<T>(g, pos[3 * (size_t)i], pos[3 * (size_t)i + 1], pos[3 * (size_t)i + 2]);
+    bool outside = false;
+    int c = cell_of<T>(g, pos[3 * (size_t)i], pos[3 * (size_t)i + 1], pos[3 * (size_t)i + 2], &outside);
+    if (outside) geom->anyOutside = 1;   // benign race: every writer stores the same value
     cellOf[i] = c;
     slot[i] = atomicAdd(&cellCount[c], 1);
 }

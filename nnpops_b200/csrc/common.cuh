@@ -36,6 +36,7 @@ struct Geom {
     int ncells;
     float origin[3];   // non-periodic: lower corner of the bounding box
     float cellInv[3];  // non-periodic: cells per unit length
+    int anyOutside;    // periodic: set by the cell-list build when some atom lies outside the primary cell [0, 1)^3 (fractional)
 };
 
 // Minimum-image displacement, "multiply by reciprocal" flavour used by ANI and CFConv
