@@ -85,9 +85,13 @@ class FusedANI(torch.nn.Module):
         self.aev_length = int(dims[0, 0])
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib.nnpops_ani_model_destroy(self._h)
-            self._h = None
+        h = self.__dict__.get("_h")
+        if h:
+            self.__dict__["_h"] = None      # plain dict access: Module.__setattr__ is not usable during interpreter shutdown
+            try:
+                lib.nnpops_ani_model_destroy(h)
+            except Exception:               # noqa: BLE001  (library already unloaded at exit)
+                pass
 
     def _evaluate(self, positions: Tensor, cell: Optional[Tensor]):
         if positions.dtype != torch.float32 or positions.dim() != 2 or positions.shape != (self.num_atoms, 3):

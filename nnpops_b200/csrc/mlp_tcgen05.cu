@@ -306,14 +306,15 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& g, uint32_t tmemBase
 // 128 bytes) and D1 | D2 are adjacent in TMEM, so for a full-width tile Ahi . [Bhi; Blo] is ONE N = 256 instruction producing D1
 // and the first half of D2 together: 8 instead of 12 tcgen05.mma per chunk.  descBits = all descriptor fields except the start
 // address (constant for the kernel); the start-address field counts 16-byte units, so stepping K by 16 halves adds 2.
-template <bool FULL>
+// KSTEPS < 4: the last chunk of a K that is not a multiple of 64 (the columns beyond K in the staged tiles are never multiplied).
+template <bool FULL, int KSTEPS = TBK / 16>
 __device__ __forceinline__ void issue_chunk(uint32_t d1, uint64_t descBits, uint32_t stageAddr, uint32_t idescTile, bool firstChunk) {
     const uint64_t aHi0 = descBits + (stageAddr >> 4);
     constexpr uint32_t kTile16 = kTileBytes >> 4;
     constexpr uint32_t idescWide = (1u << 4) | ((uint32_t)(2 * TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
     const uint32_t d2 = d1 + TBN;
 #pragma unroll
-    for (int k4 = 0; k4 < TBK / 16; k4++) {
+    for (int k4 = 0; k4 < KSTEPS; k4++) {
         const uint64_t aHi = aHi0 + 2 * k4, aLo = aHi + kTile16, bHi = aHi + 2 * kTile16, bLo = aHi + 3 * kTile16;
         const uint32_t accum = (firstChunk && k4 == 0) ? 0u : 1u;
         if (FULL) {
@@ -368,7 +369,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmemBase) : "r"(tmemSlot));
 
     const int tilesM = (g.M + TBM - 1) / TBM, tilesN = (g.N + TBN - 1) / TBN;
-    const int kChunks = g.K / TBK;
+    const int kChunks = (g.K + TBK - 1) / TBK;
+    const int lastSteps = (g.K - (kChunks - 1) * TBK) / 16;   // k16 steps of the last chunk (4 unless K % 64 != 0)
     const int numTiles = tilesM * tilesN * g.batch;
     // Tile order: batch member fastest, then n-tile, then m-tile.  Concurrent CTAs then work on the same rows of A for all
     // ensemble members at once (each row of the activation matrix is read as one contiguous run from HBM) and on few m-tiles.
@@ -413,7 +415,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
         for (int t = blockIdx.x; t < numTiles; t += gridDim.x) {
             int mt, nt, z;
             decode(t, mt, nt, z);
-            const int nTile = min(TBN, g.N - nt * TBN);   // 64 or 128 (N is a multiple of 64)
+            const int nTile = min(TBN, g.N - nt * TBN);   // a multiple of 32
             const uint32_t idescTile = (1u << 4) | ((uint32_t)(nTile >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
             mbar_wait(accEmptyBar(acc), accPhase ^ 1u);
             tc_fence_after();
@@ -424,6 +426,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
                 if (leader) {
                     const uint32_t sb = base + stage * kStageBytes;
                     if (g.dbg & 16) {}
+                    else if (kc == kChunks - 1 && lastSteps != TBK / 16) {
+                        if (nTile == TBN) {
+                            if (lastSteps == 2) issue_chunk<true, 2>(d1, descBits, sb, idescTile, kc == 0);
+                            else if (lastSteps == 1) issue_chunk<true, 1>(d1, descBits, sb, idescTile, kc == 0);
+                            else issue_chunk<true, 3>(d1, descBits, sb, idescTile, kc == 0);
+                        } else {
+                            if (lastSteps == 2) issue_chunk<false, 2>(d1, descBits, sb, idescTile, kc == 0);
+                            else if (lastSteps == 1) issue_chunk<false, 1>(d1, descBits, sb, idescTile, kc == 0);
+                            else issue_chunk<false, 3>(d1, descBits, sb, idescTile, kc == 0);
+                        }
+                    }
                     else if (nTile == TBN) issue_chunk<true>(d1, descBits, sb, idescTile, kc == 0);
                     else issue_chunk<false>(d1, descBits, sb, idescTile, kc == 0);
                     umma_commit(emptyBar(stage));          // frees the smem stage once these MMAs have read it
@@ -554,8 +567,8 @@ void gemm_tcgen05_set_streaming(bool on) { g_forceStreaming = on; }
 
 void launch_gemm_tcgen05(const GemmArgsH& a, cudaStream_t stream) {
     if (a.M <= 0 || a.N <= 0) return;
-    NNP_REQUIRE(a.K % TBK == 0 && a.K > 0, "tcgen05 GEMM: K must be a positive multiple of 64");
-    NNP_REQUIRE(a.N % 64 == 0, "tcgen05 GEMM: N must be a multiple of 64");
+    NNP_REQUIRE(a.K % 16 == 0 && a.K > 0, "tcgen05 GEMM: K must be a positive multiple of 16");
+    NNP_REQUIRE(a.N % 32 == 0, "tcgen05 GEMM: N must be a multiple of 32");
     NNP_REQUIRE(a.ldc % 8 == 0 && a.cBatchCols % 8 == 0 && a.ldact % 8 == 0 && a.actBatchCols % 8 == 0,
                 "tcgen05 GEMM: output leading dimensions must be multiples of 8");
     static bool attrSet = false;

@@ -190,7 +190,7 @@ SpeciesMlp::SpeciesMlp(int numSpecies, int ensemble, int numLayers, const int* d
     rows_ = rowStart_[numSpecies];
     const int nFeat = dims[0];
     featP_ = pad_to(nFeat, kMlpPad);
-    NNP_REQUIRE(featureStride >= featP_ && featureStride % 4 == 0, "featureStride must be >= numFeatures padded to 64");
+    NNP_REQUIRE(featureStride >= featP_ && featureStride % 4 == 0, "featureStride must be >= numFeatures padded to 32");
     layers_.resize(S_);
     width_.assign(L_ - 1, 0);
     const float* p = params;

@@ -5,7 +5,7 @@
 //   Z[n_s x (M*out)] = A[n_s x in] . W^T     (layer 0: all M ensemble members side by side; deeper layers: one GEMM per member)
 // with bias + CELU(0.1) fused in the epilogue.  Backward is the transposed chain with celu' recovered from the saved
 // activations (celu'(z) = 1 for a > 0 else a/alpha + 1), giving dE/dAEV; no parameter gradients (BatchedNN.cpp:40).
-// Zero padding of layer widths to multiples of 64 is exact (celu(0) = 0), exactly like the reference's own padding to
+// Zero padding of layer widths to multiples of 32 is exact (celu(0) = 0), exactly like the reference's own padding to
 // the per-layer maximum (BatchedNN.py:71-83).
 #pragma once
 #include <cuda_fp16.h>
@@ -14,7 +14,7 @@
 
 namespace nnpops {
 
-constexpr int kMlpPad = 64;
+constexpr int kMlpPad = 32;   // layer widths are zero-padded to multiples of 32 (ANI-2x widths already are)
 constexpr float kCeluAlpha = 0.1f;
 
 enum class MlpImpl : int { Simt = 0, Tcgen05 = 1 };
