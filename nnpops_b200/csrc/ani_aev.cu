@@ -118,7 +118,11 @@ ani_rows_kernel(int n, const float4* __restrict__ sorted, const int* __restrict_
     const float rcr2 = tab->rcr2, rca2 = tab->rca2;
     const float4 ci = sorted[p];
     int count = 0;
-    for_each_candidate_run(g, cellStart, sortedCell[p], [&](int b, int e) {
+    // the minimum-image step is skipped for runs that do not cross a periodic face (it subtracts exactly zero there, see
+    // for_each_candidate_run_w): 3 FRND on the XU pipe and 9 more instructions per candidate
+    const bool alwaysImage = g.periodic && (g.triclinic || g.anyOutside);
+    for_each_candidate_run_w(g, cellStart, sortedCell[p], [&](int b, int e, bool wrapped) {
+        const bool image = alwaysImage || wrapped;
         for (int q0 = b; q0 < e; q0 += 32) {
             const int q = q0 + lane;
             bool ok = false;
@@ -126,7 +130,8 @@ ani_rows_kernel(int n, const float4* __restrict__ sorted, const int* __restrict_
             if (q < e && q != p) {
                 const float4 cj = sorted[q];
                 float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
-                const float r2 = min_image_mul(g, dx, dy, dz);
+                const float r2 = image ? min_image_mul(g, dx, dy, dz)
+                                       : __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
                 if (r2 < rcr2) {
                     ok = true;
                     packed = (uint32_t)q | ((uint32_t)__float_as_int(cj.w) << 24) | (r2 < rca2 ? 0x80000000u : 0u);
@@ -586,10 +591,12 @@ ani_angular_fwd_grouped_kernel(int n, const float4* __restrict__ sorted, const i
     const int p = p0 + sub;
     const bool centre = p < n;
     const int S = tab->nSpecies, nA = 32, nPairs = tab->nPairs;
-    const size_t perCentre = (size_t)6 * capA + (kAniMaxSpecies + 1);
-    float* sdx = reinterpret_cast<float*>(smemRaw) + ((size_t)w * CPW + sub) * perCentre;
-    float *sdy = sdx + capA, *sdz = sdy + capA, *sr = sdz + capA, *sir = sr + capA, *sfc = sir + capA;
-    int* sOff = reinterpret_cast<int*>(sfc + capA);
+    // per centre: float4 {dx, dy, dz, r} and float2 {1 / r, fc} per neighbour, then the species offsets
+    const size_t perCentre = (size_t)6 * capA + (kAniMaxSpecies + 1 + 3) / 4 * 4;   // in floats, a multiple of 4
+    float* cbase = reinterpret_cast<float*>(smemRaw) + ((size_t)w * CPW + sub) * perCentre;
+    float4* sv = reinterpret_cast<float4*>(cbase);
+    float2* sq = reinterpret_cast<float2*>(cbase + 4 * capA);
+    int* sOff = reinterpret_cast<int*>(cbase + 6 * capA);
     const int pc = centre ? p : p0;            // lanes of a missing centre mirror the first one with zero neighbours
     const int* off = offAng + (size_t)pc * (S + 1);
     const int cnt = centre ? min(off[S], capA) : 0;
@@ -600,8 +607,8 @@ ani_angular_fwd_grouped_kernel(int n, const float4* __restrict__ sorted, const i
         const float4 cj = sorted[rowAng[(size_t)p * capA + q]];
         float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
         const float r = sqrtf(min_image_mul(g, dx, dy, dz));
-        sdx[q] = dx; sdy[q] = dy; sdz[q] = dz; sr[q] = r; sir[q] = 1.0f / r;
-        sfc[q] = 0.5f * cosf(r * kf) + 0.5f;
+        sv[q] = make_float4(dx, dy, dz, r);
+        sq[q] = make_float2(1.0f / r, 0.5f * cosf(r * kf) + 0.5f);
     }
     __syncwarp();
     const int orig = sortedOrig[pc];
@@ -618,38 +625,39 @@ ani_angular_fwd_grouped_kernel(int n, const float4* __restrict__ sorted, const i
             const int maxTrip = __reduce_max_sync(kFull, ntrip);
             if (maxTrip <= 0) continue;
             written |= 1u << pIdx;
-            const float invNt = 1.0f / (float)max(nt, 1);
+            // lane gl starts at triple q = gl and advances by G: (ia, ib) are kept incrementally.  Same species: unordered pairs
+            // a < b with q = b (b - 1) / 2 + a; different species: q = a * nt + b.
+            int ia, ib;
+            if (s == t) {
+                int bq = (int)fmaf(__fsqrt_rn(fmaf(8.0f, (float)gl, 1.0f)), 0.5f, 0.5f);
+                bq -= ((bq * (bq - 1)) >> 1) > gl ? 1 : 0;
+                bq += ((bq * (bq + 1)) >> 1) <= gl ? 1 : 0;
+                ia = gl - ((bq * (bq - 1)) >> 1); ib = bq;
+            } else {
+                const int nt1 = max(nt, 1);
+                ia = gl / nt1; ib = gl - ia * nt1;
+            }
             float acc[32];
 #pragma unroll
             for (int i = 0; i < 32; i++) acc[i] = 0.0f;
-            for (int q0 = 0; q0 < maxTrip; q0 += G) {
-                const int q = q0 + gl;
+            for (int q = gl; q < maxTrip; q += G) {
                 const bool valid = q < ntrip;
-                const int qq = valid ? q : 0;
-                int ia, ib;
-                if (s == t) {   // unordered pairs a < b inside one segment: qq = b(b-1)/2 + a
-                    int b = (int)fmaf(__fsqrt_rn(fmaf(8.0f, (float)qq, 1.0f)), 0.5f, 0.5f);
-                    b -= ((b * (b - 1)) >> 1) > qq ? 1 : 0;
-                    b += ((b * (b + 1)) >> 1) <= qq ? 1 : 0;
-                    ia = bs + qq - ((b * (b - 1)) >> 1); ib = bs + b;
-                } else {
-                    const int a = (int)(((float)qq + 0.5f) * invNt);
-                    ia = bs + a; ib = bt + qq - a * nt;
-                }
-                if (!valid) { ia = 0; ib = 0; }
-                const float ax = sdx[ia], ay = sdy[ia], az = sdz[ia], bx = sdx[ib], by = sdy[ib], bz = sdz[ib];
-                const float dot = ax * bx + ay * by + az * bz;
-                const float ipr = sir[ia] * sir[ib];
+                const int ja = valid ? bs + ia : 0, jb = valid ? (s == t ? bs : bt) + ib : 0;
+                const float4 va = sv[ja], vb = sv[jb];
+                const float2 qa = sq[ja], qb = sq[jb];
+                const float dot = va.x * vb.x + va.y * vb.y + va.z * vb.z;
+                const float ipr = qa.x * qb.x;
                 const float c = cosScale * dot * ipr;
                 float sn;
                 if (TORCHANI) {
-                    sn = sqrtf(fmaxf(1.0f - c * c, 0.0f));
+                    const float x = fmaxf(fmaf(-c, c, 1.0f), 1e-30f);
+                    sn = x * rsqrta(x);
                 } else {
-                    const float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+                    const float cx = va.y * vb.z - va.z * vb.y, cy = va.z * vb.x - va.x * vb.z, cz = va.x * vb.y - va.y * vb.x;
                     sn = sqrtf(cx * cx + cy * cy + cz * cz) * ipr;
                 }
-                const float rm = 0.5f * (sr[ia] + sr[ib]);
-                const float F = valid ? sfc[ia] * sfc[ib] : 0.0f;
+                const float rm = 0.5f * (va.w + vb.w);
+                const float F = valid ? qa.y * qb.y : 0.0f;
                 float P[NSZ];
 #pragma unroll
                 for (int z = 0; z < NSZ; z++) {
@@ -662,6 +670,14 @@ ani_angular_fwd_grouped_kernel(int n, const float4* __restrict__ sorted, const i
                     const float E = ex2a(-fEtaL2 * tt * tt);
 #pragma unroll
                     for (int z = 0; z < NSZ; z++) acc[a * NSZ + z] = fmaf(P[z], E, acc[a * NSZ + z]);
+                }
+                // advance the pair by G triples
+                if (s == t) {
+                    ia += G;
+                    while (ia >= ib) { ia -= ib; ib++; }
+                } else {
+                    ib += G;
+                    while (ib >= nt && nt > 0) { ib -= nt; ia++; }
                 }
             }
             // in-group transpose-reduce: log2(G) levels; lane gl keeps channels [gl * R, gl * R + R)
@@ -877,6 +893,136 @@ triple_backward(float dax, float day, float daz, float ra, float ira, float fa, 
     f.ax = wa * dax + kk * (dbx - pa * dax); f.ay = wa * day + kk * (dby - pa * day); f.az = wa * daz + kk * (dbz - pa * daz);
     f.bx = wb * dbx + kk * (dax - pb * dbx); f.by = wb * dby + kk * (day - pb * dby); f.bz = wb * dbz + kk * (daz - pb * dbz);
     return f;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Angular backward, fast form for the factorised TorchANI tables (same mathematics and enumeration as ani_angular_bwd_kernel
+// below): neighbour data packed as two float4 per neighbour, the centre's gradient row read as float4 (pitch 36), the species
+// pair looked up in a shared table, sin(theta) and its reciprocal from one rsqrt.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kBwdPitch = 36;
+
+template <int NSA, int NSZ>
+__global__ void __launch_bounds__(kWPB * 32)
+ani_angular_bwd_fast_kernel(int n, const float4* __restrict__ sorted, const int* __restrict__ sortedOrig, const Geom* __restrict__ geom,
+                            const AniTables* __restrict__ tab, const int* __restrict__ rowAng, const int* __restrict__ offAng, int capA,
+                            const int* __restrict__ rowMap, const float* __restrict__ grad, int stride, float* __restrict__ posGrad) {
+    static_assert(NSA * NSZ == 32, "32 angular channels");
+    extern __shared__ unsigned char smemRaw[];
+    __shared__ Geom g;
+    __shared__ float fShfA[kAniMaxShf], fCos[kAniMaxShf], fSin[kAniMaxShf];
+    __shared__ unsigned char pairTab[kAniMaxSpecies * kAniMaxSpecies];
+    const int S = tab->nSpecies, nPairs = tab->nPairs;
+    if (threadIdx.x == 0) g = *geom;
+    if (threadIdx.x < kAniMaxShf) { fShfA[threadIdx.x] = tab->fShfA[threadIdx.x]; fCos[threadIdx.x] = tab->fCos[threadIdx.x]; fSin[threadIdx.x] = tab->fSin[threadIdx.x]; }
+    for (int i = threadIdx.x; i < S * S; i += blockDim.x) pairTab[i] = (unsigned char)pair_index(S, i / S, i % S);
+    __syncthreads();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * kWPB + w;
+    if (p >= n) return;
+    // per warp: float4 sv[capA] {dx, dy, dz, r}, float4 sw[capA] {1/r, fc, dfc, species}, float sf[3][capA] forces, int sorig[capA],
+    // float sG[nPairs][36]
+    const size_t perWarp = (size_t)12 * capA + (size_t)nPairs * kBwdPitch;
+    float* wb = reinterpret_cast<float*>(smemRaw) + (size_t)w * perWarp;
+    float4* sv = reinterpret_cast<float4*>(wb);
+    float4* sw = reinterpret_cast<float4*>(wb + 4 * capA);
+    float *sfx = wb + 8 * capA, *sfy = sfx + capA, *sfz = sfy + capA;
+    int* sorig = reinterpret_cast<int*>(sfz + capA);
+    float* sG = reinterpret_cast<float*>(sorig + capA);
+    const int* off = offAng + (size_t)p * (S + 1);
+    const int cnt = min(off[S], capA);
+    const int orig = sortedOrig[p];
+    if (cnt < 2) return;
+    const float4 ci = sorted[p];
+    const float kf = kPi / tab->rca;
+    for (int q = lane; q < cnt; q += 32) {
+        const int j = rowAng[(size_t)p * capA + q];
+        const float4 cj = sorted[j];
+        float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
+        const float r = sqrtf(min_image_mul(g, dx, dy, dz));
+        float sn, cs;
+        sincosf(r * kf, &sn, &cs);
+        sv[q] = make_float4(dx, dy, dz, r);
+        sw[q] = make_float4(1.0f / r, 0.5f * cs + 0.5f, -0.5f * kf * sn, cj.w);
+        sorig[q] = sortedOrig[j];
+        sfx[q] = 0.0f; sfy[q] = 0.0f; sfz[q] = 0.0f;
+    }
+    {
+        const float* gi = grad + (size_t)(rowMap ? rowMap[orig] : orig) * stride;
+        const int tot = nPairs * 32;
+        for (int i = lane; i < tot; i += 32) sG[(i >> 5) * kBwdPitch + (i & 31)] = gi[i];
+    }
+    __syncwarp();
+    const float cosScale = tab->cosScale, fEta = tab->fEta, fEtaL2 = tab->fEtaL2, fZeta = tab->fZeta, fScale = tab->fScale;
+    float cxs = 0.0f, cys = 0.0f, czs = 0.0f;
+    const int total = (cnt * (cnt - 1)) >> 1;
+    int a = lane % cnt, d1 = lane / cnt;          // q = d1 * cnt + a, partner b = a + d1 + 1 (mod cnt)
+    for (int q = lane; q < total; q += 32) {
+        int b = a + d1 + 1;
+        if (b >= cnt) b -= cnt;
+        const float4 va = sv[a], vb = sv[b], wa4 = sw[a], wb4 = sw[b];
+        const float* gp = sG + pairTab[__float_as_int(wa4.w) * S + __float_as_int(wb4.w)] * kBwdPitch;
+        const float dot = va.x * vb.x + va.y * vb.y + va.z * vb.z;
+        const float ipr = wa4.x * wb4.x;
+        const float c = cosScale * dot * ipr;
+        const float x = fmaxf(fmaf(-c, c, 1.0f), 1e-30f);
+        const float isn = rsqrta(x), sn = x * isn;
+        const float rm = 0.5f * (va.w + vb.w);
+        float P[NSZ], Q[NSZ];
+#pragma unroll
+        for (int z = 0; z < NSZ; z++) {
+            const float base = fmaxf(1.0f + c * fCos[z] + sn * fSin[z], 0.0f);
+            const float pm1 = ex2a((fZeta - 1.0f) * lg2a(base));
+            P[z] = pm1 * base;
+            Q[z] = pm1 * (c * fSin[z] - sn * fCos[z]);        // times zeta below
+        }
+        float A = 0.0f, Bp = 0.0f, C = 0.0f;
+#pragma unroll
+        for (int k = 0; k < NSA; k++) {
+            const float tt = rm - fShfA[k];
+            const float E = ex2a(-fEtaL2 * tt * tt);
+            float gv[NSZ];
+            if (NSZ == 4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(gp + k * NSZ);
+                gv[0] = t4.x; gv[1] = t4.y; gv[2] = t4.z; gv[3] = t4.w;
+            } else {
+#pragma unroll
+                for (int z = 0; z < NSZ; z += 4) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(gp + k * NSZ + z);
+                    gv[z] = t4.x; gv[z + 1] = t4.y; gv[z + 2] = t4.z; gv[z + 3] = t4.w;
+                }
+            }
+            float Ta = 0.0f, Ua = 0.0f;
+#pragma unroll
+            for (int z = 0; z < NSZ; z++) { Ta = fmaf(gv[z], P[z], Ta); Ua = fmaf(gv[z], Q[z], Ua); }
+            const float TE = Ta * E;
+            A += TE; Bp = fmaf(TE, tt, Bp); C = fmaf(Ua, E, C);
+        }
+        A *= fScale; const float B = -fEta * fScale * Bp; C *= fZeta * fScale;
+        const float F = wa4.y * wb4.y;
+        const float FB = F * B;
+        const float wa = (wa4.z * wb4.y * A + FB) * wa4.x;
+        const float wbb = (wa4.y * wb4.z * A + FB) * wb4.x;
+        const float kk = -cosScale * isn * ipr * (F * C);
+        const float pa = dot * wa4.x * wa4.x, pb = dot * wb4.x * wb4.x;
+        const float fax = wa * va.x + kk * (vb.x - pa * va.x), fay = wa * va.y + kk * (vb.y - pa * va.y), faz = wa * va.z + kk * (vb.z - pa * va.z);
+        const float fbx = wbb * vb.x + kk * (va.x - pb * vb.x), fby = wbb * vb.y + kk * (va.y - pb * vb.y), fbz = wbb * vb.z + kk * (va.z - pb * vb.z);
+        atomicAdd(&sfx[a], fax); atomicAdd(&sfy[a], fay); atomicAdd(&sfz[a], faz);
+        atomicAdd(&sfx[b], fbx); atomicAdd(&sfy[b], fby); atomicAdd(&sfz[b], fbz);
+        cxs -= fax + fbx; cys -= fay + fby; czs -= faz + fbz;
+        a += 32;
+        while (a >= cnt) { a -= cnt; d1++; }
+    }
+    __syncwarp();
+    for (int q = lane; q < cnt; q += 32) {
+        float* dst = posGrad + 3 * (size_t)sorig[q];
+        atomicAdd(dst, sfx[q]); atomicAdd(dst + 1, sfy[q]); atomicAdd(dst + 2, sfz[q]);
+    }
+    cxs = warp_sum(cxs); cys = warp_sum(cys); czs = warp_sum(czs);
+    if (lane == 0) {
+        float* dst = posGrad + 3 * (size_t)orig;
+        atomicAdd(dst, cxs); atomicAdd(dst + 1, cys); atomicAdd(dst + 2, czs);
+    }
 }
 
 template <int MODE, int NSA, int NSZ, bool TORCHANI>
@@ -1141,7 +1287,7 @@ void AniAev::forward(const float* positions, const float* box, float* radial, in
         if (tabHost_.fast && tabHost_.nShfA == 8 && tabHost_.nShfZ == 4 && tabHost_.torchani && tabHost_.nPairs <= 32 && aligned &&
             (groupLanes == 8 || groupLanes == 16)) {
             const int cpw = 32 / groupLanes;
-            const size_t smem = (size_t)kWPB * cpw * ((size_t)6 * capA_ + kAniMaxSpecies + 1) * sizeof(float);
+            const size_t smem = (size_t)kWPB * cpw * ((size_t)6 * capA_ + (kAniMaxSpecies + 1 + 3) / 4 * 4) * sizeof(float);
             const int gridG = (n_ + kWPB * cpw - 1) / (kWPB * cpw);
             if (groupLanes == 8) {
                 auto k = ani_angular_fwd_grouped_kernel<8, 8, 4, true>;
@@ -1191,8 +1337,19 @@ void AniAev::backward(const float* radialGrad, int radialStride, const float* an
         const int gPitch = tabHost_.nAngular + 1;
         const size_t smem = (size_t)kWPB * ((size_t)12 * capA_ + (size_t)tabHost_.nPairs * gPitch) * sizeof(float);
         NNP_REQUIRE(smem <= 200 * 1024, "angular gradient row does not fit in shared memory (numSpecies^2 * numAngular too large)");
-        ANI_DISPATCH(ani_angular_bwd_kernel, n_, cells_.sorted, cells_.sortedOrig, cells_.geom, tab_, rowAng_, offAng_, capA_, rowMap_,
-                     angularGrad, angularStride, positionGrad, gPitch);
+        static const bool slowBwd = std::getenv("NNPOPS_ANGULAR_BWD_GENERIC") != nullptr;
+        if (!slowBwd && tabHost_.fast && tabHost_.nShfA == 8 && tabHost_.nShfZ == 4 && tabHost_.torchani && tabHost_.nSpecies <= 15 &&
+            (capA_ & 3) == 0) {
+            const size_t smemF = (size_t)kWPB * ((size_t)12 * capA_ + (size_t)tabHost_.nPairs * kBwdPitch) * sizeof(float);
+            NNP_REQUIRE(smemF <= 200 * 1024, "angular gradient row does not fit in shared memory (numSpecies^2 * numAngular too large)");
+            auto k = ani_angular_bwd_fast_kernel<8, 4>;
+            set_smem(k, smemF);
+            k<<<grid, kWPB * 32, smemF, stream>>>(n_, cells_.sorted, cells_.sortedOrig, cells_.geom, tab_, rowAng_, offAng_, capA_, rowMap_,
+                                                 angularGrad, angularStride, positionGrad);
+        } else {
+            ANI_DISPATCH(ani_angular_bwd_kernel, n_, cells_.sorted, cells_.sortedOrig, cells_.geom, tab_, rowAng_, offAng_, capA_, rowMap_,
+                         angularGrad, angularStride, positionGrad, gPitch);
+        }
         count_launch();
     }
     if (fork) NNP_CUDA_CHECK(cudaStreamWaitEvent(stream, evJoin_, 0));

@@ -36,8 +36,11 @@ struct CellList {
 
 // Visit the candidate ranges [begin, end) of the sorted array that can hold neighbours of an atom in cell `c`.
 // Cells adjacent along z are contiguous in memory, so a 27-cell neighbourhood is at most 18 runs (9 away from the z faces).
+// f(begin, end, wrapped): `wrapped` tells whether the run was reached across a periodic face (or the grid is too coarse to tell);
+// for an un-wrapped run of an orthorhombic box with >= 5 cells per dimension and all atoms inside the primary cell the
+// minimum-image step of a pair (centre, candidate) subtracts exactly zero and may be skipped by the caller.
 template <typename F>
-__device__ __forceinline__ void for_each_candidate_run(const Geom& g, const int* __restrict__ cellStart, int c, F&& f) {
+__device__ __forceinline__ void for_each_candidate_run_w(const Geom& g, const int* __restrict__ cellStart, int c, F&& f) {
     const int nx = g.nc[0], ny = g.nc[1], nz = g.nc[2];
     const int cz = c % nz;
     const int cy = (c / nz) % ny;
@@ -45,23 +48,32 @@ __device__ __forceinline__ void for_each_candidate_run(const Geom& g, const int*
     const bool per = g.periodic != 0;
     // z runs
     int za[2], zb[2], nrun = 1;
+    bool zw[2] = {false, false};
     if (!per) { za[0] = max(cz - 1, 0); zb[0] = min(cz + 1, nz - 1); }
-    else if (nz <= 3) { za[0] = 0; zb[0] = nz - 1; }
-    else if (cz == 0) { za[0] = 0; zb[0] = 1; za[1] = nz - 1; zb[1] = nz - 1; nrun = 2; }
-    else if (cz == nz - 1) { za[0] = nz - 2; zb[0] = nz - 1; za[1] = 0; zb[1] = 0; nrun = 2; }
+    else if (nz <= 3) { za[0] = 0; zb[0] = nz - 1; zw[0] = true; }
+    else if (cz == 0) { za[0] = 0; zb[0] = 1; za[1] = nz - 1; zb[1] = nz - 1; zw[1] = true; nrun = 2; }
+    else if (cz == nz - 1) { za[0] = nz - 2; zb[0] = nz - 1; za[1] = 0; zb[1] = 0; zw[1] = true; nrun = 2; }
     else { za[0] = cz - 1; zb[0] = cz + 1; }
+    const bool coarse = per && (nx < 5 || ny < 5 || nz < 5);
     const int x0 = (per && nx <= 2) ? 0 : -1, x1 = (per && nx == 1) ? 0 : 1;
     const int y0 = (per && ny <= 2) ? 0 : -1, y1 = (per && ny == 1) ? 0 : 1;
     for (int ox = x0; ox <= x1; ox++) {
         int ix = cx + ox;
-        if (per) { ix = (ix + nx) % nx; } else if (ix < 0 || ix >= nx) continue;
+        bool xw = false;
+        if (per) { if (ix < 0) { ix += nx; xw = true; } else if (ix >= nx) { ix -= nx; xw = true; } } else if (ix < 0 || ix >= nx) continue;
         for (int oy = y0; oy <= y1; oy++) {
             int iy = cy + oy;
-            if (per) { iy = (iy + ny) % ny; } else if (iy < 0 || iy >= ny) continue;
+            bool yw = false;
+            if (per) { if (iy < 0) { iy += ny; yw = true; } else if (iy >= ny) { iy -= ny; yw = true; } } else if (iy < 0 || iy >= ny) continue;
             const int base = (ix * ny + iy) * nz;
-            for (int r = 0; r < nrun; r++) f(cellStart[base + za[r]], cellStart[base + zb[r] + 1]);
+            for (int r = 0; r < nrun; r++) f(cellStart[base + za[r]], cellStart[base + zb[r] + 1], coarse || xw || yw || zw[r]);
         }
     }
+}
+
+template <typename F>
+__device__ __forceinline__ void for_each_candidate_run(const Geom& g, const int* __restrict__ cellStart, int c, F&& f) {
+    for_each_candidate_run_w(g, cellStart, c, [&](int b, int e, bool) { f(b, e); });
 }
 
 }  // namespace nnpops
