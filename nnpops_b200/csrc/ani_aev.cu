@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 namespace nnpops {
 
@@ -195,152 +196,6 @@ ani_rows_kernel(int n, const float4* __restrict__ sorted, const int* __restrict_
         const int j = (int)(e & 0x00ffffffu);
         if (valid) rowRad[(size_t)p * capR + dstR] = j;
         if (ang && dstA < capA) rowAng[(size_t)p * capA + dstA] = j;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Neighbour rows, lane-per-centre form.  A warp owns 32 consecutive sorted atoms -- a few z-adjacent cells of one (x, y) column --
-// and scans the union of their neighbourhoods once: every candidate is staged in shared memory and broadcast to all lanes, each
-// lane applies the reference's accept test for ITS centre and appends to its own (bank-interleaved) list.  There is no ballot /
-// compaction / match_any machinery: ~14 instructions per (centre, candidate) for a run that does not cross a periodic face (the
-// minimum-image step is then exactly a subtraction of zero and is skipped; it is kept whenever a run wraps, the box is small or
-// triclinic, or any atom lies outside the primary cell), and the grouping by species is a per-lane counting sort in arrival order,
-// so the rows are deterministic.  Accept test and arithmetic: CpuANISymmetryFunctions.cpp:129-135.
-// ------------------------------------------------------------------------------------------------------------------
-constexpr int kRowsWarps = 4;     // warps per CTA
-constexpr int kRowsChunk = 64;    // candidates staged per step
-
-__global__ void __launch_bounds__(kRowsWarps * 32)
-ani_rows_lane_kernel(int n, const float4* __restrict__ sorted, const int* __restrict__ sortedCell, const Geom* __restrict__ geom,
-                     const int* __restrict__ cellStart, const AniTables* __restrict__ tab, int capR, int capA,
-                     int* __restrict__ rowRad, int* __restrict__ rowAng, int* __restrict__ offRad, int* __restrict__ offAng,
-                     int* __restrict__ flag) {
-    extern __shared__ unsigned char smemRaw[];
-    __shared__ Geom g;
-    if (threadIdx.x == 0) g = *geom;
-    __syncthreads();
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int S = tab->nSpecies;
-    const size_t perWarp = (size_t)kRowsChunk * 4 + (size_t)capR * 32 + (size_t)2 * S * 32;   // in 4-byte words
-    uint32_t* wbase = reinterpret_cast<uint32_t*>(smemRaw) + (size_t)w * perWarp;
-    float4* cand = reinterpret_cast<float4*>(wbase);
-    uint32_t* list = wbase + kRowsChunk * 4;
-    int* cR = reinterpret_cast<int*>(list + (size_t)capR * 32);
-    int* cA = cR + S * 32;
-    const int p0 = (blockIdx.x * kRowsWarps + w) * 32;
-    if (p0 >= n) return;
-    const int p = p0 + lane;
-    const bool atom = p < n;
-    const float rcr2 = tab->rcr2, rca2 = tab->rca2;
-    const float4 ci = sorted[atom ? p : p0];
-    const int nx = g.nc[0], ny = g.nc[1], nz = g.nc[2];
-    const int myCell = atom ? sortedCell[p] : -1;
-    const int col = atom ? myCell / nz : -1, cz = atom ? myCell % nz : 0;
-    const bool per = g.periodic != 0;
-    const bool alwaysImage = per && (g.triclinic || g.anyOutside || nx < 5 || ny < 5);
-    int count = 0;
-    unsigned todo = __ballot_sync(kFull, atom);
-    while (todo) {                                        // one pass per (x, y) column present in the warp (1, rarely 2)
-        const int leader = __ffs(todo) - 1;
-        const int colL = __shfl_sync(kFull, col, leader);
-        const bool active = atom && col == colL;
-        todo &= ~__ballot_sync(kFull, active);
-        const int czmin = __reduce_min_sync(kFull, active ? cz : 0x7fffffff);
-        const int czmax = __reduce_max_sync(kFull, active ? cz : -1);
-        const int cy = colL % ny, cx = colL / ny;
-        // z range of cells to scan (inclusive), as up to two runs
-        int za[2], zb[2], nrun = 1;
-        bool zw[2] = {false, false};
-        const int lo = czmin - 1, hi = czmax + 1;
-        if (!per) { za[0] = max(lo, 0); zb[0] = min(hi, nz - 1); }
-        else if (hi - lo + 1 >= nz) { za[0] = 0; zb[0] = nz - 1; zw[0] = true; }
-        else if (lo < 0) { za[0] = 0; zb[0] = hi; za[1] = lo + nz; zb[1] = nz - 1; zw[1] = true; nrun = 2; }
-        else if (hi >= nz) { za[0] = lo; zb[0] = nz - 1; za[1] = 0; zb[1] = hi - nz; zw[1] = true; nrun = 2; }
-        else { za[0] = lo; zb[0] = hi; }
-        const bool zFar = 2 * (czmax - czmin + 2) + 1 > nz;   // |dz| could reach half the box: keep the image step
-        const int x0 = (per && nx <= 2) ? 0 : -1, x1 = (per && nx == 1) ? 0 : 1;
-        const int y0 = (per && ny <= 2) ? 0 : -1, y1 = (per && ny == 1) ? 0 : 1;
-        for (int ox = x0; ox <= x1; ox++) {
-            int ix = cx + ox;
-            bool xw = false;
-            if (per) { if (ix < 0) { ix += nx; xw = true; } else if (ix >= nx) { ix -= nx; xw = true; } }
-            else if (ix < 0 || ix >= nx) continue;
-            for (int oy = y0; oy <= y1; oy++) {
-                int iy = cy + oy;
-                bool yw = false;
-                if (per) { if (iy < 0) { iy += ny; yw = true; } else if (iy >= ny) { iy -= ny; yw = true; } }
-                else if (iy < 0 || iy >= ny) continue;
-                const int cbase = (ix * ny + iy) * nz;
-                for (int r = 0; r < nrun; r++) {
-                    const int b = cellStart[cbase + za[r]], e = cellStart[cbase + zb[r] + 1];
-                    const bool image = per && (alwaysImage || xw || yw || zw[r] || zFar);   // warp-uniform
-                    for (int q0 = b; q0 < e; q0 += kRowsChunk) {
-                        const int m = min(kRowsChunk, e - q0);
-                        __syncwarp();
-                        for (int k = lane; k < m; k += 32) cand[k] = sorted[q0 + k];
-                        __syncwarp();
-                        if (image) {
-#pragma unroll 2
-                            for (int k = 0; k < m; k++) {
-                                const float4 cj = cand[k];
-                                float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
-                                const float r2 = min_image_mul(g, dx, dy, dz);
-                                if (active && r2 < rcr2 && q0 + k != p) {
-                                    if (count < capR)
-                                        list[count * 32 + lane] = (uint32_t)(q0 + k) | ((uint32_t)__float_as_int(cj.w) << 24) | (r2 < rca2 ? 0x80000000u : 0u);
-                                    count++;
-                                }
-                            }
-                        } else {
-#pragma unroll 4
-                            for (int k = 0; k < m; k++) {
-                                const float4 cj = cand[k];
-                                const float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
-                                const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                                if (active && r2 < rcr2 && q0 + k != p) {
-                                    if (count < capR)
-                                        list[count * 32 + lane] = (uint32_t)(q0 + k) | ((uint32_t)__float_as_int(cj.w) << 24) | (r2 < rca2 ? 0x80000000u : 0u);
-                                    count++;
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-        }
-    }
-    if (count > capR) { atomicOr(flag, 1); count = capR; }
-    // per-lane counting sort by species (arrival order inside a species): counts -> offsets -> cursors -> placement
-    for (int s = 0; s < S; s++) { cR[s * 32 + lane] = 0; cA[s * 32 + lane] = 0; }
-    for (int e = 0; e < count; e++) {
-        const uint32_t v = list[e * 32 + lane];
-        const int s = (v >> 24) & 0x7f;
-        cR[s * 32 + lane]++;
-        if (v & 0x80000000u) cA[s * 32 + lane]++;
-    }
-    if (atom) {
-        int runR = 0, runA = 0;
-        int* oR = offRad + (size_t)p * (S + 1);
-        int* oA = offAng + (size_t)p * (S + 1);
-        for (int s = 0; s < S; s++) {
-            const int tr = cR[s * 32 + lane], ta = cA[s * 32 + lane];
-            oR[s] = runR; oA[s] = min(runA, capA);
-            cR[s * 32 + lane] = runR; cA[s * 32 + lane] = runA;
-            runR += tr; runA += ta;
-        }
-        oR[S] = runR; oA[S] = min(runA, capA);
-        if (runA > capA) atomicOr(flag, 2);
-        int* rr = rowRad + (size_t)p * capR;
-        int* ra = rowAng + (size_t)p * capA;
-        for (int e = 0; e < count; e++) {
-            const uint32_t v = list[e * 32 + lane];
-            const int s = (v >> 24) & 0x7f, j = (int)(v & 0x00ffffffu);
-            rr[cR[s * 32 + lane]++] = j;
-            if (v & 0x80000000u) {
-                const int d = cA[s * 32 + lane]++;
-                if (d < capA) ra[d] = j;
-            }
-        }
     }
 }
 
@@ -1247,19 +1102,10 @@ void AniAev::forward(const float* positions, const float* box, float* radial, in
     cells_.build<float>(positions, box, species_, tabHost_.rcr > tabHost_.rca ? tabHost_.rcr : tabHost_.rca, stream);
     const int grid = (n_ + kWPB - 1) / kWPB;
     {
-        static const bool warpRows = std::getenv("NNPOPS_ROWS_LANE") == nullptr;   // A/B switch: lane-per-centre kernel (3x fewer instructions, but occupancy-bound by its lists: not faster yet)
-        const size_t laneSmem = (size_t)kRowsWarps * ((size_t)kRowsChunk * 4 + (size_t)capR_ * 32 + (size_t)2 * tabHost_.nSpecies * 32) * 4;
-        if (!warpRows && laneSmem <= 200 * 1024) {
-            set_smem(ani_rows_lane_kernel, laneSmem);
-            ani_rows_lane_kernel<<<(n_ + kRowsWarps * 32 - 1) / (kRowsWarps * 32), kRowsWarps * 32, laneSmem, stream>>>(
-                n_, cells_.sorted, cells_.sortedCell, cells_.geom, cells_.cellStart, tab_, capR_, capA_, rowRad_, rowAng_, offRad_, offAng_,
-                flag_);
-        } else {
-            const size_t smem = (size_t)kWPB * capR_ * sizeof(uint32_t) + (size_t)kWPB * 128 * sizeof(int);
-            set_smem(ani_rows_kernel, smem);
-            ani_rows_kernel<<<grid, kWPB * 32, smem, stream>>>(n_, cells_.sorted, cells_.sortedCell, cells_.geom, cells_.cellStart, tab_,
-                                                               capR_, capA_, rowRad_, rowAng_, offRad_, offAng_, flag_);
-        }
+        const size_t smem = (size_t)kWPB * capR_ * sizeof(uint32_t) + (size_t)kWPB * 128 * sizeof(int);
+        set_smem(ani_rows_kernel, smem);
+        ani_rows_kernel<<<grid, kWPB * 32, smem, stream>>>(n_, cells_.sorted, cells_.sortedCell, cells_.geom, cells_.cellStart, tab_,
+                                                           capR_, capA_, rowRad_, rowAng_, offRad_, offAng_, flag_);
         count_launch();
     }
     if (ev) cudaEventRecord(ev[0], stream);
