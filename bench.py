@@ -117,7 +117,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("NNPOPS_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nnpops_nccl.%h.%p.log")      # NCCL logs to stdout otherwise: keep it to the one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -255,6 +255,63 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_box(args):
+    """One 50 000-atom box evaluated cooperatively by all ranks (variant ii): strong scaling.  Every rank holds the
+    positions; a step = owned-centre AEV + MLP + backward on every rank, then ONE NCCL all-reduce of the packed gradient + energy."""
+    import torch
+    from systems import ANI2X, ANI2X_HIDDEN, ANI2X_ENSEMBLE, water_species
+    from mlp_ref import random_networks
+    from nnpops_b200.OptimizedTorchANI import ShardedFusedANI
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nnpops_nccl.%h.%p.log")
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    n = args.atoms
+    nets = random_networks(7, ANI2X_HIDDEN, ANI2X_ENSEMBLE, 1008, seed=42)
+    model = ShardedFusedANI(7, 5.2, ANI2X["Rca"], ANI2X["EtaR"], ANI2X["ShfR"], ANI2X["EtaA"], ANI2X["Zeta"], ANI2X["ShfA"], ANI2X["ShfZ"],
+                            water_species(n), nets, mlp_impl=args.mlp, device="cuda:%d" % local)
+    pool = 4
+    confs = [make_conformer(n, c) for c in range(pool)]            # the SAME conformers on every rank
+    d_pos = [torch.tensor(p, device=dev) for p, _ in confs]
+    d_box = [torch.tensor(b, device=dev) for _, b in confs]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        e, g = model.energy_and_gradient(d_pos[i % pool], d_box[i % pool])
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        e, g = model.energy_and_gradient(d_pos[i % pool], d_box[i % pool])
+    t1.record()
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(t0.elapsed_time(t1), dist, dev)
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": round(args.steps / (ms_total / 1e3), 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ONE %d-atom periodic water box per step sharded over %d GPU(s): centres i %% world == rank per GPU, all "
+                                   "atoms as neighbour candidates, one all-reduce (NCCL) of 12 N + 4 bytes per step" % (n, world),
+                       "atoms": n, "mode": "box", "mlp_impl": args.mlp, "allreduce_bytes_per_step": 12 * n + 4},
+            "energy": float(e.cpu()[0]), "clocks": clocks}), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the reference's CpuANISymmetryFunctions through oracle/_ref (kind "reference") or, when that
 # was never built, the C restatement (kind "port").
@@ -359,10 +416,15 @@ def main():
     ap.add_argument("--mlp", default=os.environ.get("NNPOPS_MLP", DEFAULT_MLP), choices=["tcgen05", "simt"])
     ap.add_argument("--atoms", type=int, default=50000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="conformers", choices=["conformers", "box"],
+                    help="conformers: independent conformers per GPU, no collective (BASELINE config 3, the default); box: ONE box "
+                         "sharded over the GPUs (owned centres per rank, one all-reduce of energy + gradient per step: strong scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "box":
+        run_box(args)
     else:
         run_ours(args)
 

@@ -69,6 +69,15 @@ NNPOPS_API int nnpops_ani_model_create(nnpops_ani_model_t* out, int num_atoms, i
                             const int* atom_species, int n_radial, const float* radial_fn, int n_angular, const float* angular_fn,
                             int ensemble_size, int num_layers, const int* dims, const float* params, int mlp_impl,
                             int max_radial_neighbors, int max_angular_neighbors);
+/* One periodic box sharded over shard_count GPUs (one process per GPU): this model evaluates only the centres i with
+ * i % shard_count == shard_rank, with ALL atoms as neighbour candidates (every rank passes the full position array).  energy is the
+ * rank's partial sum and position_grad its partial dE/dx over all atoms; the caller sums both over the ranks (one all-reduce of
+ * 4 + 12 * num_atoms bytes, e.g. ncclAllReduce over NVLink) -- the "degenerate halo" exchange of SURVEY.md section 8e.  The reference has no
+ * multi-GPU path. */
+NNPOPS_API int nnpops_ani_model_create_sharded(nnpops_ani_model_t* out, int num_atoms, int num_species, float radial_cutoff, float angular_cutoff,
+                            const int* atom_species, int n_radial, const float* radial_fn, int n_angular, const float* angular_fn,
+                            int ensemble_size, int num_layers, const int* dims, const float* params, int mlp_impl,
+                            int max_radial_neighbors, int max_angular_neighbors, int shard_rank, int shard_count);
 NNPOPS_API void nnpops_ani_model_destroy(nnpops_ani_model_t h);
 /* energy: device float[1] (sum over atoms of the ensemble-mean atomic energies, no self-energy shift);
  * position_grad: device float [num_atoms][3] = dE/dx */

@@ -60,11 +60,14 @@ class FusedANI(torch.nn.Module):
 
     species: int sequence [N] with values in [0, num_species); networks[s][e][l] = (W, b) numpy arrays.
     mlp_impl: "tcgen05" (tensor cores) or "simt" (fp32 validation path).
+    shard: (rank, world) -- one box sharded over `world` GPUs: this instance evaluates only the centres i with i % world == rank
+    (all atoms stay neighbour candidates); energy and gradient are then PARTIAL and must be summed over the ranks
+    (ShardedFusedANI does that with one all-reduce).
     """
 
     def __init__(self, num_species: int, Rcr: float, Rca: float, EtaR, ShfR, EtaA, Zeta, ShfA, ShfZ, species: Sequence[int],
                  networks, mlp_impl: str = "tcgen05", device: str = "cuda", max_radial_neighbors: int = 0,
-                 max_angular_neighbors: int = 0):
+                 max_angular_neighbors: int = 0, shard: Tuple[int, int] = (0, 1)):
         super().__init__()
         self.num_atoms = len(species)
         self.num_species = int(num_species)
@@ -76,10 +79,11 @@ class FusedANI(torch.nn.Module):
         sp = np.ascontiguousarray(species, np.int32)
         h = C.c_void_p()
         with torch.cuda.device(self.device_):
-            check(lib.nnpops_ani_model_create(C.byref(h), self.num_atoms, self.num_species, float(Rcr), float(Rca), ptr(sp),
-                                              len(radial_fn), ptr(radial_fn), len(angular_fn), ptr(angular_fn), len(networks[0]),
-                                              dims.shape[1] - 1, ptr(dims), ptr(params), {"simt": 0, "tcgen05": 1}[mlp_impl],
-                                              max_radial_neighbors, max_angular_neighbors))
+            check(lib.nnpops_ani_model_create_sharded(C.byref(h), self.num_atoms, self.num_species, float(Rcr), float(Rca), ptr(sp),
+                                                      len(radial_fn), ptr(radial_fn), len(angular_fn), ptr(angular_fn), len(networks[0]),
+                                                      dims.shape[1] - 1, ptr(dims), ptr(params), {"simt": 0, "tcgen05": 1}[mlp_impl],
+                                                      max_radial_neighbors, max_angular_neighbors, int(shard[0]), int(shard[1])))
+        self.shard = (int(shard[0]), int(shard[1]))
         self._h = h
         self.mlp_impl = mlp_impl
         self.aev_length = int(dims[0, 0])
@@ -168,6 +172,60 @@ class FusedANI(torch.nn.Module):
         f = C.c_int(0)
         check(lib.nnpops_ani_model_overflowed(self._h, C.byref(f)))
         return f.value
+
+
+def shard_mask(num_atoms: int, rank: int, world: int) -> np.ndarray:
+    """Ownership of the centres when one box is sharded over `world` ranks: atom i belongs to rank i mod world (the rule of
+    nnpops_ani_model_create_sharded).  Interleaving balances species and density without looking at the geometry."""
+    return (np.arange(num_atoms) % world) == rank
+
+
+class ShardedFusedANI(torch.nn.Module):
+    """One periodic box evaluated cooperatively by all ranks of a torch.distributed group (one process per GPU): every rank holds
+    the full position array, evaluates the AEVs and networks of its own centres (FusedANI with shard=(rank, world)) and the
+    partial energy and dE/dx are summed with ONE all-reduce of 4 + 12 N bytes (NCCL over NVLink) -- the exchange step of
+    SURVEY.md section 8e, variant (ii).  ``energy_and_gradient`` returns the TOTAL energy [1] and gradient [N, 3] on every rank.
+    The reference has no multi-GPU path."""
+
+    def __init__(self, *args, group=None, local_factory=None, **kwargs):
+        super().__init__()
+        import torch.distributed as dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        # local_factory(rank, world) -> object with energy_and_gradient(positions, cell): lets the host logic run without a GPU
+        self.local = (local_factory(self.rank, self.world) if local_factory is not None
+                      else FusedANI(*args, shard=(self.rank, self.world), **kwargs))
+        self._packed = None
+
+    def energy_and_gradient(self, positions: Tensor, cell: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+        e, g = self.local.energy_and_gradient(positions, cell)
+        if self.world == 1:
+            return e, g
+        import torch.distributed as dist
+        n = g.shape[0]
+        if self._packed is None or self._packed.numel() != 3 * n + 1:
+            self._packed = torch.empty(3 * n + 1, dtype=torch.float32, device=g.device)
+        self._packed[:3 * n] = g.reshape(-1)      # one message: gradient + energy
+        self._packed[3 * n:] = e
+        dist.all_reduce(self._packed, op=dist.ReduceOp.SUM, group=self.group)
+        return self._packed[3 * n:].clone(), self._packed[:3 * n].reshape(n, 3).clone()
+
+    def forward(self, positions: Tensor, cell: Optional[Tensor] = None) -> Tensor:
+        return _ShardedEnergyGrad.apply(self, positions, cell)
+
+
+class _ShardedEnergyGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, positions, cell):
+        e, g = model.energy_and_gradient(positions, cell)
+        ctx.save_for_backward(g)
+        return e
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (g,) = ctx.saved_tensors
+        return None, g * grad_out, None
 
 
 def _linear_layers(sequential) -> List[Tuple[np.ndarray, np.ndarray]]:

@@ -43,6 +43,10 @@ public:
     // Optional map atom -> output row (device int[numAtoms]); nullptr = identity.  Used by the fused ANI model to write the AEV
     // matrix in species-sorted row order.
     void setRowMap(const int* deviceRowMap) { rowMap_ = deviceRowMap; }
+    // Optional ownership mask (device unsigned char[numAtoms], indexed by atom): when one box is sharded over several GPUs a rank
+    // evaluates only the centres it owns (all atoms stay neighbour candidates) and backward() switches to the centre-owned radial
+    // form, so that positionGrad holds this rank's PARTIAL dE/dx over all atoms (sum over ranks = total).  nullptr = all owned.
+    void setOwned(const unsigned char* deviceMask) { owned_ = deviceMask; }
 
     // positions [n][3], box [3][3] or nullptr (all device, fp32).  radial/angular: device, row strides in floats.
     // ev (optional): forward records ev[0] after the neighbour rows and ev[1] after the radial kernel; backward records ev[0]
@@ -78,6 +82,7 @@ private:
     int* flag_ = nullptr;        // overflow flag
     unsigned long long* counters_ = nullptr;   // [2] scratch for countTriples / countRadialPairs
     const int* rowMap_ = nullptr;
+    const unsigned char* owned_ = nullptr;
     bool haveForward_ = false;
     cudaStream_t aux_ = nullptr;            // radial kernels run here, concurrently with the angular kernels on the caller's stream
     cudaEvent_t evFork_ = nullptr, evJoin_ = nullptr;

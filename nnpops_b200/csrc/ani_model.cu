@@ -38,9 +38,15 @@ void AniModel::readFeatures(int which, float* out, cudaStream_t stream) {
 // columns, a 5-element protein 560.  NNPOPS_DENSE_AEV=1 (or compact = false) disables it.
 AniModel::AniModel(int numAtoms, int numSpecies, float rcr, float rca, const int* atomSpecies, int nRadial, const float* radialFn,
                    int nAngular, const float* angularFn, int ensemble, int numLayers, const int* dims, const float* params,
-                   int maxRadialNeighbors, int maxAngularNeighbors, bool compact)
+                   int maxRadialNeighbors, int maxAngularNeighbors, bool compact, int shardRank, int shardCount)
     : n_(numAtoms) {
     NNP_REQUIRE(numSpecies >= 1 && numSpecies <= kAniMaxSpecies, "unsupported number of species");
+    NNP_REQUIRE(shardCount >= 1 && shardRank >= 0 && shardRank < shardCount, "shard rank must be in [0, shard count)");
+    // One box sharded over several GPUs: atom i is a CENTRE of rank i mod shardCount (interleaved ownership balances species and
+    // density without any knowledge of the geometry); every atom stays a neighbour candidate on every rank.
+    std::vector<unsigned char> owned(numAtoms > 0 ? numAtoms : 1, 1);
+    if (shardCount > 1)
+        for (int i = 0; i < numAtoms; i++) owned[i] = (i % shardCount == shardRank) ? 1 : 0;
     const int S = numSpecies, L = numLayers;
     const int nFeatFull = S * nRadial + S * (S + 1) / 2 * nAngular;
     NNP_REQUIRE(dims[0] == nFeatFull, "network input size must equal the AEV length");
@@ -73,8 +79,8 @@ AniModel::AniModel(int numAtoms, int numSpecies, float rcr, float rca, const int
     std::vector<int> speciesC(numAtoms), dimsC((size_t)Sc * (L + 1));
     for (int i = 0; i < numAtoms; i++) speciesC[i] = compactOf[atomSpecies[i]];
     std::vector<float> paramsC;
-    std::vector<long long> atomsOf(S, 0);
-    for (int i = 0; i < numAtoms; i++) atomsOf[atomSpecies[i]]++;
+    std::vector<long long> atomsOf(S, 0);   // centres of this rank per species
+    for (int i = 0; i < numAtoms; i++) atomsOf[atomSpecies[i]] += owned[i];
     {
         const float* p = params;
         for (int s = 0; s < S; s++) {
@@ -109,13 +115,19 @@ AniModel::AniModel(int numAtoms, int numSpecies, float rcr, float rca, const int
     stride_ = (nFeat + kMlpPad - 1) / kMlpPad * kMlpPad;
     // species-sorted row order (stable in the atom index): the species of a system never change, so this is done once
     std::vector<int> rowStart(Sc + 1, 0);
-    for (int i = 0; i < numAtoms; i++) rowStart[speciesC[i] + 1]++;
+    for (int i = 0; i < numAtoms; i++) rowStart[speciesC[i] + 1] += owned[i];
     for (int s = 0; s < Sc; s++) rowStart[s + 1] += rowStart[s];
+    const int nOwned = rowStart[Sc];
     std::vector<int> cursor(rowStart.begin(), rowStart.end() - 1);
     rowOfAtom_.resize(numAtoms);
-    for (int i = 0; i < numAtoms; i++) rowOfAtom_[i] = cursor[speciesC[i]]++;
-    const size_t na = (size_t)(numAtoms > 0 ? numAtoms : 1);
-    NNP_CUDA_CHECK(cudaMalloc(&rowMap_, sizeof(int) * na));
+    // centres of other ranks have empty neighbour rows; whatever the AEV kernels store for them lands in the spare row nOwned
+    for (int i = 0; i < numAtoms; i++) rowOfAtom_[i] = owned[i] ? cursor[speciesC[i]]++ : nOwned;
+    const size_t na = (size_t)nOwned + 1;
+    if (shardCount > 1) {
+        NNP_CUDA_CHECK(cudaMalloc(&owned_, owned.size()));
+        NNP_CUDA_CHECK(cudaMemcpy(owned_, owned.data(), owned.size(), cudaMemcpyHostToDevice));
+    }
+    NNP_CUDA_CHECK(cudaMalloc(&rowMap_, sizeof(int) * (size_t)(numAtoms > 0 ? numAtoms : 1)));
     if (numAtoms > 0) NNP_CUDA_CHECK(cudaMemcpy(rowMap_, rowOfAtom_.data(), sizeof(int) * numAtoms, cudaMemcpyHostToDevice));
     NNP_CUDA_CHECK(cudaMalloc(&colOfFull_, sizeof(int) * nFeatFull));
     NNP_CUDA_CHECK(cudaMemcpy(colOfFull_, colOfFull.data(), sizeof(int) * nFeatFull, cudaMemcpyHostToDevice));
@@ -124,11 +136,12 @@ AniModel::AniModel(int numAtoms, int numSpecies, float rcr, float rca, const int
     NNP_CUDA_CHECK(cudaMemset(feat_, 0, sizeof(float) * na * stride_));   // padding columns stay zero forever
     NNP_CUDA_CHECK(cudaMemset(featGrad_, 0, sizeof(float) * na * stride_));
     aev_->setRowMap(rowMap_);
+    aev_->setOwned(owned_);
     mlp_.reset(new SpeciesMlp(Sc, ensemble, numLayers, dimsC.data(), paramsC.data(), rowStart.data(), stride_));
 }
 
 AniModel::~AniModel() {
-    cudaFree(rowMap_); cudaFree(colOfFull_); cudaFree(feat_); cudaFree(featGrad_);
+    cudaFree(rowMap_); cudaFree(owned_); cudaFree(colOfFull_); cudaFree(feat_); cudaFree(featGrad_);
     for (cudaEvent_t e : events_) cudaEventDestroy(e);
 }
 

@@ -12,7 +12,7 @@ class AniModel {
 public:
     AniModel(int numAtoms, int numSpecies, float rcr, float rca, const int* atomSpecies, int nRadial, const float* radialFn,
              int nAngular, const float* angularFn, int ensemble, int numLayers, const int* dims, const float* params,
-             int maxRadialNeighbors, int maxAngularNeighbors, bool compact = true);
+             int maxRadialNeighbors, int maxAngularNeighbors, bool compact = true, int shardRank = 0, int shardCount = 1);
     ~AniModel();
     // energy: device float[1]; positionGrad: device [n][3] = dE/dx (forces = -positionGrad)
     void energyAndGradient(const float* positions, const float* box, float* energy, float* positionGrad, cudaStream_t stream);
@@ -38,6 +38,7 @@ private:
     std::unique_ptr<SpeciesMlp> mlp_;
     int n_, stride_, nFeat_, nFeatFull_;
     double denseFlopsFwd_ = 0;
+    unsigned char* owned_ = nullptr;   // device [numAtoms] when the box is sharded over several ranks (else nullptr)
     int* colOfFull_ = nullptr;   // device [nFeatFull]: compact column or -1
     float* feat_ = nullptr;
     float* featGrad_ = nullptr;

@@ -142,13 +142,23 @@ int nnpops_ani_model_create(nnpops_ani_model_t* out, int num_atoms, int num_spec
                             const int* atom_species, int n_radial, const float* radial_fn, int n_angular, const float* angular_fn,
                             int ensemble_size, int num_layers, const int* dims, const float* params, int mlp_impl,
                             int max_radial_neighbors, int max_angular_neighbors) {
+    return nnpops_ani_model_create_sharded(out, num_atoms, num_species, radial_cutoff, angular_cutoff, atom_species, n_radial, radial_fn,
+                                           n_angular, angular_fn, ensemble_size, num_layers, dims, params, mlp_impl, max_radial_neighbors,
+                                           max_angular_neighbors, 0, 1);
+}
+
+int nnpops_ani_model_create_sharded(nnpops_ani_model_t* out, int num_atoms, int num_species, float radial_cutoff, float angular_cutoff,
+                                    const int* atom_species, int n_radial, const float* radial_fn, int n_angular, const float* angular_fn,
+                                    int ensemble_size, int num_layers, const int* dims, const float* params, int mlp_impl,
+                                    int max_radial_neighbors, int max_angular_neighbors, int shard_rank, int shard_count) {
     return guarded([&] {
         require_device();
         NNP_REQUIRE(out != nullptr, "out must not be NULL");
         auto* h = new nnpops_ani_model;
         try {
             h->impl = new AniModel(num_atoms, num_species, radial_cutoff, angular_cutoff, atom_species, n_radial, radial_fn, n_angular,
-                                   angular_fn, ensemble_size, num_layers, dims, params, max_radial_neighbors, max_angular_neighbors);
+                                   angular_fn, ensemble_size, num_layers, dims, params, max_radial_neighbors, max_angular_neighbors, true,
+                                   shard_rank, shard_count);
             h->impl->mlp().setImpl(mlp_impl == 1 ? MlpImpl::Tcgen05 : MlpImpl::Simt);
             h->n = num_atoms;
         } catch (...) {

@@ -247,7 +247,7 @@ SpeciesMlp::SpeciesMlp(int numSpecies, int ensemble, int numLayers, const int* d
     }
     act_.assign(L_ - 1, nullptr);
     dz_.assign(L_ - 1, nullptr);
-    const size_t nr = (size_t)std::max(rows_, 1);
+    const size_t nr = (size_t)rows_ + 1;   // one spare row (target of the AEV stores of centres this rank does not own)
     for (int l = 0; l < L_ - 1; l++) {
         NNP_CUDA_CHECK(cudaMalloc(&act_[l], sizeof(float) * nr * width_[l]));
         NNP_CUDA_CHECK(cudaMalloc(&dz_[l], sizeof(float) * nr * width_[l]));
@@ -288,7 +288,7 @@ void SpeciesMlp::setImpl(MlpImpl impl) {
             to_split_device(ly.W, cnt, &ly.Whi, &ly.Wlo);
             to_split_device(ly.Wt, cnt, &ly.Wthi, &ly.Wtlo);
         }
-    const size_t nr = (size_t)std::max(rows_, 1);
+    const size_t nr = (size_t)rows_ + 1;   // one spare row (target of the AEV stores of centres this rank does not own)
     actHi_.assign(L_ - 1, nullptr); actLo_.assign(L_ - 1, nullptr); dzHi_.assign(L_ - 1, nullptr); dzLo_.assign(L_ - 1, nullptr);
     for (int l = 0; l < L_ - 1; l++) {
         for (__half** p : {&actHi_[l], &actLo_[l], &dzHi_[l], &dzLo_[l]}) {

@@ -46,3 +46,60 @@ def test_single_rank_sharding_is_identity():
     import bench
     assert bench.shard_conformers(5, 0, 1) == [0, 1, 2, 3, 4]
     assert bench.max_over_ranks(3.5, None, torch.device("cpu")) == 3.5
+
+
+class _FakeLocal:
+    """Stand-in for FusedANI(shard=(rank, world)) on CPU: a pair potential whose centres are split with the library's own rule."""
+
+    def __init__(self, rank, world, n):
+        from nnpops_b200.OptimizedTorchANI import shard_mask
+        self.mask = torch.from_numpy(shard_mask(n, rank, world))
+
+    def energy_and_gradient(self, positions, cell=None):
+        with torch.enable_grad():                                                # also called inside an autograd.Function
+            pos = positions.detach().clone().requires_grad_(True)
+            d = (pos[:, None, :] - pos[None, :, :]).norm(dim=-1) + torch.eye(len(pos))
+            e_atom = (torch.exp(-d) * (1 - torch.eye(len(pos)))).sum(1)      # energy of centre i: depends on all atoms
+            e = (e_atom * self.mask).sum().reshape(1)
+            (g,) = torch.autograd.grad(e.sum(), pos)
+        return e.detach().float(), g.float()
+
+
+def _box_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    from nnpops_b200.OptimizedTorchANI import ShardedFusedANI
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 37
+    pos = torch.linspace(0, 5, 3 * n).reshape(n, 3).float() ** 1.3
+    m = ShardedFusedANI(local_factory=lambda r, w: _FakeLocal(r, w, n))
+    e, g = m.energy_and_gradient(pos)
+    p2 = pos.clone().requires_grad_(True)
+    m(p2).sum().backward()                                                  # the autograd face gives the same total gradient
+    ref = _FakeLocal(0, 1, n).energy_and_gradient(pos)
+    out.put((rank, float((e - ref[0]).abs().max()), float((g - ref[1]).abs().max()), float((p2.grad - ref[1]).abs().max())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_box_allreduce_world2():
+    """One box sharded over 2 ranks (gloo): partial energies / gradients of the owned centres sum to the single-rank result on
+    EVERY rank; the ownership masks partition the atoms."""
+    sys.path.insert(0, ROOT)
+    from nnpops_b200.OptimizedTorchANI import shard_mask
+    masks = [shard_mask(37, r, 3) for r in range(3)]
+    assert (sum(m.astype(int) for m in masks) == 1).all()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_box_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(2)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert sorted(r[0] for r in res) == [0, 1]
+    for _, de, dg, dga in res:
+        assert de < 1e-4 and dg < 1e-5 and dga < 1e-5
