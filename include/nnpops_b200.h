@@ -155,6 +155,14 @@ NNPOPS_API int nnpops_pme_direct(const float* positions, const float* charges, c
 NNPOPS_API int nnpops_pme_reciprocal_forward(const float* positions, const float* charges, const float* box, int num_atoms, int gridx,
                                              int gridy, int gridz, int order, float alpha, float coulomb, const float* xmoduli,
                                              const float* ymoduli, const float* zmoduli, float* energy, float* recip_grid, void* stream);
+/* The forward pass in two stages, for a system sharded over several GPUs (one process per GPU): every rank spreads ITS atoms into a
+ * full-size real grid float [gridx][gridy][gridz] (zeroed by the call), the ranks sum their grids (one all-reduce, e.g. ncclAllReduce
+ * over NVLink), and every rank solves the same grid (FFT + convolution + energy) so that nnpops_pme_reciprocal_backward can then be
+ * called with the rank's own atoms.  nnpops_pme_reciprocal_forward == spread into an internal grid + solve.  (pmeCUDA.cu:30-168.) */
+NNPOPS_API int nnpops_pme_spread(const float* positions, const float* charges, const float* box, int num_atoms, int gridx, int gridy,
+                                 int gridz, int order, float coulomb, float* real_grid, void* stream);
+NNPOPS_API int nnpops_pme_solve(float* real_grid, const float* box, int gridx, int gridy, int gridz, float alpha, const float* xmoduli,
+                                const float* ymoduli, const float* zmoduli, float* energy, float* recip_grid, void* stream);
 NNPOPS_API int nnpops_pme_reciprocal_backward(const float* positions, const float* charges, const float* box, int num_atoms, int gridx,
                                               int gridy, int gridz, int order, float coulomb, const float* recip_grid, float* pos_deriv,
                                               float* charge_deriv, void* stream);

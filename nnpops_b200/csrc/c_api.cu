@@ -29,6 +29,8 @@ void pme_reciprocal_forward(const float*, const float*, const float*, int, int, 
                             const float*, float*, float*, cudaStream_t);
 void pme_reciprocal_backward(const float*, const float*, const float*, int, int, int, int, int, float, const float*, float*, float*,
                              cudaStream_t);
+void pme_spread(const float*, const float*, const float*, int, int, int, int, int, float, float*, cudaStream_t);
+void pme_solve(float*, const float*, int, int, int, float, const float*, const float*, const float*, float*, float*, cudaStream_t);
 }
 
 using namespace nnpops;
@@ -336,6 +338,24 @@ int nnpops_pme_reciprocal_forward(const float* positions, const float* charges, 
         require_device();
         pme_reciprocal_forward(positions, charges, box, num_atoms, gridx, gridy, gridz, order, alpha, coulomb, xmoduli, ymoduli, zmoduli,
                                energy, recip_grid, (cudaStream_t)stream);
+    });
+}
+
+int nnpops_pme_spread(const float* positions, const float* charges, const float* box, int num_atoms, int gridx, int gridy, int gridz,
+                      int order, float coulomb, float* real_grid, void* stream) {
+    return guarded([&] {
+        require_device();
+        NNP_REQUIRE(real_grid != nullptr, "real_grid must not be NULL");
+        pme_spread(positions, charges, box, num_atoms, gridx, gridy, gridz, order, coulomb, real_grid, (cudaStream_t)stream);
+    });
+}
+
+int nnpops_pme_solve(float* real_grid, const float* box, int gridx, int gridy, int gridz, float alpha, const float* xmoduli,
+                     const float* ymoduli, const float* zmoduli, float* energy, float* recip_grid, void* stream) {
+    return guarded([&] {
+        require_device();
+        NNP_REQUIRE(real_grid != nullptr && recip_grid != nullptr && energy != nullptr, "real_grid, recip_grid and energy must not be NULL");
+        pme_solve(real_grid, box, gridx, gridy, gridz, alpha, xmoduli, ymoduli, zmoduli, energy, recip_grid, (cudaStream_t)stream);
     });
 }
 

@@ -357,31 +357,50 @@ void pme_direct(const float* positions, const float* charges, const int* neighbo
     NNP_CUDA_CHECK(cudaGetLastError());
 }
 
-// recipGrid: device float2 [gx][gy][gz/2+1], receives the convolved half-complex grid (saved by the caller for backward)
-void pme_reciprocal_forward(const float* positions, const float* charges, const float* box, int numAtoms, int gx, int gy, int gz, int order,
-                            float alpha, float coulomb, const float* xmod, const float* ymod, const float* zmod, float* energy,
-                            float* recipGrid, cudaStream_t stream) {
+// The reciprocal-space forward pass in two stages, so that a system sharded over several GPUs can sum its charge grids between
+// them (one all-reduce of gx * gy * gz floats; SURVEY.md section 8e, PME row):
+//   pme_spread: realGrid[gx][gy][gz] <- B-spline charge spreading of the atoms given (zeroes the grid first)   pmeCUDA.cu:30-93
+//   pme_solve : R2C FFT of realGrid, convolution with the Ewald kernel, energy                                  pmeCUDA.cu:95-168
+void pme_spread(const float* positions, const float* charges, const float* box, int numAtoms, int gx, int gy, int gz, int order,
+                float coulomb, float* realGrid, cudaStream_t stream) {
     NNP_REQUIRE(order == 4 || order == 5, "Only pmeOrder 4 or 5 is supported with CUDA");
     NNP_REQUIRE(gx > 0 && gy > 0 && gz > 0, "The grid dimensions must be positive");
-    PmeWorkspace& ws = pme_workspace(gx, gy, gz);
     const size_t nReal = (size_t)gx * gy * gz;
-    NNP_CUDA_CHECK(cudaMemsetAsync(ws.realGrid, 0, sizeof(float) * nReal, stream));
-    NNP_CUDA_CHECK(cudaMemsetAsync(ws.energyAcc, 0, sizeof(double), stream));
+    NNP_CUDA_CHECK(cudaMemsetAsync(realGrid, 0, sizeof(float) * nReal, stream));
     const float sqrtCoulomb = (float)std::sqrt((double)coulomb);
     if (numAtoms > 0) {
         const int grid = std::min((numAtoms + 127) / 128, sm_count() * 8);
-        if (order == 4) pme_spread_kernel<4><<<grid, 128, 0, stream>>>(numAtoms, positions, charges, box, gx, gy, gz, sqrtCoulomb, ws.realGrid);
-        else pme_spread_kernel<5><<<grid, 128, 0, stream>>>(numAtoms, positions, charges, box, gx, gy, gz, sqrtCoulomb, ws.realGrid);
+        if (order == 4) pme_spread_kernel<4><<<grid, 128, 0, stream>>>(numAtoms, positions, charges, box, gx, gy, gz, sqrtCoulomb, realGrid);
+        else pme_spread_kernel<5><<<grid, 128, 0, stream>>>(numAtoms, positions, charges, box, gx, gy, gz, sqrtCoulomb, realGrid);
         count_launch();
     }
+    NNP_CUDA_CHECK(cudaGetLastError());
+}
+
+// recipGrid: device float2 [gx][gy][gz/2+1], receives the convolved half-complex grid (saved by the caller for backward)
+void pme_solve(float* realGrid, const float* box, int gx, int gy, int gz, float alpha, const float* xmod, const float* ymod,
+               const float* zmod, float* energy, float* recipGrid, cudaStream_t stream) {
+    NNP_REQUIRE(gx > 0 && gy > 0 && gz > 0, "The grid dimensions must be positive");
+    PmeWorkspace& ws = pme_workspace(gx, gy, gz);
+    NNP_CUDA_CHECK(cudaMemsetAsync(ws.energyAcc, 0, sizeof(double), stream));
     NNP_CUFFT_CHECK(cufftSetStream(ws.r2c, stream));
-    NNP_CUFFT_CHECK(cufftExecR2C(ws.r2c, ws.realGrid, reinterpret_cast<cufftComplex*>(recipGrid)));
+    NNP_CUFFT_CHECK(cufftExecR2C(ws.r2c, realGrid, reinterpret_cast<cufftComplex*>(recipGrid)));
     const long long total = (long long)gx * gy * (gz / 2 + 1);
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 8);
     pme_convolve_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<float2*>(recipGrid), box, gx, gy, gz, alpha, xmod, ymod, zmod, ws.energyAcc);
     publish_energy_kernel<<<1, 1, 0, stream>>>(ws.energyAcc, 0.5, energy);
     count_launch(2);
     NNP_CUDA_CHECK(cudaGetLastError());
+}
+
+void pme_reciprocal_forward(const float* positions, const float* charges, const float* box, int numAtoms, int gx, int gy, int gz, int order,
+                            float alpha, float coulomb, const float* xmod, const float* ymod, const float* zmod, float* energy,
+                            float* recipGrid, cudaStream_t stream) {
+    NNP_REQUIRE(order == 4 || order == 5, "Only pmeOrder 4 or 5 is supported with CUDA");
+    NNP_REQUIRE(gx > 0 && gy > 0 && gz > 0, "The grid dimensions must be positive");
+    PmeWorkspace& ws = pme_workspace(gx, gy, gz);
+    pme_spread(positions, charges, box, numAtoms, gx, gy, gz, order, coulomb, ws.realGrid, stream);
+    pme_solve(ws.realGrid, box, gx, gy, gz, alpha, xmod, ymod, zmod, energy, recipGrid, stream);
 }
 
 void pme_reciprocal_backward(const float* positions, const float* charges, const float* box, int numAtoms, int gx, int gy, int gz, int order,

@@ -103,3 +103,18 @@ def test_sharded_box_allreduce_world2():
     assert sorted(r[0] for r in res) == [0, 1]
     for _, de, dg, dga in res:
         assert de < 1e-4 and dg < 1e-5 and dga < 1e-5
+
+
+def test_shard_range_partitions():
+    sys.path.insert(0, ROOT)
+    import importlib
+    import types
+    # the PME module needs the CUDA library at import: test the pure helper through its source
+    src = open(os.path.join(ROOT, "nnpops_b200", "pme", "pme.py")).read()
+    start = src.index("def shard_range"); end = src.index("def pme_spread")
+    ns = {}
+    exec(src[start:end], ns)
+    for n, w in ((200000, 8), (7, 3), (5, 8), (0, 2)):
+        blocks = [ns["shard_range"](n, r, w) for r in range(w)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(b[1] == blocks[i + 1][0] for i, b in enumerate(blocks[:-1])) and all(lo <= hi for lo, hi in blocks)

@@ -223,6 +223,42 @@ def test_pme_random_system_vs_oracle():
     assert rel_err(ch.grad.cpu().numpy(), q0d + q0r) < 1e-4
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_pme_reciprocal_sharded_matches_single(world):
+    """Reciprocal PME with the atoms dealt to `world` ranks, emulated on one GPU: every rank spreads its block, the
+    grids are summed (the all-reduce), every rank solves the same grid and differentiates its own atoms; energy and the assembled
+    derivatives equal the single-rank op."""
+    from nnpops_b200.pme import PME
+    from nnpops_b200.pme.pme import pme_reciprocal, pme_reciprocal_sharded, pme_spread, shard_range
+    rng = np.random.default_rng(11)
+    n = 501
+    box = np.array([[3.0, 0, 0], [0.4, 3.1, 0], [-0.3, 0.5, 2.9]], np.float32)
+    pos = (rng.uniform(0, 1, (n, 3)) @ box).astype(np.float32)
+    q = rng.uniform(-0.5, 0.5, n).astype(np.float32); q -= q.mean()
+    pme = PME(32, 30, 36, 5, 3.2, 138.935, torch.zeros((n, 0), dtype=torch.int32))
+    mod = [m.cuda() for m in pme.moduli]
+    b = torch.tensor(box, device="cuda")
+    p0 = torch.tensor(pos, device="cuda", requires_grad=True); c0 = torch.tensor(q, device="cuda", requires_grad=True)
+    e0 = pme_reciprocal(p0, c0, b, 32, 30, 36, 5, 3.2, 138.935, *mod)
+    e0.backward()
+    # what the all-reduce would deliver: the sum of the ranks' private grids
+    total = sum(pme_spread(p0.detach()[slice(*shard_range(n, r, world))], c0.detach()[slice(*shard_range(n, r, world))], b, 32, 30, 36, 5, 138.935)
+                for r in range(world))
+    gp = torch.zeros_like(p0); gq = torch.zeros_like(c0)
+    for r in range(world):
+        def reduce(t, r=r):                       # grid: replace by the global sum; packed derivatives: keep the local block (summed below)
+            if t.dim() == 3:
+                t.copy_(total)
+        p = torch.tensor(pos, device="cuda", requires_grad=True); c = torch.tensor(q, device="cuda", requires_grad=True)
+        e = pme_reciprocal_sharded(p, c, b, 32, 30, 36, 5, 3.2, 138.935, *mod, emulate=(r, world, reduce))
+        assert abs(e.item() - e0.item()) <= 2e-6 * abs(e0.item()) + 1e-5
+        e.backward()
+        lo, hi = shard_range(n, r, world)
+        assert not p.grad[:lo].any() and not p.grad[hi:].any()          # a rank differentiates its own atoms only
+        gp += p.grad; gq += c.grad
+    assert rel_err(gp.cpu().numpy(), p0.grad.cpu().numpy()) < 2e-6 and rel_err(gq.cpu().numpy(), c0.grad.cpu().numpy()) < 2e-6
+
+
 def test_pme_double_derivative_raises():
     """TestPme.py:296-318."""
     from nnpops_b200.pme import PME
