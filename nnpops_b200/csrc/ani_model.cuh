@@ -22,6 +22,7 @@ public:
     static constexpr int kStages = 7;
     void timingBegin(int maxSteps);
     int timingEnd(float* stageMs);
+    bool timingActive() const { return timingUsed_ < timingCap_; }
     void readFeatures(int which, float* out, cudaStream_t stream);   // atom order, [n][aevLength]
     int aevLength() const { return nFeatFull_; }        // the model's full AEV length (readFeatures layout)
     int activeFeatures() const { return nFeat_; }      // columns that can be non-zero for this system's species

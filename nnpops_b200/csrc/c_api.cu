@@ -3,6 +3,7 @@
 #include <cstring>
 #include <string>
 #include "ani_model.cuh"
+#include <cstdlib>
 
 namespace nnpops {
 void batched_linear_forward(const float*, const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
@@ -72,6 +73,12 @@ struct nnpops_ani_model {
     float* dGrad = nullptr;
     float* dEnergy = nullptr;
     int n = 0;
+    // The host-buffer entry point works on handle-owned device buffers, so its whole kernel sequence (~25 launches on two streams,
+    // 48 tensor-map encodes) is captured once into a CUDA graph and replayed: one launch call per evaluation instead of ~25.
+    cudaGraphExec_t graphExec = nullptr;
+    cudaStream_t capStream = nullptr;
+    int graphHasBox = -1;
+    int hostCalls = 0;
 };
 
 struct nnpops_cfconv_neighbors {
@@ -173,6 +180,8 @@ int nnpops_ani_model_create_sharded(nnpops_ani_model_t* out, int num_atoms, int 
 
 void nnpops_ani_model_destroy(nnpops_ani_model_t h) {
     if (!h) return;
+    if (h->graphExec) cudaGraphExecDestroy(h->graphExec);
+    if (h->capStream) cudaStreamDestroy(h->capStream);
     delete h->impl;
     cudaFree(h->dPos); cudaFree(h->dBox); cudaFree(h->dGrad); cudaFree(h->dEnergy);
     delete h;
@@ -200,7 +209,34 @@ int nnpops_ani_model_energy_grad_host(nnpops_ani_model_t h, const float* positio
         }
         NNP_CUDA_CHECK(cudaMemcpyAsync(h->dPos, positions_host, sizeof(float) * 3 * h->n, cudaMemcpyHostToDevice, s));
         if (box_host) NNP_CUDA_CHECK(cudaMemcpyAsync(h->dBox, box_host, sizeof(float) * 9, cudaMemcpyHostToDevice, s));
-        h->impl->energyAndGradient(h->dPos, box_host ? h->dBox : nullptr, h->dEnergy, h->dGrad, s);
+        static const bool noGraph = std::getenv("NNPOPS_NO_GRAPH") != nullptr;
+        const int hasBox = box_host ? 1 : 0;
+        const bool graphable = !noGraph && !h->impl->timingActive() && h->n > 0;
+        if (graphable && h->graphExec && h->graphHasBox == hasBox) {
+            NNP_CUDA_CHECK(cudaGraphLaunch(h->graphExec, s));
+        } else if (graphable && h->hostCalls >= 1) {
+            // the first call ran eagerly (one-time attribute / workspace set-up); capture on a private stream (the caller's may be the
+            // legacy default stream, which cannot be captured) and replay on the caller's
+            if (h->graphExec) { cudaGraphExecDestroy(h->graphExec); h->graphExec = nullptr; }
+            if (!h->capStream) NNP_CUDA_CHECK(cudaStreamCreateWithFlags(&h->capStream, cudaStreamNonBlocking));
+            cudaGraph_t graph = nullptr;
+            NNP_CUDA_CHECK(cudaStreamBeginCapture(h->capStream, cudaStreamCaptureModeThreadLocal));
+            try {
+                h->impl->energyAndGradient(h->dPos, box_host ? h->dBox : nullptr, h->dEnergy, h->dGrad, h->capStream);
+            } catch (...) {
+                cudaStreamEndCapture(h->capStream, &graph);
+                if (graph) cudaGraphDestroy(graph);
+                throw;
+            }
+            NNP_CUDA_CHECK(cudaStreamEndCapture(h->capStream, &graph));
+            NNP_CUDA_CHECK(cudaGraphInstantiate(&h->graphExec, graph, 0));
+            cudaGraphDestroy(graph);
+            h->graphHasBox = hasBox;
+            NNP_CUDA_CHECK(cudaGraphLaunch(h->graphExec, s));
+        } else {
+            h->impl->energyAndGradient(h->dPos, box_host ? h->dBox : nullptr, h->dEnergy, h->dGrad, s);
+        }
+        h->hostCalls++;
         NNP_CUDA_CHECK(cudaMemcpyAsync(energy_host, h->dEnergy, sizeof(float), cudaMemcpyDeviceToHost, s));
         NNP_CUDA_CHECK(cudaMemcpyAsync(position_grad_host, h->dGrad, sizeof(float) * 3 * h->n, cudaMemcpyDeviceToHost, s));
         NNP_CUDA_CHECK(cudaStreamSynchronize(s));
