@@ -216,7 +216,7 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 template <int MODE, typename WAIT>
 __device__ __forceinline__ void epilogue_tile(const TcArgs& g, uint32_t tmemBase, int acc, int q, int hsel, int lane, int mt, int nt, int z,
                                               unsigned char* stg, float& esum, const uint32_t (&actH)[16], const uint32_t (&actL)[16],
-                                              WAIT&& waitAccumulator) {
+                                              float biasLane, float w3Lane, WAIT&& waitAccumulator) {
     const int mw = mt * TBM + q * 32;              // first row of this warp
     const int m = mw + lane, n0 = nt * TBN;
     const int rowsValid = min(32, g.M - mw);       // warp-uniform, may be <= 0
@@ -225,20 +225,26 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& g, uint32_t tmemBase
     const int c = hsel;
     const int n = n0 + c * 32;
     if (n < g.N) {                                  // warp-uniform
+        if (MODE == 1 || MODE == 3) {
+            // bias (and last-layer weights) of the warp's 32 columns were fetched one tile ahead, one column per lane; they pass
+            // through the (idle) staging block so that every lane can read them as broadcast float4
+            reinterpret_cast<float*>(stg)[lane] = biasLane;
+            if (MODE == 3) reinterpret_cast<float*>(stg)[32 + lane] = w3Lane;
+            __syncwarp();
+        }
         waitAccumulator(); waited = true;
         uint32_t ph[16], pl[16];
         const bool rowOk = m < g.M;
 #pragma unroll
         for (int h = 0; h < 2; h++) {               // two 16-column halves keep the register footprint small
             float4 bv[4], wv[4];
-            if (MODE == 1 || MODE == 3) {       // bias (and last-layer weights), requested before the accumulator is read
-                const float4* bp = reinterpret_cast<const float4*>(g.bias + (size_t)z * g.biasBatch + n + 16 * h);
+            if (MODE == 1 || MODE == 3) {
+                const float4* bp = reinterpret_cast<const float4*>(stg) + 4 * h;
 #pragma unroll
-                for (int j = 0; j < 4; j++) bv[j] = __ldg(bp + j);
+                for (int j = 0; j < 4; j++) bv[j] = bp[j];
                 if (MODE == 3) {
-                    const float4* wp = reinterpret_cast<const float4*>(g.w3 + (size_t)z * g.biasBatch + n + 16 * h);
 #pragma unroll
-                    for (int j = 0; j < 4; j++) wv[j] = __ldg(wp + j);
+                    for (int j = 0; j < 4; j++) wv[j] = bp[8 + j];
                 }
             }
             uint32_t r1[16], r2[16];
@@ -293,6 +299,7 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& g, uint32_t tmemBase
                 pl[8 * h + i] = pack_h2((v[2 * i] - f2.x) * kLoScale, (v[2 * i + 1] - f2.y) * kLoScale);
             }
         }
+        if (MODE == 1 || MODE == 3) __syncwarp();   // all lanes are done reading the bias block before it becomes the store staging
         if (MODE != 0 && rowsValid > 0 && !(g.dbg & 5)) {
             const size_t co = (size_t)mw * g.ldc + (size_t)z * g.cBatchCols + n;
             staged_store_half(stg, ph, g.Chi + co, g.ldc, rowsValid, lane);
@@ -475,10 +482,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
         if (MODE == 2 && !(g.dbg & 2) && (int)blockIdx.x < numTiles) prefetch_act(blockIdx.x);
+        float biasNext = 0.0f, w3Next = 0.0f;
+        auto prefetch_cols = [&](int t) {
+            int mt, nt, z;
+            decode(t, mt, nt, z);
+            const int col = nt * TBN + hsel * 32 + lane;
+            if (col < g.N) {
+                biasNext = __ldg(g.bias + (size_t)z * g.biasBatch + col);
+                if (MODE == 3) w3Next = __ldg(g.w3 + (size_t)z * g.biasBatch + col);
+            }
+        };
+        if ((MODE == 1 || MODE == 3) && (int)blockIdx.x < numTiles) prefetch_cols(blockIdx.x);
         for (int t = blockIdx.x; t < numTiles; t += gridDim.x) {
             int mt, nt, z;
             decode(t, mt, nt, z);
             float esum = 0.0f;
+            const float biasCur = biasNext, w3Cur = w3Next;
+            if ((MODE == 1 || MODE == 3) && t + (int)gridDim.x < numTiles) prefetch_cols(t + gridDim.x);
             uint32_t actH[16], actL[16];
             if (MODE == 2 && !(g.dbg & 2)) {
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -493,7 +513,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
                 __syncwarp();
                 if (t + (int)gridDim.x < numTiles) prefetch_act(t + gridDim.x);
             }
-            epilogue_tile<MODE>(g, tmemBase, acc, q, hsel, lane, mt, nt, z, stg, esum, actH, actL, [&]() {
+            epilogue_tile<MODE>(g, tmemBase, acc, q, hsel, lane, mt, nt, z, stg, esum, actH, actL, biasCur, w3Cur, [&]() {
                 mbar_wait(accFullBar(acc), accPhase);
                 tc_fence_after();
             });
