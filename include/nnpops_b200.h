@@ -33,7 +33,7 @@ NNPOPS_API int nnpops_abi_version(void);
  * which the torch Holder drives from src/pytorch/SymmetryFunctions.cpp:124-133,155,172.
  * radial_fn  : n_radial  x {eta, rs}                (struct RadialFunction,  ANISymmetryFunctions.h:29-32)
  * angular_fn : n_angular x {eta, rs, zeta, thetas}  (struct AngularFunction, ANISymmetryFunctions.h:34-39)
- * max_*_neighbors: capacity of the per-atom neighbour rows (0 = defaults 256 / 96); nnpops_ani_overflowed reports a
+ * max_*_neighbors: capacity of the per-atom neighbour rows (0 = defaults 256 / 64); nnpops_ani_overflowed reports a
  * system denser than that (the reference has no such limit because it stores an N x N table).
  * ------------------------------------------------------------------------------------------------------------------ */
 typedef struct nnpops_ani* nnpops_ani_t;

@@ -1073,7 +1073,7 @@ AniAev::AniAev(int numAtoms, int numSpecies, float rcr, float rca, const int* at
     for (int i = 0; i < numAtoms; i++)
         NNP_REQUIRE(atomSpecies[i] >= 0 && atomSpecies[i] < numSpecies, "atomSpecies entries must be in [0, numSpecies)");
     capR_ = maxRadialNeighbors > 0 ? maxRadialNeighbors : 256;
-    capA_ = maxAngularNeighbors > 0 ? maxAngularNeighbors : 96;
+    capA_ = maxAngularNeighbors > 0 ? maxAngularNeighbors : 64;   // 3.5 A at liquid density: 17 on average, 24 at most; shared-memory rows scale with it
     capR_ = (capR_ + 31) / 32 * 32;
     capA_ = (capA_ + 31) / 32 * 32;
     AniTables& t = tabHost_;
