@@ -203,9 +203,9 @@ def run_ours(args):
     mlp_peak = pk["bf16_tflops_sustained"]
     # the radial kernels run on an auxiliary stream concurrently with the angular ones: each pair is timed as one region on the
     # launching stream and rated against the sum of its algorithmic flops
-    kern("ani_angular_fwd_kernel || ani_radial_fwd_kernel", stages["radial_fwd"] + stages["angular_fwd"], 1,
+    kern("ani_angular_fwd_grouped_kernel || ani_radial_fwd_kernel", stages["radial_fwd"] + stages["angular_fwd"], 1,
          tri * 146.0 + prs * 134.0, "fp32", FP32_PEAK_TFLOPS, "TFLOP/s")
-    kern("ani_angular_bwd_kernel || ani_radial_bwd_kernel", stages["radial_bwd"] + stages["angular_bwd"], 1,
+    kern("ani_angular_bwd_fast_kernel || ani_radial_bwd_scatter_kernel", stages["radial_bwd"] + stages["angular_bwd"], 1,
          tri * 370.0 + prs * 212.0, "fp32", FP32_PEAK_TFLOPS, "TFLOP/s")
     kern("cell_list+ani_rows_kernel", stages["cells+rows"], n, 64.0 + 4.0 * 2 * prs / max(n, 1), "hbm", pk["hbm_gbs"], "GB/s")
     mlp_ach = mlp_flops / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
