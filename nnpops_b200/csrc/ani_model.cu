@@ -154,10 +154,6 @@ void AniModel::energyAndGradient(const float* positions, const float* box, float
     aev_->forward(positions, box, feat_, stride_, feat_ + rw, stride_, stream, ev ? ev + 1 : nullptr,   // ev[1], ev[2]
                   tc ? mlp_->featHi() : nullptr, tc ? mlp_->featLo() : nullptr);
     if (ev) cudaEventRecord(ev[3], stream);
-    if (tc) {
-        static const int slab = std::getenv("NNPOPS_MLP_SLAB") ? std::atoi(std::getenv("NNPOPS_MLP_SLAB")) : 0;
-        mlp_->setSlab(slab, featGrad_);
-    }
     mlp_->forward(tc ? nullptr : feat_, energy, stream);
     if (ev) cudaEventRecord(ev[4], stream);
     mlp_->backward(featGrad_, stream);

@@ -26,6 +26,14 @@ namespace nnpops {
 
 namespace {
 
+// Development switches (scripts/gemm_dbg.py): parts of the kernel can be turned off through NNPOPS_GEMM_DBG when the library is built with
+// -DNNPOPS_GEMM_DEBUG (NNPOPS_BUILD_DEFINES=-DNNPOPS_GEMM_DEBUG python -m nnpops_b200.build --force); compiled out otherwise.
+#ifdef NNPOPS_GEMM_DEBUG
+#define GEMM_DBG(bit) ((g.dbg & (bit)) != 0)
+#else
+#define GEMM_DBG(bit) false
+#endif
+
 constexpr int TBM = 128, TBN = 128, TBK = 64, kAccStages = 2;
 // Operand ring depth: 3 stages; the celu'-mask epilogue (mode 2) gives one stage up for per-warp activation prefetch buffers.
 __host__ __device__ constexpr int stages_of(int mode) { return mode == 2 ? 2 : 3; }
@@ -251,7 +259,7 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& g, uint32_t tmemBase
             tmem_ld16(tbase + c * 32 + 16 * h, r1);
             tmem_ld16(tbase + TBN + c * 32 + 16 * h, r2);
             tmem_ld_wait();
-            if (rowsValid <= 0 || (g.dbg & 4)) continue;
+            if (rowsValid <= 0 || GEMM_DBG(4)) continue;
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; j++) v[j] = fmaf(__uint_as_float(r2[j]), kLoInv, __uint_as_float(r1[j]));
@@ -300,7 +308,7 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& g, uint32_t tmemBase
             }
         }
         if (MODE == 1 || MODE == 3) __syncwarp();   // all lanes are done reading the bias block before it becomes the store staging
-        if (MODE != 0 && rowsValid > 0 && !(g.dbg & 5)) {
+        if (MODE != 0 && rowsValid > 0 && !GEMM_DBG(5)) {
             const size_t co = (size_t)mw * g.ldc + (size_t)z * g.cBatchCols + n;
             staged_store_half(stg, ph, g.Chi + co, g.ldc, rowsValid, lane);
             staged_store_half(stg, pl, g.Clo + co, g.ldc, rowsValid, lane);
@@ -401,9 +409,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
                 mbar_wait(emptyBar(stage), phase ^ 1u);
                 if (leader) {
                     const uint32_t sb = base + stage * kStageBytes;
-                    mbar_expect_tx(fullBar(stage), (g.dbg & 8) ? kStageBytes - 2 * kTileBytes : kStageBytes);
+                    mbar_expect_tx(fullBar(stage), GEMM_DBG(8) ? kStageBytes - 2 * kTileBytes : kStageBytes);
                     const int xa = z * g.aBatchCols + kc * TBK;
-                    if (!(g.dbg & 8)) {
+                    if (!GEMM_DBG(8)) {
                     tma_load_2d(sb, &mapAhi, fullBar(stage), xa, m0);
                     tma_load_2d(sb + kTileBytes, &mapAlo, fullBar(stage), xa, m0);
                     }
@@ -432,7 +440,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
                 tc_fence_after();
                 if (leader) {
                     const uint32_t sb = base + stage * kStageBytes;
-                    if (g.dbg & 16) {}
+                    if (GEMM_DBG(16)) {}
                     else if (kc == kChunks - 1 && lastSteps != TBK / 16) {
                         if (nTile == TBN) {
                             if (lastSteps == 2) issue_chunk<true, 2>(d1, descBits, sb, idescTile, kc == 0);
@@ -481,7 +489,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        if (MODE == 2 && !(g.dbg & 2) && (int)blockIdx.x < numTiles) prefetch_act(blockIdx.x);
+        if (MODE == 2 && !GEMM_DBG(2) && (int)blockIdx.x < numTiles) prefetch_act(blockIdx.x);
         float biasNext = 0.0f, w3Next = 0.0f;
         auto prefetch_cols = [&](int t) {
             int mt, nt, z;
@@ -500,7 +508,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
             const float biasCur = biasNext, w3Cur = w3Next;
             if ((MODE == 1 || MODE == 3) && t + (int)gridDim.x < numTiles) prefetch_cols(t + gridDim.x);
             uint32_t actH[16], actL[16];
-            if (MODE == 2 && !(g.dbg & 2)) {
+            if (MODE == 2 && !GEMM_DBG(2)) {
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
                 __syncwarp();
 #pragma unroll

@@ -313,36 +313,6 @@ void SpeciesMlp::forwardTc(const float* features, float* energy, cudaStream_t st
         split_rows_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, stream>>>(features, n8, featHi_, featLo_);
         count_launch();
     }
-    if (slabRows_ > 0 && graphExec_ && !capturing_) {
-        NNP_CUDA_CHECK(cudaGraphLaunch(graphExec_, stream));
-        return;
-    }
-    if (slabRows_ > 0 && !capturing_ && std::getenv("NNPOPS_MLP_GRAPH") && ++eagerCalls_ > 1) {
-        capturing_ = true;
-        cudaGraph_t graph;
-        cudaStream_t cap;
-        NNP_CUDA_CHECK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
-        NNP_CUDA_CHECK(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
-        forwardTc(features, energy, cap);
-        NNP_CUDA_CHECK(cudaStreamEndCapture(cap, &graph));
-        cudaStreamDestroy(cap);
-        NNP_CUDA_CHECK(cudaGraphInstantiate(&graphExec_, graph, 0));
-        cudaGraphDestroy(graph);
-        capturing_ = false;
-        NNP_CUDA_CHECK(cudaGraphLaunch(graphExec_, stream));
-        return;
-    }
-    if (slabRows_ > 0) {
-        // L2 blocking: the whole forward + backward chain runs slab by slab on scratch buffers that every slab reuses, so the
-        // activations and gradients between the layers live in the 126 MB L2 instead of making a round trip through HBM
-        for (int s = 0; s < S_; s++)
-            for (int r0 = rowStart_[s]; r0 < rowStart_[s + 1]; r0 += slabRows_) {
-                const int nr = std::min(slabRows_, rowStart_[s + 1] - r0);
-                forwardRowsTc(s, r0, nr, 0, stream);
-                backwardRowsTc(s, r0, nr, 0, slabGrad_, stream);
-            }
-        return;
-    }
     for (int s = 0; s < S_; s++) {
         const int r0 = rowStart_[s], nr = rowStart_[s + 1] - r0;
         if (nr > 0) forwardRowsTc(s, r0, nr, r0, stream);
@@ -375,7 +345,6 @@ void SpeciesMlp::forwardRowsTc(int s, int r0, int nr, int w0, cudaStream_t strea
 }
 
 void SpeciesMlp::backwardTc(float* featureGrad, cudaStream_t stream) {
-    if (slabRows_ > 0) return;   // already done slab by slab inside forwardTc (slabGrad_)
     for (int s = 0; s < S_; s++) {
         const int r0 = rowStart_[s], nr = rowStart_[s + 1] - r0;
         if (nr > 0) backwardRowsTc(s, r0, nr, r0, featureGrad, stream);

@@ -42,9 +42,6 @@ public:
     __half* featHi() { return featHi_; }
     __half* featLo() { return featLo_; }
     bool tensorCore() const { return impl_ == MlpImpl::Tcgen05; }
-    // L2 blocking (tensor-core path): forward() then runs forward AND backward slab by slab, writing dE/dfeatures to featureGrad;
-    // the following backward(featureGrad) call is a no-op
-    void setSlab(int rows, float* featureGrad) { slabRows_ = rows; slabGrad_ = featureGrad; }
     int numRows() const { return rows_; }
     double flopsForward() const { return flopsFwd_; }   // algorithmic (un-padded) flops of one forward pass
 
@@ -70,11 +67,6 @@ private:
     void backwardTc(float* featureGrad, cudaStream_t stream);
     void forwardRowsTc(int s, int r0, int nr, int w0, cudaStream_t stream);
     void backwardRowsTc(int s, int r0, int nr, int w0, float* featureGrad, cudaStream_t stream);
-    cudaGraphExec_t graphExec_ = nullptr;
-    bool capturing_ = false;
-    int eagerCalls_ = 0;
-    int slabRows_ = 0;            // > 0: forward and backward run slab by slab (L2 blocking); needs setSlabGradTarget
-    float* slabGrad_ = nullptr;   // where the slab-wise backward writes dE/dfeatures
     double* energyAcc_ = nullptr;
     double energyBias_ = 0;      // sum over atoms and members of the last-layer bias
     MlpImpl impl_ = MlpImpl::Simt;

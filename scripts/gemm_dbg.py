@@ -1,5 +1,6 @@
 """Development aid: decompose the time of one tcgen05 GEMM shape by switching parts of the kernel off (NNPOPS_GEMM_DBG bits:
-1 no epilogue stores, 2 no activation loads, 4 no epilogue math, 8 no A loads, 16 no MMA issue)."""
+1 no epilogue stores, 2 no activation loads, 4 no epilogue math, 8 no A loads, 16 no MMA issue).  The switches exist only in a library built
+with NNPOPS_BUILD_DEFINES=-DNNPOPS_GEMM_DEBUG python -m nnpops_b200.build --force."""
 import ctypes as C, os, sys, subprocess
 if len(sys.argv) > 1:
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
