@@ -361,6 +361,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
     const uint32_t tmemSlot = barBase + 8u * (2 * kStages + 2 * kAccStages);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    // Programmatic dependent launch: the next GEMM of the chain may start its CTAs (barrier init, TMEM allocation, descriptor
+    // prefetch) on SMs this grid has already left; it blocks in griddepcontrol.wait below until this grid has completed.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAhi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAlo) : "memory");
@@ -377,6 +381,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmemSlot), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // everything this kernel reads from global memory was written before this point
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -619,11 +624,19 @@ void launch_gemm_tcgen05(const GemmArgsH& a, cudaStream_t stream) {
     { const char* e = std::getenv("NNPOPS_GEMM_DBG"); g.dbg = e ? std::atoi(e) : 0; }
     const int tiles = ((a.M + TBM - 1) / TBM) * ((a.N + TBN - 1) / TBN) * a.batch;
     const int grid = tiles < num_sms() ? tiles : num_sms();
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool noPdl = std::getenv("NNPOPS_NO_PDL") != nullptr;
+    cfg.attrs = attr; cfg.numAttrs = noPdl ? 0 : 1;
     switch (g.mode) {
-        case 0: gemm_tcgen05_kernel<0><<<grid, kThreads, smem_bytes_of(0), stream>>>(mAhi, mAlo, mBhi, mBlo, g); break;
-        case 1: gemm_tcgen05_kernel<1><<<grid, kThreads, smem_bytes_of(1), stream>>>(mAhi, mAlo, mBhi, mBlo, g); break;
-        case 2: gemm_tcgen05_kernel<2><<<grid, kThreads, smem_bytes_of(2), stream>>>(mAhi, mAlo, mBhi, mBlo, g); break;
-        case 3: gemm_tcgen05_kernel<3><<<grid, kThreads, smem_bytes_of(3), stream>>>(mAhi, mAlo, mBhi, mBlo, g); break;
+        case 0: cfg.dynamicSmemBytes = smem_bytes_of(0); NNP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<0>, mAhi, mAlo, mBhi, mBlo, g)); break;
+        case 1: cfg.dynamicSmemBytes = smem_bytes_of(1); NNP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<1>, mAhi, mAlo, mBhi, mBlo, g)); break;
+        case 2: cfg.dynamicSmemBytes = smem_bytes_of(2); NNP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2>, mAhi, mAlo, mBhi, mBlo, g)); break;
+        case 3: cfg.dynamicSmemBytes = smem_bytes_of(3); NNP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<3>, mAhi, mAlo, mBhi, mBlo, g)); break;
         default: NNP_REQUIRE(false, "tcgen05 GEMM: unknown epilogue mode");
     }
     count_launch();
