@@ -221,10 +221,10 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 
 // warp (q = TMEM lane quarter, hsel = column block) handles rows q*32 + lane and columns [hsel*32, hsel*32 + 32) of the tile.  Four
 // epilogue warps per scheduler: the latencies of one warp's chain (bias / activation loads, TMEM load, staging) hide behind the others
-template <int MODE, typename WAIT>
+template <int MODE, typename WAIT, typename ACTDONE>
 __device__ __forceinline__ void epilogue_tile(const TcArgs& g, uint32_t tmemBase, int acc, int q, int hsel, int lane, int mt, int nt, int z,
-                                              unsigned char* stg, float& esum, const uint32_t (&actH)[16], const uint32_t (&actL)[16],
-                                              float biasLane, float w3Lane, WAIT&& waitAccumulator) {
+                                              unsigned char* stg, float& esum, const unsigned char* actBuf, float biasLane, float w3Lane,
+                                              WAIT&& waitAccumulator, ACTDONE&& actConsumed) {
     const int mw = mt * TBM + q * 32;              // first row of this warp
     const int m = mw + lane, n0 = nt * TBN;
     const int rowsValid = min(32, g.M - mw);       // warp-uniform, may be <= 0
@@ -292,9 +292,20 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& g, uint32_t tmemBase
                     }
                 }
             } else {
+                // the activation block of this tile sits in the warp's cp.async buffers: read this half's 16 columns of the lane's row
+                // (hi and lo), and hand the buffers back for the next tile's prefetch once the second half has been read
+                uint32_t actH[8], actL[8];
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const uint4 th = *reinterpret_cast<const uint4*>(actBuf + stage_off(lane, 2 * h + i));
+                    const uint4 tl = *reinterpret_cast<const uint4*>(actBuf + kStageWarpBytes + stage_off(lane, 2 * h + i));
+                    actH[4 * i] = th.x; actH[4 * i + 1] = th.y; actH[4 * i + 2] = th.z; actH[4 * i + 3] = th.w;
+                    actL[4 * i] = tl.x; actL[4 * i + 1] = tl.y; actL[4 * i + 2] = tl.z; actL[4 * i + 3] = tl.w;
+                }
+                if (h == 1) actConsumed();
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    const float2 fh = unpack_h2(actH[8 * h + i]), fl = unpack_h2(actL[8 * h + i]);
+                    const float2 fh = unpack_h2(actH[i]), fl = unpack_h2(actL[i]);
                     v[2 * i] *= celu_grad_from_act_f(fmaf(fl.x, kLoInv, fh.x));
                     v[2 * i + 1] *= celu_grad_from_act_f(fmaf(fl.y, kLoInv, fh.y));
                 }
@@ -512,24 +523,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
             float esum = 0.0f;
             const float biasCur = biasNext, w3Cur = w3Next;
             if ((MODE == 1 || MODE == 3) && t + (int)gridDim.x < numTiles) prefetch_cols(t + gridDim.x);
-            uint32_t actH[16], actL[16];
             if (MODE == 2 && !GEMM_DBG(2)) {
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
                 __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const uint4 th = *reinterpret_cast<const uint4*>(actBuf + stage_off(lane, i));
-                    const uint4 tl = *reinterpret_cast<const uint4*>(actBuf + kStageWarpBytes + stage_off(lane, i));
-                    actH[4 * i] = th.x; actH[4 * i + 1] = th.y; actH[4 * i + 2] = th.z; actH[4 * i + 3] = th.w;
-                    actL[4 * i] = tl.x; actL[4 * i + 1] = tl.y; actL[4 * i + 2] = tl.z; actL[4 * i + 3] = tl.w;
-                }
-                __syncwarp();
-                if (t + (int)gridDim.x < numTiles) prefetch_act(t + gridDim.x);
             }
-            epilogue_tile<MODE>(g, tmemBase, acc, q, hsel, lane, mt, nt, z, stg, esum, actH, actL, biasCur, w3Cur, [&]() {
+            bool actHanded = false;
+            auto actConsumed = [&]() {
+                __syncwarp();
+                if (MODE == 2 && !GEMM_DBG(2) && t + (int)gridDim.x < numTiles) prefetch_act(t + gridDim.x);
+                actHanded = true;
+            };
+            epilogue_tile<MODE>(g, tmemBase, acc, q, hsel, lane, mt, nt, z, stg, esum, actBuf, biasCur, w3Cur, [&]() {
                 mbar_wait(accFullBar(acc), accPhase);
                 tc_fence_after();
-            });
+            }, actConsumed);
+            if (MODE == 2 && !actHanded) actConsumed();   // tiles this warp skipped (no rows / columns): keep the prefetch chain going
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(accEmptyBar(acc));
