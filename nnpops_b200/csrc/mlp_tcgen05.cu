@@ -138,11 +138,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// celu(x) = max(x, 0) + min(0, alpha (exp(x / alpha) - 1)), branch-free: one ex2 per element whatever the sign
+// celu(x) = x for x > 0, alpha (exp(x / alpha) - 1) otherwise: one ex2 per element whatever the sign, then a select (for large
+// positive x the exponential overflows to +inf, which the select discards)
 __device__ __forceinline__ float celu_f(float x) {
     float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(x, 0.0f) * (1.4426950408889634f / kCeluAlpha)));
-    return fmaxf(x, 0.0f) + fmaf(kCeluAlpha, e, -kCeluAlpha);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * (1.4426950408889634f / kCeluAlpha)));
+    const float neg = fmaf(kCeluAlpha, e, -kCeluAlpha);
+    return x > 0.0f ? x : neg;
 }
 __device__ __forceinline__ float celu_grad_from_act_f(float a) { return a > 0.0f ? 1.0f : a * (1.0f / kCeluAlpha) + 1.0f; }
 
