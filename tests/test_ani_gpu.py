@@ -213,6 +213,26 @@ def test_fused_energy_forces(name, impl):
     assert errs["aev"] < TOL and errs["dA"] < TOL and errs["forces"] < TOL and errs["energy"] < TOL
 
 
+@pytest.mark.parametrize("n", [1, 2, 7, 33])
+def test_fused_tiny_systems(n):
+    """Ragged sizes around the kernels' group / warp granularities (4 centres per warp in the angular forward, 128-row GEMM tiles),
+    including an atom without neighbours: energy and forces vs the fp64 oracle chain, with a species set that leaves most AEV
+    columns inactive."""
+    rng = np.random.default_rng(100 + n)
+    pos = (rng.uniform(0.0, 1.0, (n, 3)) * (1.2 * max(n, 2) ** (1 / 3)) + np.arange(n)[:, None] * 0.37).astype(np.float32)
+    species = rng.choice([0, 3, 6], n).astype(np.int32)
+    m, nets = fused(pos, species, None, 5.1, "tcgen05")
+    e, g = m.energy_and_gradient(dev(pos), None)
+    e = float(e.cpu()[0]); g = g.cpu().numpy()
+    assert m.overflowed() == 0
+    rfn, afn = ani2x_tables()
+    r0, a0 = O.ani_forward(pos, species, 7, 5.1, 3.5, rfn, afn, box=None, bits=64)
+    e0, dA = mlp_energy_and_grad(np.concatenate([r0, a0], axis=1), species, nets, torch.float64)
+    g0 = O.ani_backward(pos, species, 7, 5.1, 3.5, rfn, afn, dA[:, :112], dA[:, 112:], box=None, bits=64)
+    assert abs(e - e0) <= 1e-5 * max(abs(e0), 1e-3)
+    assert np.abs(g - g0).max() <= 1e-5 * max(np.abs(g0).max(), 1e-3)
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_box_partials_sum_to_the_whole(world):
     """One box sharded over `world` ranks (variant ii), emulated on one GPU: the partial energies and gradients of the
