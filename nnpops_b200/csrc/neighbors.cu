@@ -122,14 +122,17 @@ pairs_kernel(int n, const T* __restrict__ pos, const T* __restrict__ boxPtr, con
         cursor += __popc(m);
         mine += __popc(m);
     };
-    for_each_candidate_run(g, cellStart, sortedCell[p], [&](int b, int e) {
+    // runs that do not cross a periodic face need no minimum-image step in the pre-test (it would subtract zero; cell_list.cuh)
+    const bool alwaysImage = g.periodic && (g.triclinic || g.anyOutside);
+    for_each_candidate_run_w(g, cellStart, sortedCell[p], [&](int b, int e, bool wrapped) {
+        const bool image = alwaysImage || wrapped;
         for (int q0 = max(b, p + 1); q0 < e; q0 += 32) {
             const int q = q0 + lane;
             bool keep = false;
             if (q < e) {
                 const float4 cq = sorted[q];
                 float ax = cq.x - cp.x, ay = cq.y - cp.y, az = cq.z - cp.z;
-                keep = min_image_mul(g, ax, ay, az) <= pre2;
+                keep = (image ? min_image_mul(g, ax, ay, az) : ax * ax + ay * ay + az * az) <= pre2;
             }
             const unsigned m = __ballot_sync(kFull, keep);
             if (keep) queue[queued + __popc(m & ((1u << lane) - 1u))] = q;
