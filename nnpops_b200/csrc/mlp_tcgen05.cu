@@ -239,7 +239,7 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& g, uint32_t tmemBase
             // bias (and last-layer weights) of the warp's 32 columns were fetched one tile ahead, one column per lane; they pass
             // through the (idle) staging block so that every lane can read them as broadcast float4
             reinterpret_cast<float*>(stg)[lane] = biasLane;
-            if (MODE == 3) reinterpret_cast<float*>(stg)[32 + lane] = w3Lane;
+            if (MODE == 3) { reinterpret_cast<float*>(stg)[32 + lane] = w3Lane; reinterpret_cast<float*>(stg)[64 + lane] = w3Lane * g.seedScale; }
             __syncwarp();
         }
         waitAccumulator(); waited = true;
@@ -247,14 +247,14 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& g, uint32_t tmemBase
         const bool rowOk = m < g.M;
 #pragma unroll
         for (int h = 0; h < 2; h++) {               // two 16-column halves keep the register footprint small
-            float4 bv[4], wv[4];
+            float4 bv[4], wv[4], sv[4];
             if (MODE == 1 || MODE == 3) {
                 const float4* bp = reinterpret_cast<const float4*>(stg) + 4 * h;
 #pragma unroll
                 for (int j = 0; j < 4; j++) bv[j] = bp[j];
                 if (MODE == 3) {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) wv[j] = bp[8 + j];
+                    for (int j = 0; j < 4; j++) { wv[j] = bp[8 + j]; sv[j] = bp[16 + j]; }
                 }
             }
             uint32_t r1[16], r2[16];
@@ -275,24 +275,32 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& g, uint32_t tmemBase
                 }
                 continue;
             }
-            if (MODE == 1 || MODE == 3) {
+            if (MODE == 1) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     v[4 * j] = celu_f(v[4 * j] + bv[j].x); v[4 * j + 1] = celu_f(v[4 * j + 1] + bv[j].y);
                     v[4 * j + 2] = celu_f(v[4 * j + 2] + bv[j].z); v[4 * j + 3] = celu_f(v[4 * j + 3] + bv[j].w);
                 }
-                if (MODE == 3) {
+            } else if (MODE == 3) {
+                // last hidden layer: a = celu(z + b) feeds the energy (a . w3) and the backward seed w3 / M * celu'(z); celu' is the
+                // exponential celu already computed (x <= 0) or 1, and w3 arrives pre-multiplied by the seed scale in a second copy
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const float w4[4] = {wv[j].x, wv[j].y, wv[j].z, wv[j].w};
+                for (int j = 0; j < 4; j++) {
+                    const float b4[4] = {bv[j].x, bv[j].y, bv[j].z, bv[j].w};
+                    const float w4[4] = {wv[j].x, wv[j].y, wv[j].z, wv[j].w};
+                    const float s4[4] = {sv[j].x, sv[j].y, sv[j].z, sv[j].w};
 #pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            const float a = v[4 * j + i];
-                            if (rowOk) esum = fmaf(a, w4[i], esum);
-                            v[4 * j + i] = g.seedScale * w4[i] * celu_grad_from_act_f(a);
-                        }
+                    for (int i = 0; i < 4; i++) {
+                        const float x = v[4 * j + i] + b4[i];
+                        float e;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * (1.4426950408889634f / kCeluAlpha)));
+                        const bool pos = x > 0.0f;
+                        const float a = pos ? x : fmaf(kCeluAlpha, e, -kCeluAlpha);
+                        esum = fmaf(a, w4[i], esum);
+                        v[4 * j + i] = s4[i] * (pos ? 1.0f : e);
                     }
                 }
+                if (!rowOk) esum = 0.0f;          // rows beyond M carry zero activations but a non-zero bias: keep them out of the energy
             } else {
                 // the activation block of this tile sits in the warp's cp.async buffers: read this half's 16 columns of the lane's row
                 // (hi and lo), and hand the buffers back for the next tile's prefetch once the second half has been read
