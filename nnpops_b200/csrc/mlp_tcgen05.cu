@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <tuple>
 #include "species_mlp.cuh"
 
@@ -585,9 +586,17 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2-D fp16 tensor [rows][cols] with row pitch ld (elements); box = 64 columns x 128 rows, 128-byte swizzle, OOB reads give zeros
+// 2-D fp16 tensor [rows][cols] with row pitch ld (elements); box = 64 columns x 128 rows, 128-byte swizzle, OOB reads give zeros.
+// The encodes are cached: a model launches the same dozen GEMMs on the same buffers every evaluation, and 48 driver calls per
+// evaluation are a visible share of the host time of small systems and of the sharded-box mode.
 CUtensorMap make_map(const __half* ptr, long long rows, long long cols, long long ld) {
     NNP_REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld * 2) % 16 == 0, "tcgen05 GEMM operands must be 16-byte aligned");
+    static std::mutex mu;
+    static std::map<std::tuple<const void*, long long, long long, long long>, CUtensorMap> cache;
+    const auto key = std::make_tuple((const void*)ptr, rows, cols, ld);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
     CUtensorMap m;
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
@@ -597,6 +606,8 @@ CUtensorMap make_map(const __half* ptr, long long rows, long long cols, long lon
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     NNP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
+    if (cache.size() > 4096) cache.clear();   // long-lived processes creating many models: bound the table
+    cache.emplace(key, m);
     return m;
 }
 
