@@ -85,6 +85,28 @@ class ClockSampler:
                 "samples": len(self.sm)}
 
 
+class StdoutToStderr:
+    """NCCL prints its version banner (and any NCCL_DEBUG output) on the process's stdout; the contract is ONE JSON line there.
+    File descriptor 1 is pointed at stderr for the duration of the run and restored just before the result is printed."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def restore(self):
+        if self.saved is not None:
+            sys.stdout.flush()
+            os.dup2(self.saved, 1)
+            os.close(self.saved)
+            self.saved = None
+
+    def __exit__(self, *exc):
+        self.restore()
+        return False
+
+
 def shard_conformers(total, rank, world):
     """Conformer ids evaluated by `rank`: BASELINE config 3 deals conformer c to rank c mod world (independent conformers, no
     collective on the data path)."""
@@ -250,8 +272,10 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(n, budget_s=20.0)
+    args.quiet.restore()
     print(json.dumps(out), flush=True)
     if dist is not None:
+        os.dup2(2, 1)   # the teardown may log again
         dist.destroy_process_group()
 
 
@@ -300,6 +324,7 @@ def run_box(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_total = max_over_ranks(t0.elapsed_time(t1), dist, dev)
     if rank == 0:
+        args.quiet.restore()
         print(json.dumps({
             "metric": METRIC, "value": round(args.steps / (ms_total / 1e3), 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "strong",
@@ -309,6 +334,7 @@ def run_box(args):
                        "atoms": n, "mode": "box", "mlp_impl": args.mlp, "allreduce_bytes_per_step": 12 * n + 4},
             "energy": float(e.cpu()[0]), "clocks": clocks}), flush=True)
     if dist is not None:
+        os.dup2(2, 1)
         dist.destroy_process_group()
 
 
@@ -423,10 +449,13 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
-    elif args.mode == "box":
-        run_box(args)
-    else:
-        run_ours(args)
+        return
+    with StdoutToStderr() as quiet:
+        args.quiet = quiet
+        if args.mode == "box":
+            run_box(args)
+        else:
+            run_ours(args)
 
 
 if __name__ == "__main__":
