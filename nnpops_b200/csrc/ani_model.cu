@@ -154,9 +154,14 @@ void AniModel::energyAndGradient(const float* positions, const float* box, float
     aev_->forward(positions, box, feat_, stride_, feat_ + rw, stride_, stream, ev ? ev + 1 : nullptr,   // ev[1], ev[2]
                   tc ? mlp_->featHi() : nullptr, tc ? mlp_->featLo() : nullptr);
     if (ev) cudaEventRecord(ev[3], stream);
-    mlp_->forward(tc ? nullptr : feat_, energy, stream);
-    if (ev) cudaEventRecord(ev[4], stream);
-    mlp_->backward(featGrad_, stream);
+    if (mlp_->fused()) {   // forward + backward of the network in one kernel: the whole MLP time is booked on stage 3
+        mlp_->forwardBackward(energy, featGrad_, stream);
+        if (ev) cudaEventRecord(ev[4], stream);
+    } else {
+        mlp_->forward(tc ? nullptr : feat_, energy, stream);
+        if (ev) cudaEventRecord(ev[4], stream);
+        mlp_->backward(featGrad_, stream);
+    }
     if (ev) cudaEventRecord(ev[5], stream);
     aev_->backward(featGrad_, stride_, featGrad_ + rw, stride_, positionGrad, stream, ev ? ev + 6 : nullptr);   // ev[6]
     if (ev) cudaEventRecord(ev[7], stream);

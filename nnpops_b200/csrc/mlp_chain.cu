@@ -1,0 +1,538 @@
+// Fused per-tile layer chain of the species MLP on tcgen05 (see mlp_chain.cuh).
+//
+// One persistent CTA per SM walks over tiles of 128 atoms of one species and, per tile, over the M ensemble members; for each
+// (tile, member) it runs the six GEMMs of the network back to back ("chain"):
+//     F1  A1  = celu(X   W0^T + b0)        N = d1, K = d0     A operand: X    (shared memory, TMA, loaded once per tile)
+//     F2  A2  = celu(A1  W1^T + b1)        N = d2, K = d1     A operand: A1   (tensor memory)
+//     F3  a3  = celu(A2  W2^T + b2)        N = d3, K = d2     A operand: A2   (shared memory); E += a3 . w3; dZ2 = w3/M celu'
+//     G3  dZ1 = (dZ2 W2) * celu'(A2)       N = d2, K = d3     A operand: dZ2  (tensor memory); overwrites A2 in place
+//     G2  dZ0 = (dZ1 W1) * celu'(A1)       N = d1, K = d2     A operand: dZ1  (shared memory)
+//     G1  dX += dZ0 W0                     N = d0, K = d1     A operand: dZ0  (tensor memory); st / red.add to global
+// Every operand is an fp16 hi/lo pair (mlp_tcgen05.cu: x = hi + 2^-11 lo, three MMAs per product, fp32 accumulation), so the
+// result carries ~22 mantissa bits.  Activations alternate between tensor memory and shared memory because neither holds two
+// consecutive ones: TMEM = 2 accumulator stages x 128 columns + 256 columns of packed fp16 A operand (K <= 256); shared memory
+// = X (<= 64 KB) + one activation buffer (<= 96 KB) + a ring of 16 KB weight blocks.  The only activation that does not fit, A1
+// (needed again for celu' in G2), goes through a per-CTA fp32 scratch that stays in L2 (128 KB per CTA, rewritten every chain).
+//
+// Work split inside the CTA (576 threads):
+//   warp 0        TMA producer: X once per tile, then one 16 KB weight block [64 hi rows + 64 lo rows][64 k] per (n-chunk, k-chunk)
+//   warp 1        TMEM allocator + MMA issuer (one elected lane): per k16 step  [D1 | D2] (+)= Ahi . [Bhi; Blo]  (N = 128) and
+//                 D2 += Alo . Bhi (N = 64); tcgen05.commit frees ring slots and publishes accumulator stages
+//   warps 2-9     epilogue group 0 (accumulator stage 0),  warps 10-17 epilogue group 1 (stage 1): 64-column chunks alternate
+//                 between the groups, so the epilogue of chunk c overlaps the MMAs of chunk c + 1.  A thread owns one row (TMEM
+//                 lane) and 32 columns; it writes the next layer's A operand straight into tensor memory (tcgen05.st) or into
+//                 the swizzled K-major shared-memory tiles, then arrives on the per-64-column "operand ready" barrier the MMA
+//                 warp waits on before it issues the first k-chunk that needs those columns.
+#include "mlp_chain.cuh"
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include "tcgen05_util.cuh"
+
+namespace nnpops {
+
+namespace {
+using namespace tc;
+
+constexpr int kMaxSp = 7;
+constexpr int kRows = 128;
+constexpr uint32_t kTile = 128 * 128;        // 16 KB: [128 rows][64 halves] A tile, or [64 hi + 64 lo rows][64 halves] B block
+constexpr int kMaxRing = 8;
+constexpr int kFirstEpiWarp = 2, kGroupWarps = 8;
+constexpr int kThreads = (kFirstEpiWarp + 2 * kGroupWarps) * 32;
+constexpr uint32_t kAccCols = 128;           // one accumulator stage: D1 (64 columns) | D2 (64 columns)
+constexpr uint32_t kOpaHi = 256, kOpaLo = 384;   // A operand in TMEM: packed fp16 pairs, hi part and lo part (128 columns each: K <= 256)
+constexpr int kStashCols = 256;
+constexpr uint32_t kMaxSmem = 232448;
+
+struct ChainSpecies {
+    int d0, d1, d2, d3;
+    int rows, rowStart, tileBegin, tileEnd;
+    const float* bias[3];
+    const float* w3;
+};
+
+struct ChainParams {
+    CUtensorMap maps[kMaxSp][8];   // 0..5: packed weights of F1 F2 F3 G3 G2 G1; 6, 7: X hi / lo of the species' rows
+    ChainSpecies sp[kMaxSp];
+    int numSpecies, numTiles, M;
+    int xChunks, sChunks, ring;    // 64-column chunks of X and of the shared-memory activation buffer; weight ring depth
+    float* dX;
+    int ldx;
+    float* stash;                  // [grid][256 columns][128 rows] fp32
+    double* energyAcc;
+    float seedScale, outScale;
+};
+
+__host__ __device__ constexpr int chunks_of(int n) { return (n + 63) >> 6; }
+
+__device__ __forceinline__ void layer_dims(const ChainSpecies& s, int j, int& N, int& K) {
+    switch (j) {
+        case 0: N = s.d1; K = s.d0; break;
+        case 1: N = s.d2; K = s.d1; break;
+        case 2: N = s.d3; K = s.d2; break;
+        case 3: N = s.d2; K = s.d3; break;
+        case 4: N = s.d1; K = s.d2; break;
+        default: N = s.d0; K = s.d1; break;
+    }
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// what an epilogue thread needs to know about its chunk
+struct EpiCtx {
+    uint32_t laneBase;      // TMEM address of the thread's lane, column 0
+    uint32_t accCol;        // first column of the accumulator stage (+ the warp's 32-column half)
+    uint32_t sbufRow;       // shared-memory address of the thread's row in chunk 0 of the activation buffer (hi part)
+    uint32_t sLoOff;        // byte offset of the lo tiles of that buffer
+    int r7;                 // row & 7 (swizzle phase)
+    int hsel, n0, c;
+    bool rowOk;
+};
+
+// TYPE: 0 F1, 1 F2, 2 F3, 3 G3, 4 G2, 5 G1.  Processes the thread's 32 columns [n0, n0 + 32) of chunk c as two halves of 16.
+template <int TYPE>
+__device__ __forceinline__ void epi_chunk(const ChainParams& P, const EpiCtx& x, const float* __restrict__ colA, const float* __restrict__ colB,
+                                          float* stash, float* dxRow, bool firstMember, uint32_t accFullBar, uint32_t fullPhase, uint32_t accEmptyBar, int lane,
+                                          float& esum) {
+    float st[TYPE == 4 ? 32 : 1];
+    if (TYPE == 4) {   // A1 of these columns, written by F1's epilogue of this chain: fetch before the accumulator is needed
+#pragma unroll
+        for (int i = 0; i < 32; i++) st[i] = __ldcg(stash + (size_t)(x.n0 + i) * kRows);
+    }
+    mbar_wait(accFullBar, fullPhase);
+    tc_fence_after();
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        uint32_t r1[16], r2[16];
+        tmem_ld16(x.laneBase + x.accCol + 16 * h, r1);
+        tmem_ld16(x.laneBase + x.accCol + 64 + 16 * h, r2);
+        tmem_ld_wait();
+        if (h == 1) {   // the accumulator stage has been read completely: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(accEmptyBar);
+        }
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = fmaf(__uint_as_float(r2[j]), kLoInv, __uint_as_float(r1[j]));
+        const int col = x.n0 + 16 * h;
+        if (TYPE == 5) {
+            if (x.rowOk) {
+                float* dst = dxRow + col;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float a = v[j] * P.outScale, b = v[j + 1] * P.outScale, c = v[j + 2] * P.outScale, d = v[j + 3] * P.outScale;
+                    if (firstMember) *reinterpret_cast<float4*>(dst + j) = make_float4(a, b, c, d);
+                    else red_add_v4(dst + j, a, b, c, d);
+                }
+            }
+            continue;
+        }
+        if (TYPE == 0 || TYPE == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(colA + col + j));
+                v[j] = celu_f(v[j] + b.x); v[j + 1] = celu_f(v[j + 1] + b.y); v[j + 2] = celu_f(v[j + 2] + b.z); v[j + 3] = celu_f(v[j + 3] + b.w);
+            }
+            if (TYPE == 0) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) __stcg(stash + (size_t)(col + j) * kRows, v[j]);
+            }
+        } else if (TYPE == 2) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(colA + col + j));
+                const float4 w = __ldg(reinterpret_cast<const float4*>(colB + col + j));
+                const float b4[4] = {b.x, b.y, b.z, b.w}, w4[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float z = v[j + i] + b4[i];
+                    float e;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * (1.4426950408889634f / kCeluAlpha)));
+                    const bool pos = z > 0.0f;
+                    const float a = pos ? z : fmaf(kCeluAlpha, e, -kCeluAlpha);
+                    esum = fmaf(x.rowOk ? a : 0.0f, w4[i], esum);
+                    v[j + i] = (w4[i] * P.seedScale) * (pos ? 1.0f : e);
+                }
+            }
+        } else if (TYPE == 4) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[j] *= celu_grad_from_act_f(st[16 * h + j]);
+        }
+        // where the two 16-byte units of this half live in the thread's row of the swizzled shared-memory tile
+        const int u0 = x.hsel * 4 + 2 * h;
+        const uint32_t sA = x.sbufRow + (uint32_t)x.c * kTile + (uint32_t)((u0 ^ x.r7) << 4);
+        const uint32_t sB = x.sbufRow + (uint32_t)x.c * kTile + (uint32_t)(((u0 + 1) ^ x.r7) << 4);
+        if (TYPE == 3) {   // celu'(A2) from the activation tile this thread is about to overwrite
+            const uint4 h0 = ld_shared_v4(sA), h1 = ld_shared_v4(sB), l0 = ld_shared_v4(sA + x.sLoOff), l1 = ld_shared_v4(sB + x.sLoOff);
+            const uint32_t hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            const uint32_t ll[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const float2 fh = unpack_h2(hh[i]), fl = unpack_h2(ll[i]);
+                v[2 * i] *= celu_grad_from_act_f(fmaf(fl.x, kLoInv, fh.x));
+                v[2 * i + 1] *= celu_grad_from_act_f(fmaf(fl.y, kLoInv, fh.y));
+            }
+        }
+        uint32_t ph[8], pl[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) split_pack(v[2 * i], v[2 * i + 1], ph[i], pl[i]);
+        if (TYPE == 1 || TYPE == 3) {
+            st_shared_v4(sA, ph[0], ph[1], ph[2], ph[3]);
+            st_shared_v4(sB, ph[4], ph[5], ph[6], ph[7]);
+            st_shared_v4(sA + x.sLoOff, pl[0], pl[1], pl[2], pl[3]);
+            st_shared_v4(sB + x.sLoOff, pl[4], pl[5], pl[6], pl[7]);
+        } else {
+            tmem_st8(x.laneBase + kOpaHi + (uint32_t)(col >> 1), ph);
+            tmem_st8(x.laneBase + kOpaLo + (uint32_t)(col >> 1), pl);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_constant__ ChainParams P) {
+    extern __shared__ unsigned char smemRaw[];
+    const uint32_t rawAddr = smem_u32(smemRaw);
+    const uint32_t base = (rawAddr + 1023u) & ~1023u;
+    const uint32_t xbuf = base;
+    const uint32_t sbuf = xbuf + 2u * P.xChunks * kTile;
+    const uint32_t ring = sbuf + 2u * P.sChunks * kTile;
+    const uint32_t barBase = ring + (uint32_t)P.ring * kTile;
+    auto bFull = [&](int s) { return barBase + 8u * s; };
+    auto bEmpty = [&](int s) { return barBase + 8u * (kMaxRing + s); };
+    auto accFull = [&](int s) { return barBase + 8u * (2 * kMaxRing + s); };
+    auto accEmpty = [&](int s) { return barBase + 8u * (2 * kMaxRing + 2 + s); };
+    auto opReady = [&](int s) { return barBase + 8u * (2 * kMaxRing + 4 + s); };
+    const uint32_t xFull = barBase + 8u * (2 * kMaxRing + 8), xEmpty = xFull + 8u;
+    const uint32_t tmemSlot = xEmpty + 8u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < P.numSpecies; s++)
+            for (int m = 0; m < 8; m++) asm volatile("prefetch.tensormap [%0];" ::"l"(&P.maps[s][m]) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < P.ring; s++) { mbar_init(bFull(s), 1); mbar_init(bEmpty(s), 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(accFull(s), 1); mbar_init(accEmpty(s), kGroupWarps); }
+        for (int s = 0; s < 4; s++) mbar_init(opReady(s), kGroupWarps);
+        mbar_init(xFull, 1);
+        mbar_init(xEmpty, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmemSlot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmemBase;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmemBase) : "r"(tmemSlot));
+
+    auto species_of = [&](int t) {
+        int s = 0;
+        while (s + 1 < P.numSpecies && t >= P.sp[s].tileEnd) s++;
+        return s;
+    };
+
+    if (warp == 0) {
+        // ---- TMA producer ----
+        const bool leader = elect_one();
+        int stage = 0;
+        uint32_t phase = 0, xPhase = 0;
+        for (int t = blockIdx.x; t < P.numTiles; t += gridDim.x) {
+            const int si = species_of(t);
+            const ChainSpecies& sp = P.sp[si];
+            const int row0 = (t - sp.tileBegin) * kRows;
+            const int cx = chunks_of(sp.d0);
+            mbar_wait(xEmpty, xPhase ^ 1u);
+            xPhase ^= 1u;
+            if (leader) {
+                mbar_expect_tx(xFull, 2u * cx * kTile);
+                for (int kc = 0; kc < cx; kc++) {
+                    tma_load_2d(xbuf + kc * kTile, &P.maps[si][6], xFull, kc * 64, row0);
+                    tma_load_2d(xbuf + (P.xChunks + kc) * kTile, &P.maps[si][7], xFull, kc * 64, row0);
+                }
+            }
+            __syncwarp();
+            for (int e = 0; e < P.M; e++)
+                for (int j = 0; j < 6; j++) {
+                    int N, K;
+                    layer_dims(sp, j, N, K);
+                    const int cn = chunks_of(N), ck = chunks_of(K);
+                    for (int c = 0; c < cn; c++)
+                        for (int kc = 0; kc < ck; kc++) {
+                            mbar_wait(bEmpty(stage), phase ^ 1u);
+                            if (leader) {
+                                mbar_expect_tx(bFull(stage), kTile);
+                                tma_load_2d(ring + stage * kTile, &P.maps[si][j], bFull(stage), kc * 64, (e * cn + c) * 128);
+                            }
+                            __syncwarp();
+                            if (++stage == P.ring) { stage = 0; phase ^= 1u; }
+                        }
+                }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer ----
+        const bool leader = elect_one();
+        const uint64_t descBits = make_desc(0);
+        constexpr uint32_t idescWide = idesc_f16(128, 128), idescNarrow = idesc_f16(128, 64);
+        int stage = 0;
+        uint32_t phase = 0, accBits = 0, opBits = 0, xPhase = 0;
+        for (int t = blockIdx.x; t < P.numTiles; t += gridDim.x) {
+            const int si = species_of(t);
+            const ChainSpecies& sp = P.sp[si];
+            mbar_wait(xFull, xPhase);
+            xPhase ^= 1u;
+            tc_fence_after();
+            for (int e = 0; e < P.M; e++) {
+                int chunkIdx = 0;
+                for (int j = 0; j < 6; j++) {
+                    int N, K;
+                    layer_dims(sp, j, N, K);
+                    const int cn = chunks_of(N), ck = chunks_of(K);
+                    const bool aTmem = (j & 1) != 0;                 // F2, G3, G1 read their A operand from tensor memory
+                    const uint32_t aSmem = j == 0 ? xbuf : sbuf;
+                    const uint32_t aLo16 = ((j == 0 ? P.xChunks : P.sChunks) * kTile) >> 4;
+                    for (int c = 0; c < cn; c++) {
+                        const int acc = chunkIdx & 1;
+                        chunkIdx++;
+                        mbar_wait(accEmpty(acc), ((accBits >> acc) & 1u) ^ 1u);
+                        accBits ^= 1u << acc;
+                        tc_fence_after();
+                        const uint32_t d = tmemBase + acc * kAccCols;
+                        for (int kc = 0; kc < ck; kc++) {
+                            if (c == 0 && j > 0) {   // columns [64 kc, 64 kc + 64) of the A operand come from the previous layer's epilogue
+                                mbar_wait(opReady(kc), (opBits >> kc) & 1u);
+                                opBits ^= 1u << kc;
+                                tc_fence_after();
+                            }
+                            mbar_wait(bFull(stage), phase);
+                            tc_fence_after();
+                            if (leader) {
+                                const int ksteps = min(4, (K - kc * 64) >> 4);
+                                const uint64_t bDesc = descBits + ((ring + stage * kTile) >> 4);
+                                if (aTmem) {
+                                    const uint32_t aHi = tmemBase + kOpaHi + kc * 32;
+#pragma unroll
+                                    for (int s = 0; s < 4; s++) {
+                                        if (s < ksteps) {
+                                            umma_f16_ts(d, aHi + 8 * s, bDesc + 2 * s, idescWide, (kc | s) != 0 ? 1u : 0u);
+                                            umma_f16_ts(d + 64, aHi + (kOpaLo - kOpaHi) + 8 * s, bDesc + 2 * s, idescNarrow, 1u);
+                                        }
+                                    }
+                                } else {
+                                    const uint64_t aDesc = descBits + ((aSmem + kc * kTile) >> 4);
+#pragma unroll
+                                    for (int s = 0; s < 4; s++) {
+                                        if (s < ksteps) {
+                                            umma_f16(d, aDesc + 2 * s, bDesc + 2 * s, idescWide, (kc | s) != 0 ? 1u : 0u);
+                                            umma_f16(d + 64, aDesc + aLo16 + 2 * s, bDesc + 2 * s, idescNarrow, 1u);
+                                        }
+                                    }
+                                }
+                                umma_commit(bEmpty(stage));
+                                if (kc == ck - 1) umma_commit(accFull(acc));
+                                if (j == 0 && e == P.M - 1 && c == cn - 1 && kc == ck - 1) umma_commit(xEmpty);   // X may be replaced
+                            }
+                            __syncwarp();
+                            if (++stage == P.ring) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        // ---- epilogue groups ----
+        const int ew = warp - kFirstEpiWarp, g = ew >> 3, q = warp & 3, hsel = (ew >> 2) & 1;
+        const int r = q * 32 + lane;
+        EpiCtx x;
+        x.laneBase = tmemBase + ((uint32_t)(q * 32) << 16);
+        x.accCol = (uint32_t)g * kAccCols + (uint32_t)hsel * 32;
+        x.sbufRow = sbuf + (uint32_t)r * 128;
+        x.sLoOff = (uint32_t)P.sChunks * kTile;
+        x.r7 = r & 7;
+        x.hsel = hsel;
+        float* const stash = P.stash + (size_t)blockIdx.x * (kStashCols * kRows) + r;
+        uint32_t fullPhase = 0;
+        for (int t = blockIdx.x; t < P.numTiles; t += gridDim.x) {
+            const int si = species_of(t);
+            const ChainSpecies& sp = P.sp[si];
+            const int row0 = (t - sp.tileBegin) * kRows;
+            x.rowOk = row0 + r < sp.rows;
+            float* const dxRow = P.dX + (size_t)(sp.rowStart + row0 + r) * P.ldx;
+            float esum = 0.0f;
+            for (int e = 0; e < P.M; e++) {
+                int chunkIdx = 0;
+                for (int j = 0; j < 6; j++) {
+                    int N, K;
+                    layer_dims(sp, j, N, K);
+                    const int cn = chunks_of(N);
+                    for (int c = 0; c < cn; c++) {
+                        const int acc = chunkIdx & 1;
+                        chunkIdx++;
+                        if (acc != g) continue;
+                        x.c = c;
+                        x.n0 = c * 64 + hsel * 32;
+                        const bool valid = x.n0 < N;             // warp-uniform: widths are multiples of 32
+                        if (valid) {
+                            switch (j) {
+                                case 0: epi_chunk<0>(P, x, sp.bias[0] + (size_t)e * N, nullptr, stash, dxRow, false, accFull(g), fullPhase, accEmpty(g), lane, esum); break;
+                                case 1: epi_chunk<1>(P, x, sp.bias[1] + (size_t)e * N, nullptr, stash, dxRow, false, accFull(g), fullPhase, accEmpty(g), lane, esum); break;
+                                case 2: epi_chunk<2>(P, x, sp.bias[2] + (size_t)e * N, sp.w3 + (size_t)e * N, stash, dxRow, false, accFull(g), fullPhase, accEmpty(g), lane, esum); break;
+                                case 3: epi_chunk<3>(P, x, nullptr, nullptr, stash, dxRow, false, accFull(g), fullPhase, accEmpty(g), lane, esum); break;
+                                case 4: epi_chunk<4>(P, x, nullptr, nullptr, stash, dxRow, false, accFull(g), fullPhase, accEmpty(g), lane, esum); break;
+                                default: epi_chunk<5>(P, x, nullptr, nullptr, stash, dxRow, e == 0, accFull(g), fullPhase, accEmpty(g), lane, esum); break;
+                            }
+                        } else {
+                            mbar_wait(accFull(g), fullPhase);
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(accEmpty(g));
+                        }
+                        fullPhase ^= 1u;
+                        if (j < 5) {
+                            // publish the 64-column slice of the next layer's A operand this warp has (or has not) contributed to
+                            if (j == 1 || j == 3) fence_proxy_async_smem();
+                            else { tmem_st_wait(); tc_fence_before(); }
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(opReady(c));
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, o);
+            if (lane == 0 && esum != 0.0f) atomicAdd(P.energyAcc, (double)esum);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(512u) : "memory");
+    }
+}
+
+// weights of one GEMM as the TMA-friendly block matrix: for member e and 64-row chunk c, rows (e*cn + c)*128 + [0, 64) hold the fp16
+// high parts of output rows 64 c .. 64 c + 63 (zero beyond N) and rows + [64, 128) the scaled low parts; K columns, row pitch K
+void pack_weights(std::vector<__half>& out, int M, int N, int K, const float* W, bool transposed, int ldw, int memberStride) {
+    const int cn = chunks_of(N);
+    out.assign((size_t)M * cn * 128 * K, __float2half_rn(0.0f));
+    for (int e = 0; e < M; e++)
+        for (int n = 0; n < N; n++) {
+            const int c = n >> 6, rr = n & 63;
+            __half* hi = out.data() + ((size_t)(e * cn + c) * 128 + rr) * K;
+            __half* lo = hi + (size_t)64 * K;
+            for (int k = 0; k < K; k++) {
+                // forward: W[e][n][k]; transposed (backward): the same layer's W[e][k][n]
+                const float v = transposed ? W[(size_t)e * memberStride + (size_t)k * ldw + n] : W[(size_t)e * memberStride + (size_t)n * ldw + k];
+                const __half h = __float2half_rn(v);
+                hi[k] = h;
+                lo[k] = __float2half_rn((v - __half2float(h)) * kLoScale);
+            }
+        }
+}
+
+}  // namespace
+
+struct MlpChain::Impl {
+    ChainParams P;
+    std::vector<__half*> dev;
+    float* stash = nullptr;
+    int grid = 0;
+    uint32_t smem = 0;
+};
+
+bool MlpChain::eligible(int numSpecies, const SpeciesDesc* sp, int featureStride) {
+    if (numSpecies < 1 || numSpecies > kMaxSp) return false;
+    int sMax = 0;
+    for (int s = 0; s < numSpecies; s++) {
+        const int* d = sp[s].d;
+        if (d[0] != featureStride || d[0] > 128 || d[1] > 256 || d[2] > 256 || d[3] > 256) return false;
+        for (int l = 0; l < 4; l++)
+            if (d[l] <= 0 || d[l] % 32 != 0) return false;
+        sMax = std::max(sMax, chunks_of(d[2]));
+    }
+    const uint32_t fixed = 2u * (chunks_of(featureStride) + sMax) * kTile + 1024 + 512;
+    return fixed + 3 * kTile <= kMaxSmem;
+}
+
+MlpChain::MlpChain(int ensemble, int numSpecies, const SpeciesDesc* sp, const __half* featHi, const __half* featLo, int featureStride)
+    : impl_(new Impl) {
+    NNP_REQUIRE(eligible(numSpecies, sp, featureStride), "MlpChain: network shape not supported by the fused kernel");
+    ChainParams& P = impl_->P;
+    std::memset(&P, 0, sizeof(P));
+    P.numSpecies = numSpecies; P.M = ensemble; P.ldx = featureStride;
+    P.xChunks = chunks_of(featureStride);
+    int tiles = 0;
+    for (int s = 0; s < numSpecies; s++) {
+        ChainSpecies& c = P.sp[s];
+        c.d0 = sp[s].d[0]; c.d1 = sp[s].d[1]; c.d2 = sp[s].d[2]; c.d3 = sp[s].d[3];
+        c.rows = sp[s].rows; c.rowStart = sp[s].rowStart;
+        c.tileBegin = tiles;
+        tiles += (c.rows + kRows - 1) / kRows;
+        c.tileEnd = tiles;
+        for (int l = 0; l < 3; l++) c.bias[l] = sp[s].bias[l];
+        c.w3 = sp[s].w3;
+        P.sChunks = std::max(P.sChunks, chunks_of(c.d2));
+        // GEMM j: N, K, layer, transposed
+        const int gN[6] = {c.d1, c.d2, c.d3, c.d2, c.d1, c.d0}, gK[6] = {c.d0, c.d1, c.d2, c.d3, c.d2, c.d1};
+        const int gL[6] = {0, 1, 2, 2, 1, 0};
+        for (int j = 0; j < 6; j++) {
+            const int l = gL[j], in = sp[s].d[l], out = sp[s].d[l + 1];
+            std::vector<__half> host;
+            pack_weights(host, ensemble, gN[j], gK[j], sp[s].W[l], j >= 3, in, out * in);
+            __half* d = nullptr;
+            NNP_CUDA_CHECK(cudaMalloc(&d, sizeof(__half) * host.size()));
+            NNP_CUDA_CHECK(cudaMemcpy(d, host.data(), sizeof(__half) * host.size(), cudaMemcpyHostToDevice));
+            impl_->dev.push_back(d);
+            P.maps[s][j] = tc_make_map(d, (long long)ensemble * chunks_of(gN[j]) * 128, gK[j], gK[j]);
+        }
+        if (c.rows > 0) {
+            P.maps[s][6] = tc_make_map(featHi + (size_t)c.rowStart * featureStride, c.rows, featureStride, featureStride);
+            P.maps[s][7] = tc_make_map(featLo + (size_t)c.rowStart * featureStride, c.rows, featureStride, featureStride);
+        } else {
+            P.maps[s][6] = P.maps[s][0]; P.maps[s][7] = P.maps[s][0];
+        }
+    }
+    P.numTiles = tiles;
+    const uint32_t fixed = 2u * (P.xChunks + P.sChunks) * kTile + 1024 + 512;
+    P.ring = (int)std::min<uint32_t>(kMaxRing, (kMaxSmem - fixed) / kTile);
+    impl_->smem = fixed + P.ring * kTile;
+    int dev = 0, sms = 0;
+    NNP_CUDA_CHECK(cudaGetDevice(&dev));
+    NNP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    impl_->grid = std::max(1, std::min(tiles, sms));
+    NNP_CUDA_CHECK(cudaMalloc(&impl_->stash, sizeof(float) * (size_t)impl_->grid * kStashCols * kRows));
+    P.stash = impl_->stash;
+}
+
+MlpChain::~MlpChain() {
+    for (__half* p : impl_->dev) cudaFree(p);
+    cudaFree(impl_->stash);
+    delete impl_;
+}
+
+void MlpChain::launch(double* energyAcc, float* dX, float seedScale, float outScale, cudaStream_t stream) {
+    ChainParams& P = impl_->P;
+    if (P.numTiles == 0) return;
+    P.energyAcc = energyAcc; P.dX = dX; P.seedScale = seedScale; P.outScale = outScale;
+    // per device, every time: the attribute is cheap to set and a process may drive several GPUs
+    NNP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)impl_->smem));
+    mlp_chain_kernel<<<impl_->grid, kThreads, impl_->smem, stream>>>(P);
+    NNP_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+}
+
+}  // namespace nnpops

@@ -22,6 +22,7 @@
 #include <mutex>
 #include <tuple>
 #include "species_mlp.cuh"
+#include "tcgen05_util.cuh"
 
 namespace nnpops {
 
@@ -49,110 +50,7 @@ constexpr int kThreads = (kFirstEpiWarp + kEpiWarps) * 32;   // 576 threads -> u
 __host__ __device__ constexpr uint32_t smem_bytes_of(int mode) {
     return stages_of(mode) * kStageBytes + kEpiWarps * warp_bytes_of(mode) + 1024 /*alignment slack*/ + 256 /*barriers*/;
 }
-constexpr float kLoScale = 2048.0f, kLoInv = 1.0f / 2048.0f;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmemD), "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// true in exactly one lane of a converged warp; ptxas recognises ELECT and keeps the leader's operands in uniform registers
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "elect.sync _|p, 0xffffffff;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major operand tile [rows][64 halves] written by TMA with SWIZZLE_128B: 8-row groups are 1024 bytes apart (SBO), the
-// leading-dimension offset is unused for swizzled K-major layouts (encoded 1), descriptor version 1 (Blackwell), layout type 2.
-__device__ __forceinline__ uint64_t make_desc(uint32_t smemAddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smemAddr >> 4) & 0x3fff);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, "
-        "%27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// celu(x) = x for x > 0, alpha (exp(x / alpha) - 1) otherwise: one ex2 per element whatever the sign, then a select (for large
-// positive x the exponential overflows to +inf, which the select discards)
-__device__ __forceinline__ float celu_f(float x) {
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * (1.4426950408889634f / kCeluAlpha)));
-    const float neg = fmaf(kCeluAlpha, e, -kCeluAlpha);
-    return x > 0.0f ? x : neg;
-}
-__device__ __forceinline__ float celu_grad_from_act_f(float a) { return a > 0.0f ? 1.0f : a * (1.0f / kCeluAlpha) + 1.0f; }
-
-__device__ __forceinline__ void split_f(float v, __half& hi, __half& lo) {
-    hi = __float2half_rn(v);
-    lo = __float2half_rn((v - __half2float(hi)) * kLoScale);
-}
+using namespace tc;   // inline-PTX wrappers (tcgen05_util.cuh)
 
 struct TcArgs {
     int M, N, K, batch;
@@ -214,12 +112,6 @@ __device__ __forceinline__ void staged_load_half(unsigned char* stg, uint32_t (&
         pk[4 * i] = t.x; pk[4 * i + 1] = t.y; pk[4 * i + 2] = t.z; pk[4 * i + 3] = t.w;
     }
     __syncwarp();
-}
-
-__device__ __forceinline__ float2 unpack_h2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-    const __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 // warp (q = TMEM lane quarter, hsel = column block) handles rows q*32 + lane and columns [hsel*32, hsel*32 + 32) of the tile.  Four
@@ -570,11 +462,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_con
 
 // ---- host side ----------------------------------------------------------------------------------------------------
 
+}  // namespace
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-EncodeTiledFn encode_fn() {
+static EncodeTiledFn encode_fn() {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* p = nullptr;
@@ -589,7 +483,7 @@ EncodeTiledFn encode_fn() {
 // 2-D fp16 tensor [rows][cols] with row pitch ld (elements); box = 64 columns x 128 rows, 128-byte swizzle, OOB reads give zeros.
 // The encodes are cached: a model launches the same dozen GEMMs on the same buffers every evaluation, and 48 driver calls per
 // evaluation are a visible share of the host time of small systems and of the sharded-box mode.
-CUtensorMap make_map(const __half* ptr, long long rows, long long cols, long long ld) {
+CUtensorMap tc_make_map(const __half* ptr, long long rows, long long cols, long long ld) {
     NNP_REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld * 2) % 16 == 0, "tcgen05 GEMM operands must be 16-byte aligned");
     static std::mutex mu;
     static std::map<std::tuple<const void*, long long, long long, long long>, CUtensorMap> cache;
@@ -610,6 +504,8 @@ CUtensorMap make_map(const __half* ptr, long long rows, long long cols, long lon
     cache.emplace(key, m);
     return m;
 }
+
+namespace {
 
 bool g_forceStreaming = std::getenv("NNPOPS_GEMM_STREAMING") != nullptr;   // A/B switch for measurements
 
@@ -641,8 +537,8 @@ void launch_gemm_tcgen05(const GemmArgsH& a, cudaStream_t stream) {
         NNP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_of(3)));
         attrSet = true;
     }
-    const CUtensorMap mAhi = make_map(a.Ahi, a.M, a.aCols, a.lda), mAlo = make_map(a.Alo, a.M, a.aCols, a.lda);
-    const CUtensorMap mBhi = make_map(a.Bhi, a.bRows, a.K, a.ldb), mBlo = make_map(a.Blo, a.bRows, a.K, a.ldb);
+    const CUtensorMap mAhi = tc_make_map(a.Ahi, a.M, a.aCols, a.lda), mAlo = tc_make_map(a.Alo, a.M, a.aCols, a.lda);
+    const CUtensorMap mBhi = tc_make_map(a.Bhi, a.bRows, a.K, a.ldb), mBlo = tc_make_map(a.Blo, a.bRows, a.K, a.ldb);
     TcArgs g;
     std::memset(&g, 0, sizeof(g));
     g.M = a.M; g.N = a.N; g.K = a.K; g.batch = a.batch; g.aBatchCols = a.aBatchCols; g.bBatchRows = a.bBatchRows; g.mode = a.epilogue;

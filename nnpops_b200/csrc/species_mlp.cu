@@ -2,6 +2,7 @@
 // mlp_tcgen05.cu and plugs in through the same GemmArgs.
 #include "species_mlp.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace nnpops {
@@ -245,6 +246,7 @@ SpeciesMlp::SpeciesMlp(int numSpecies, int ensemble, int numLayers, const int* d
             NNP_CUDA_CHECK(cudaMemcpy(ly.b, hb[s][l].data(), sizeof(float) * nb, cudaMemcpyHostToDevice));
         }
     }
+    hW_ = std::move(hW);
     act_.assign(L_ - 1, nullptr);
     dz_.assign(L_ - 1, nullptr);
     const size_t nr = (size_t)rows_ + 1;   // one spare row (target of the AEV stores of centres this rank does not own)
@@ -304,6 +306,33 @@ void SpeciesMlp::setImpl(MlpImpl impl) {
     // the fp32 activation buffers of the validation path are not needed any more
     for (float*& p : act_) { cudaFree(p); p = nullptr; }
     for (float*& p : dz_) { cudaFree(p); p = nullptr; }
+    // three hidden layers on a compact input: the whole chain runs in one kernel with the activations on chip (mlp_chain.cu)
+    if (L_ == 4 && std::getenv("NNPOPS_NO_CHAIN") == nullptr && !hW_.empty()) {
+        std::vector<MlpChain::SpeciesDesc> sd(S_);
+        for (int s = 0; s < S_; s++) {
+            MlpChain::SpeciesDesc& d = sd[s];
+            d.d[0] = layers_[s][0].inP;
+            for (int l = 0; l < 3; l++) { d.d[l + 1] = layers_[s][l].outP; d.W[l] = hW_[s][l].data(); d.bias[l] = layers_[s][l].b; }
+            d.rowStart = rowStart_[s]; d.rows = rowStart_[s + 1] - rowStart_[s];
+            d.w3 = layers_[s][3].W;
+        }
+        bool padOk = true;   // the chain reads featureStride columns of X: they must all be real (padded) input columns
+        for (int s = 0; s < S_; s++) padOk = padOk && layers_[s][0].inP == featStride_;
+        if (padOk && MlpChain::eligible(S_, sd.data(), featStride_))
+            chain_.reset(new MlpChain(M_, S_, sd.data(), featHi_, featLo_, featStride_));
+    }
+    hW_.clear();
+    hW_.shrink_to_fit();
+}
+
+void SpeciesMlp::forwardBackward(float* energy, float* featureGrad, cudaStream_t stream) {
+    NNP_REQUIRE(chain_ != nullptr, "SpeciesMlp::forwardBackward needs the fused chain kernel");
+    NNP_CUDA_CHECK(cudaMemsetAsync(energyAcc_, 0, sizeof(double), stream));
+    chain_->launch(energyAcc_, featureGrad, kGradScale / M_, 1.0f / kGradScale, stream);
+    finish_energy_kernel<<<1, 1, 0, stream>>>(energyAcc_, energyBias_, M_, energy);
+    count_launch();
+    NNP_CUDA_CHECK(cudaGetLastError());
+    haveForward_ = true;
 }
 
 void SpeciesMlp::forwardTc(const float* features, float* energy, cudaStream_t stream) {

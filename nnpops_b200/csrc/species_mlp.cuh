@@ -9,8 +9,10 @@
 // the per-layer maximum (BatchedNN.py:71-83).
 #pragma once
 #include <cuda_fp16.h>
+#include <memory>
 #include <vector>
 #include "common.cuh"
+#include "mlp_chain.cuh"
 
 namespace nnpops {
 
@@ -36,6 +38,10 @@ public:
     void forward(const float* features, float* energy, cudaStream_t stream);
     // featureGrad: device [rows][featureStride] <- dE/dfeatures (same row order); uses the activations of the last forward
     void backward(float* featureGrad, cudaStream_t stream);
+    // Tensor-core path with the fused layer-chain kernel (mlp_chain.cu): energy and dE/dfeatures of one evaluation in one launch.
+    // fused() says whether the network shape allows it (else call forward + backward); NNPOPS_NO_CHAIN=1 switches it off.
+    bool fused() const { return chain_ != nullptr; }
+    void forwardBackward(float* energy, float* featureGrad, cudaStream_t stream);
 
     // tensor-core path: the feature matrix as fp16 hi/lo pairs [rows][featureStride]; the AEV kernels write it directly and
     // forward() is then called with features == nullptr
@@ -67,6 +73,8 @@ private:
     void backwardTc(float* featureGrad, cudaStream_t stream);
     void forwardRowsTc(int s, int r0, int nr, int w0, cudaStream_t stream);
     void backwardRowsTc(int s, int r0, int nr, int w0, float* featureGrad, cudaStream_t stream);
+    std::unique_ptr<MlpChain> chain_;
+    std::vector<std::vector<std::vector<float>>> hW_;   // host copy of the padded weights [S][L] until setImpl has built its operands
     double* energyAcc_ = nullptr;
     double energyBias_ = 0;      // sum over atoms and members of the last-layer bias
     MlpImpl impl_ = MlpImpl::Simt;
