@@ -38,7 +38,7 @@ constexpr int kMaxSp = 7;
 constexpr int kRows = 128;
 constexpr uint32_t kTile = 128 * 128;        // 16 KB: [128 rows][64 halves] A tile, or [64 hi + 64 lo rows][64 halves] B block
 constexpr int kMaxRing = 8;
-constexpr int kFirstEpiWarp = 2, kGroupWarps = 8;
+constexpr int kFirstEpiWarp = 4, kGroupWarps = 8;   // warps 0..3: TMA producer, two MMA issuers, one idle (keeps warp % 4 = TMEM lane quarter simple)
 constexpr int kThreads = (kFirstEpiWarp + 2 * kGroupWarps) * 32;
 constexpr uint32_t kAccCols = 128;           // one accumulator stage: D1 (64 columns) | D2 (64 columns)
 constexpr uint32_t kOpaHi = 256, kOpaLo = 384;   // A operand in TMEM: packed fp16 pairs, hi part and lo part (128 columns each: K <= 256)
@@ -89,6 +89,30 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// tcgen05.mma with the shared-memory descriptors given as low words (start address | LBO) + one common high word: the issue loop
+// then runs on 32-bit adds only
+__device__ __forceinline__ void umma_ss_lo(uint32_t tmemD, uint32_t aLo, uint32_t bLo, uint32_t descHi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "mov.b64 da, {%1, %3};\n"
+        "mov.b64 db, {%2, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+        "}\n" ::"r"(tmemD), "r"(aLo), "r"(bLo), "r"(descHi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_ts_lo(uint32_t tmemD, uint32_t tmemA, uint32_t bLo, uint32_t descHi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 db;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "mov.b64 db, {%2, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
+        "}\n" ::"r"(tmemD), "r"(tmemA), "r"(bLo), "r"(descHi), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 // what an epilogue thread needs to know about its chunk
 struct EpiCtx {
     uint32_t laneBase;      // TMEM address of the thread's lane, column 0
@@ -110,6 +134,11 @@ __device__ __forceinline__ void epi_chunk(const ChainParams& P, const EpiCtx& x,
 #pragma unroll
         for (int i = 0; i < 32; i++) st[i] = __ldcg(stash + (size_t)(x.n0 + i) * kRows);
     }
+    // per-column constants (bias; output-layer weight): lane l fetches column n0 + l before the wait and every lane picks its
+    // values up by shuffle -- with 224 KB of shared memory in use the L1 holds next to nothing, a load after the wait costs an L2 trip
+    float colConstA = 0.0f, colConstB = 0.0f;
+    if (TYPE <= 2) colConstA = __ldg(colA + x.n0 + lane);
+    if (TYPE == 2) colConstB = __ldg(colB + x.n0 + lane);
     mbar_wait(accFullBar, fullPhase);
     tc_fence_after();
 #pragma unroll
@@ -141,30 +170,22 @@ __device__ __forceinline__ void epi_chunk(const ChainParams& P, const EpiCtx& x,
         }
         if (TYPE == 0 || TYPE == 1) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(colA + col + j));
-                v[j] = celu_f(v[j] + b.x); v[j + 1] = celu_f(v[j + 1] + b.y); v[j + 2] = celu_f(v[j + 2] + b.z); v[j + 3] = celu_f(v[j + 3] + b.w);
-            }
+            for (int j = 0; j < 16; j++) v[j] = celu_f(v[j] + __shfl_sync(0xffffffffu, colConstA, 16 * h + j));
             if (TYPE == 0) {
 #pragma unroll
                 for (int j = 0; j < 16; j++) __stcg(stash + (size_t)(col + j) * kRows, v[j]);
             }
         } else if (TYPE == 2) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(colA + col + j));
-                const float4 w = __ldg(reinterpret_cast<const float4*>(colB + col + j));
-                const float b4[4] = {b.x, b.y, b.z, b.w}, w4[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const float z = v[j + i] + b4[i];
-                    float e;
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * (1.4426950408889634f / kCeluAlpha)));
-                    const bool pos = z > 0.0f;
-                    const float a = pos ? z : fmaf(kCeluAlpha, e, -kCeluAlpha);
-                    esum = fmaf(x.rowOk ? a : 0.0f, w4[i], esum);
-                    v[j + i] = (w4[i] * P.seedScale) * (pos ? 1.0f : e);
-                }
+            for (int j = 0; j < 16; j++) {
+                const float z = v[j] + __shfl_sync(0xffffffffu, colConstA, 16 * h + j);
+                const float w = __shfl_sync(0xffffffffu, colConstB, 16 * h + j);
+                float e;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * (1.4426950408889634f / kCeluAlpha)));
+                const bool pos = z > 0.0f;
+                const float a = pos ? z : fmaf(kCeluAlpha, e, -kCeluAlpha);
+                esum = fmaf(x.rowOk ? a : 0.0f, w, esum);
+                v[j] = (w * P.seedScale) * (pos ? 1.0f : e);
             }
         } else if (TYPE == 4) {
 #pragma unroll
@@ -214,7 +235,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
     auto accEmpty = [&](int s) { return barBase + 8u * (2 * kMaxRing + 2 + s); };
     auto opReady = [&](int s) { return barBase + 8u * (2 * kMaxRing + 4 + s); };
     const uint32_t xFull = barBase + 8u * (2 * kMaxRing + 8), xEmpty = xFull + 8u;
-    const uint32_t tmemSlot = xEmpty + 8u;
+    const uint32_t chainDone = xEmpty + 8u;   // both issuers' MMAs of a chain have completed (its last layer reads the TMEM operand)
+    const uint32_t tmemSlot = chainDone + 8u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -226,8 +248,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
         for (int s = 0; s < 2; s++) { mbar_init(accFull(s), 1); mbar_init(accEmpty(s), kGroupWarps); }
         for (int s = 0; s < 4; s++) mbar_init(opReady(s), kGroupWarps);
         mbar_init(xFull, 1);
-        mbar_init(xEmpty, 1);
+        mbar_init(xEmpty, 2);   // both MMA issuers
+        mbar_init(chainDone, 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // flat chunk schedule of one chain per species (entry = layer << 3 | chunk): keeps the epilogue's loop state down to a counter
+    unsigned char* const chunkTab = smemRaw + (barBase - rawAddr) + 256;
+    if (warp == 2 && lane < P.numSpecies) {
+        int n = 0;
+        for (int j = 0; j < 6; j++) {
+            int N, K;
+            layer_dims(P.sp[lane], j, N, K);
+            for (int c = 0; c < chunks_of(N); c++) chunkTab[lane * 32 + n++] = (unsigned char)(j << 3 | c);
+        }
+        chunkTab[lane * 32 + 31] = (unsigned char)n;
     }
     __syncwarp();
     if (warp == 1) {
@@ -246,114 +280,146 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
         return s;
     };
 
-    if (warp == 0) {
-        // ---- TMA producer ----
-        const bool leader = elect_one();
-        int stage = 0;
-        uint32_t phase = 0, xPhase = 0;
-        for (int t = blockIdx.x; t < P.numTiles; t += gridDim.x) {
-            const int si = species_of(t);
-            const ChainSpecies& sp = P.sp[si];
-            const int row0 = (t - sp.tileBegin) * kRows;
-            const int cx = chunks_of(sp.d0);
-            mbar_wait(xEmpty, xPhase ^ 1u);
-            xPhase ^= 1u;
-            if (leader) {
-                mbar_expect_tx(xFull, 2u * cx * kTile);
-                for (int kc = 0; kc < cx; kc++) {
-                    tma_load_2d(xbuf + kc * kTile, &P.maps[si][6], xFull, kc * 64, row0);
-                    tma_load_2d(xbuf + (P.xChunks + kc) * kTile, &P.maps[si][7], xFull, kc * 64, row0);
+    if (warp == 0 || warp == 3) {
+        // ---- TMA producers: warp 0 feeds issuer 0 (even chunks), warp 3 issuer 1 (odd chunks), each through its own half of the weight
+        // ring.  One ring per issuer, because an mbarrier wait only knows the PARITY of a phase: a consumer that is allowed to wait
+        // for fill m + 1 of a slot before the other consumer has seen fill m reads "done" from the stale parity.  Warp 0 also loads X.
+        if (elect_one()) {
+            const int g = warp == 0 ? 0 : 1;
+            const int half = P.ring >> 1, s0 = g * half;
+            int stage = 0;
+            uint32_t phase = 0, xPhase = 0;
+            for (int t = blockIdx.x; t < P.numTiles; t += gridDim.x) {
+                const int si = species_of(t);
+                const ChainSpecies& sp = P.sp[si];
+                if (g == 0) {
+                    const int row0 = (t - sp.tileBegin) * kRows;
+                    const int cx = chunks_of(sp.d0);
+                    mbar_wait(xEmpty, xPhase ^ 1u);
+                    xPhase ^= 1u;
+                    mbar_expect_tx(xFull, 2u * cx * kTile);
+                    for (int kc = 0; kc < cx; kc++) {
+                        tma_load_2d(xbuf + kc * kTile, &P.maps[si][6], xFull, kc * 64, row0);
+                        tma_load_2d(xbuf + (P.xChunks + kc) * kTile, &P.maps[si][7], xFull, kc * 64, row0);
+                    }
                 }
-            }
-            __syncwarp();
-            for (int e = 0; e < P.M; e++)
-                for (int j = 0; j < 6; j++) {
-                    int N, K;
-                    layer_dims(sp, j, N, K);
-                    const int cn = chunks_of(N), ck = chunks_of(K);
-                    for (int c = 0; c < cn; c++)
-                        for (int kc = 0; kc < ck; kc++) {
-                            mbar_wait(bEmpty(stage), phase ^ 1u);
-                            if (leader) {
-                                mbar_expect_tx(bFull(stage), kTile);
-                                tma_load_2d(ring + stage * kTile, &P.maps[si][j], bFull(stage), kc * 64, (e * cn + c) * 128);
+                for (int e = 0; e < P.M; e++) {
+                    int chunkIdx = 0;
+                    for (int j = 0; j < 6; j++) {
+                        int N, K;
+                        layer_dims(sp, j, N, K);
+                        const int cn = chunks_of(N), ck = chunks_of(K);
+                        for (int c = 0; c < cn; c++) {
+                            if ((chunkIdx++ & 1) != g) continue;
+                            for (int kc = 0; kc < ck; kc++) {
+                                mbar_wait(bEmpty(s0 + stage), phase ^ 1u);
+                                mbar_expect_tx(bFull(s0 + stage), kTile);
+                                tma_load_2d(ring + (s0 + stage) * kTile, &P.maps[si][j], bFull(s0 + stage), kc * 64, (e * cn + c) * 128);
+                                if (++stage == half) { stage = 0; phase ^= 1u; }
                             }
-                            __syncwarp();
-                            if (++stage == P.ring) { stage = 0; phase ^= 1u; }
-                        }
-                }
-        }
-    } else if (warp == 1) {
-        // ---- MMA issuer ----
-        const bool leader = elect_one();
-        const uint64_t descBits = make_desc(0);
-        constexpr uint32_t idescWide = idesc_f16(128, 128), idescNarrow = idesc_f16(128, 64);
-        int stage = 0;
-        uint32_t phase = 0, accBits = 0, opBits = 0, xPhase = 0;
-        for (int t = blockIdx.x; t < P.numTiles; t += gridDim.x) {
-            const int si = species_of(t);
-            const ChainSpecies& sp = P.sp[si];
-            mbar_wait(xFull, xPhase);
-            xPhase ^= 1u;
-            tc_fence_after();
-            for (int e = 0; e < P.M; e++) {
-                int chunkIdx = 0;
-                for (int j = 0; j < 6; j++) {
-                    int N, K;
-                    layer_dims(sp, j, N, K);
-                    const int cn = chunks_of(N), ck = chunks_of(K);
-                    const bool aTmem = (j & 1) != 0;                 // F2, G3, G1 read their A operand from tensor memory
-                    const uint32_t aSmem = j == 0 ? xbuf : sbuf;
-                    const uint32_t aLo16 = ((j == 0 ? P.xChunks : P.sChunks) * kTile) >> 4;
-                    for (int c = 0; c < cn; c++) {
-                        const int acc = chunkIdx & 1;
-                        chunkIdx++;
-                        mbar_wait(accEmpty(acc), ((accBits >> acc) & 1u) ^ 1u);
-                        accBits ^= 1u << acc;
-                        tc_fence_after();
-                        const uint32_t d = tmemBase + acc * kAccCols;
-                        for (int kc = 0; kc < ck; kc++) {
-                            if (c == 0 && j > 0) {   // columns [64 kc, 64 kc + 64) of the A operand come from the previous layer's epilogue
-                                mbar_wait(opReady(kc), (opBits >> kc) & 1u);
-                                opBits ^= 1u << kc;
-                                tc_fence_after();
-                            }
-                            mbar_wait(bFull(stage), phase);
-                            tc_fence_after();
-                            if (leader) {
-                                const int ksteps = min(4, (K - kc * 64) >> 4);
-                                const uint64_t bDesc = descBits + ((ring + stage * kTile) >> 4);
-                                if (aTmem) {
-                                    const uint32_t aHi = tmemBase + kOpaHi + kc * 32;
-#pragma unroll
-                                    for (int s = 0; s < 4; s++) {
-                                        if (s < ksteps) {
-                                            umma_f16_ts(d, aHi + 8 * s, bDesc + 2 * s, idescWide, (kc | s) != 0 ? 1u : 0u);
-                                            umma_f16_ts(d + 64, aHi + (kOpaLo - kOpaHi) + 8 * s, bDesc + 2 * s, idescNarrow, 1u);
-                                        }
-                                    }
-                                } else {
-                                    const uint64_t aDesc = descBits + ((aSmem + kc * kTile) >> 4);
-#pragma unroll
-                                    for (int s = 0; s < 4; s++) {
-                                        if (s < ksteps) {
-                                            umma_f16(d, aDesc + 2 * s, bDesc + 2 * s, idescWide, (kc | s) != 0 ? 1u : 0u);
-                                            umma_f16(d + 64, aDesc + aLo16 + 2 * s, bDesc + 2 * s, idescNarrow, 1u);
-                                        }
-                                    }
-                                }
-                                umma_commit(bEmpty(stage));
-                                if (kc == ck - 1) umma_commit(accFull(acc));
-                                if (j == 0 && e == P.M - 1 && c == cn - 1 && kc == ck - 1) umma_commit(xEmpty);   // X may be replaced
-                            }
-                            __syncwarp();
-                            if (++stage == P.ring) { stage = 0; phase ^= 1u; }
                         }
                     }
                 }
             }
         }
-    } else {
+        __syncwarp();
+    } else if (warp == 1 || warp == 2) {
+        // ---- MMA issuers: warp 1 owns accumulator stage 0 (even chunks of a chain), warp 2 stage 1 (odd chunks); in each ONE elected
+        // thread runs the whole loop.  Two issuers because a single thread cannot get the ~60 instructions of a 16 KB weight block
+        // (8 small MMAs + barrier traffic) out in the 384 cycles the tensor pipe needs for it.  Ordering between the two is carried
+        // by the data: a chunk of layer j is issued only after every 64-column slice of its A operand has been published (opReady),
+        // i.e. after all MMAs of layer j - 1 -- from both issuers -- have completed and been read by the epilogue.
+        if (elect_one()) {
+            const int g = warp - 1;
+            constexpr uint32_t idescWide = idesc_f16(128, 128), idescNarrow = idesc_f16(128, 64);
+            const uint32_t descHi = (uint32_t)(make_desc(0) >> 32);
+            auto desc_lo = [](uint32_t addr) { return ((addr >> 4) & 0x3fffu) | (1u << 16); };   // start address | LBO = 1
+            constexpr uint32_t kTile16 = kTile >> 4;
+            const int half = P.ring >> 1, s0 = g * half;   // this issuer's half of the weight ring
+            const uint32_t ringLo = desc_lo(ring) + s0 * kTile16, xLo = desc_lo(xbuf), sLo = desc_lo(sbuf);
+            const uint32_t d = tmemBase + g * kAccCols;
+            const uint32_t accFullBar = accFull(g), accEmptyBar = accEmpty(g);
+            int stage = 0;
+            uint32_t phase = 0, accPhase = 0, opBits = 0, xPhase = 0;
+            for (int t = blockIdx.x; t < P.numTiles; t += gridDim.x) {
+                const int si = species_of(t);
+                const ChainSpecies& sp = P.sp[si];
+                mbar_wait(xFull, xPhase);
+                xPhase ^= 1u;
+                tc_fence_after();
+                for (int e = 0; e < P.M; e++) {
+                    int chunkIdx = 0;
+                    for (int j = 0; j < 6; j++) {
+                        int N, K;
+                        layer_dims(sp, j, N, K);
+                        const int cn = chunks_of(N), ck = chunks_of(K);
+                        const int lastSteps = (K - (ck - 1) * 64) >> 4;
+                        const bool aTmem = (j & 1) != 0;                 // F2, G3, G1 read their A operand from tensor memory
+                        // A operand: address of k-chunk 0 (TMEM column, or descriptor low word), stride per k-chunk, offset of the lo part
+                        const uint32_t aBase = aTmem ? tmemBase + kOpaHi : (j == 0 ? xLo : sLo);
+                        const uint32_t aChunk = aTmem ? 32u : kTile16;
+                        const uint32_t aLoOff = aTmem ? (kOpaLo - kOpaHi) : (uint32_t)(j == 0 ? P.xChunks : P.sChunks) * kTile16;
+                        bool needOp = j > 0;   // the A operand of this layer has not been waited for yet (by this issuer)
+                        bool chainCommitted = false;
+                        for (int c = 0; c < cn; c++) {
+                            const int acc = chunkIdx & 1;
+                            chunkIdx++;
+                            if (acc != g) continue;   // the other issuer's chunk
+                            mbar_wait(accEmptyBar, accPhase ^ 1u);
+                            accPhase ^= 1u;
+                            tc_fence_after();
+                            for (int kc = 0; kc < ck; kc++) {
+                                if (needOp) {   // columns [64 kc, 64 kc + 64) of the A operand come from the previous layer's epilogue
+                                    mbar_wait(opReady(kc), (opBits >> kc) & 1u);
+                                    opBits ^= 1u << kc;
+                                }
+                                mbar_wait(bFull(s0 + stage), phase);
+                                tc_fence_after();
+                                const uint32_t bLo = ringLo + stage * kTile16;
+                                const uint32_t a = aBase + kc * aChunk;
+                                const int steps = kc == ck - 1 ? lastSteps : 4;
+                                if (aTmem) {
+#pragma unroll
+                                    for (int k = 0; k < 4; k++)
+                                        if (k < steps) {
+                                            umma_ts_lo(d, a + 8 * k, bLo + 2 * k, descHi, idescWide, (kc | k) != 0 ? 1u : 0u);
+                                            umma_ts_lo(d + 64, a + aLoOff + 8 * k, bLo + 2 * k, descHi, idescNarrow, 1u);
+                                        }
+                                } else {
+#pragma unroll
+                                    for (int k = 0; k < 4; k++)
+                                        if (k < steps) {
+                                            umma_ss_lo(d, a + 2 * k, bLo + 2 * k, descHi, idescWide, (kc | k) != 0 ? 1u : 0u);
+                                            umma_ss_lo(d + 64, a + aLoOff + 2 * k, bLo + 2 * k, descHi, idescNarrow, 1u);
+                                        }
+                                }
+                                umma_commit(bEmpty(s0 + stage));
+                                if (kc == ck - 1) {
+                                    umma_commit(accFullBar);
+                                    // G1 reads dZ0 from the TMEM operand columns the next chain's first epilogue overwrites: that epilogue waits
+                                    // until the last G1 chunk of BOTH issuers has completed
+                                    if (j == 5 && c >= cn - 2) { umma_commit(chainDone); chainCommitted = true; }
+                                }
+                                if (++stage == half) { stage = 0; phase ^= 1u; }
+                            }
+                            if (needOp) {
+                                needOp = false;
+                                // every slice of this layer's A operand is published, so all MMAs of the previous layer are complete: when
+                                // that layer was the last F1 of the tile, X may be replaced
+                                if (j == 1 && e == P.M - 1) mbar_arrive(xEmpty);
+                            }
+                        }
+                        if (needOp) {   // no chunk of this layer was ours: keep the barrier phases in step (xEmpty counts both issuers)
+                            opBits ^= (1u << ck) - 1u;
+                            if (j == 1 && e == P.M - 1) mbar_arrive(xEmpty);
+                        }
+                        if (j == 5 && !chainCommitted) mbar_arrive(chainDone);   // G1 had a single chunk and it was the other issuer's
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= kFirstEpiWarp) {
         // ---- epilogue groups ----
         const int ew = warp - kFirstEpiWarp, g = ew >> 3, q = warp & 3, hsel = (ew >> 2) & 1;
         const int r = q * 32 + lane;
@@ -365,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
         x.r7 = r & 7;
         x.hsel = hsel;
         float* const stash = P.stash + (size_t)blockIdx.x * (kStashCols * kRows) + r;
-        uint32_t fullPhase = 0;
+        uint32_t fullPhase = 0, chainPhase = 0;
         for (int t = blockIdx.x; t < P.numTiles; t += gridDim.x) {
             const int si = species_of(t);
             const ChainSpecies& sp = P.sp[si];
@@ -373,19 +439,23 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
             x.rowOk = row0 + r < sp.rows;
             float* const dxRow = P.dX + (size_t)(sp.rowStart + row0 + r) * P.ldx;
             float esum = 0.0f;
+            const unsigned char* const tab = chunkTab + si * 32;
+            const int nChunks = tab[31];
             for (int e = 0; e < P.M; e++) {
-                int chunkIdx = 0;
-                for (int j = 0; j < 6; j++) {
+                bool chainWaited = false;
+                for (int ci = g; ci < nChunks; ci += 2) {          // chunks alternate between the two accumulator stages / groups
+                    const int j = tab[ci] >> 3, c = tab[ci] & 7;
                     int N, K;
                     layer_dims(sp, j, N, K);
-                    const int cn = chunks_of(N);
-                    for (int c = 0; c < cn; c++) {
-                        const int acc = chunkIdx & 1;
-                        chunkIdx++;
-                        if (acc != g) continue;
+                    {
                         x.c = c;
                         x.n0 = c * 64 + hsel * 32;
                         const bool valid = x.n0 < N;             // warp-uniform: widths are multiples of 32
+                        if (!chainWaited) {   // the previous chain's G1 (both issuers) must be done with the TMEM operand before F1 rewrites it
+                            mbar_wait(chainDone, chainPhase ^ 1u);
+                            chainPhase ^= 1u;
+                            chainWaited = true;
+                        }
                         if (valid) {
                             switch (j) {
                                 case 0: epi_chunk<0>(P, x, sp.bias[0] + (size_t)e * N, nullptr, stash, dxRow, false, accFull(g), fullPhase, accEmpty(g), lane, esum); break;
@@ -465,7 +535,7 @@ bool MlpChain::eligible(int numSpecies, const SpeciesDesc* sp, int featureStride
         sMax = std::max(sMax, chunks_of(d[2]));
     }
     const uint32_t fixed = 2u * (chunks_of(featureStride) + sMax) * kTile + 1024 + 512;
-    return fixed + 3 * kTile <= kMaxSmem;
+    return fixed + 4 * kTile <= kMaxSmem;
 }
 
 MlpChain::MlpChain(int ensemble, int numSpecies, const SpeciesDesc* sp, const __half* featHi, const __half* featLo, int featureStride)
@@ -508,12 +578,13 @@ MlpChain::MlpChain(int ensemble, int numSpecies, const SpeciesDesc* sp, const __
     }
     P.numTiles = tiles;
     const uint32_t fixed = 2u * (P.xChunks + P.sChunks) * kTile + 1024 + 512;
-    P.ring = (int)std::min<uint32_t>(kMaxRing, (kMaxSmem - fixed) / kTile);
+    P.ring = (int)std::min<uint32_t>(kMaxRing, (kMaxSmem - fixed) / kTile) & ~1;   // an even number of slots: one half per MMA issuer
     impl_->smem = fixed + P.ring * kTile;
     int dev = 0, sms = 0;
     NNP_CUDA_CHECK(cudaGetDevice(&dev));
     NNP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     impl_->grid = std::max(1, std::min(tiles, sms));
+    if (const char* e = std::getenv("NNPOPS_CHAIN_GRID")) impl_->grid = std::max(1, std::min(impl_->grid, std::atoi(e)));   // development: force several tiles per CTA
     NNP_CUDA_CHECK(cudaMalloc(&impl_->stash, sizeof(float) * (size_t)impl_->grid * kStashCols * kRows));
     P.stash = impl_->stash;
 }

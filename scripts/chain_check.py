@@ -41,7 +41,7 @@ def main():
             e, g = m.energy_and_gradient(p, box)
             torch.cuda.synchronize()
             out[chain] = (float(e.cpu()[0]), g.cpu().numpy().astype(np.float64), m.feature_grad().cpu().numpy().astype(np.float64))
-            if n >= 20000:
+            if n >= int(os.environ.get('CHAIN_TIMING_MIN', '20000')):
                 for _ in range(3):
                     m.energy_and_gradient(p, box)
                 torch.cuda.synchronize()
