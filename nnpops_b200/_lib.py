@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnnpops_b200.so")
+LIB_PATH = os.environ.get("NNPOPS_LIB_PATH") or os.path.join(_HERE, "libnnpops_b200.so")   # the override is a development aid (A/B builds)
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
