@@ -50,6 +50,10 @@ NNPOPS_API int nnpops_ani_forward(nnpops_ani_t h, const float* positions, const 
 NNPOPS_API int nnpops_ani_backward(nnpops_ani_t h, const float* radial_grad, const float* angular_grad, float* position_grad, void* stream);
 /* synchronises the device; *flags != 0 when a neighbour row overflowed (bit 0 radial, bit 1 angular) */
 NNPOPS_API int nnpops_ani_overflowed(nnpops_ani_t h, int* flags);
+/* never blocks: the same flags as of the last forward whose device work has completed, plus the row capacities in use (any
+ * pointer may be NULL).  The reference has no neighbour limit (N x N table, CudaANISymmetryFunctions.cu:44); callers that cannot
+ * synchronise (graph replay) use this to report a truncated row on their next call. */
+NNPOPS_API int nnpops_ani_overflow_poll(nnpops_ani_t h, int* flags, int* max_radial_neighbors, int* max_angular_neighbors);
 /* synchronises; work counters of the last forward: triples = sum_i n_i(n_i-1)/2, pairs = undirected pairs within the radial cutoff */
 NNPOPS_API int nnpops_ani_work(nnpops_ani_t h, long long* triples, long long* radial_pairs, void* stream);
 
@@ -98,6 +102,7 @@ NNPOPS_API int nnpops_ani_model_work(nnpops_ani_model_t h, long long* triples, l
  * aev_length = full length, active_features = columns kept, mlp_flops_forward_executed = flops actually issued per forward. */
 NNPOPS_API int nnpops_ani_model_info(nnpops_ani_model_t h, int* aev_length, int* active_features, double* mlp_flops_forward_executed);
 NNPOPS_API int nnpops_ani_model_overflowed(nnpops_ani_model_t h, int* flags);
+NNPOPS_API int nnpops_ani_model_overflow_poll(nnpops_ani_model_t h, int* flags, int* max_radial_neighbors, int* max_angular_neighbors);
 /* CUDA-event timing of the pipeline stages on the launching stream, for benchmarks: after timing_begin the next max_steps
  * evaluations record events; timing_end synchronises and returns the summed milliseconds of the 7 stages
  * {cell list + neighbour rows, radial fwd, angular fwd, MLP fwd, MLP bwd, radial bwd, angular bwd} and the evaluations seen */

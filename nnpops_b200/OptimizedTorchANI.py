@@ -102,6 +102,7 @@ class FusedANI(torch.nn.Module):
             raise RuntimeError('"positions" has to be a float32 tensor of shape (%d, 3)' % self.num_atoms)
         if positions.device.type != "cuda":
             raise RuntimeError("nnpops_b200 runs on CUDA devices only (no CPU fallback)")
+        self._raise_if_overflowed()
         pos = positions.detach().contiguous()
         box = None
         if cell is not None:
@@ -113,6 +114,15 @@ class FusedANI(torch.nn.Module):
         with torch.cuda.device(pos.device):
             check(lib.nnpops_ani_model_energy_grad(self._h, ptr(pos), ptr(box), ptr(energy), ptr(grad), current_stream(pos.device)))
         return energy, grad
+
+    def _raise_if_overflowed(self):
+        """Never blocks: a neighbour row that overflowed in an EARLIER evaluation is reported now (the reference has no neighbour
+        limit; this path must stay asynchronous, so it cannot check the evaluation it is about to launch)."""
+        f, r, a = C.c_int(0), C.c_int(0), C.c_int(0)
+        check(lib.nnpops_ani_model_overflow_poll(self._h, C.byref(f), C.byref(r), C.byref(a)))
+        if f.value:
+            raise RuntimeError("nnpops_b200: a neighbour row overflowed in an earlier evaluation (capacities %d radial / %d angular): "
+                               "results since then are wrong. Pass larger max_radial_neighbors / max_angular_neighbors." % (r.value, a.value))
 
     def energy_and_gradient(self, positions: Tensor, cell: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
         """(energy [1], dE/dx [N, 3]) without autograd bookkeeping."""
@@ -197,6 +207,15 @@ class ShardedFusedANI(torch.nn.Module):
         self.local = (local_factory(self.rank, self.world) if local_factory is not None
                       else FusedANI(*args, shard=(self.rank, self.world), **kwargs))
         self._packed = None
+
+    def _raise_if_overflowed(self):
+        """Never blocks: a neighbour row that overflowed in an EARLIER evaluation is reported now (the reference has no neighbour
+        limit; this path must stay asynchronous, so it cannot check the evaluation it is about to launch)."""
+        f, r, a = C.c_int(0), C.c_int(0), C.c_int(0)
+        check(lib.nnpops_ani_model_overflow_poll(self._h, C.byref(f), C.byref(r), C.byref(a)))
+        if f.value:
+            raise RuntimeError("nnpops_b200: a neighbour row overflowed in an earlier evaluation (capacities %d radial / %d angular): "
+                               "results since then are wrong. Pass larger max_radial_neighbors / max_angular_neighbors." % (r.value, a.value))
 
     def energy_and_gradient(self, positions: Tensor, cell: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
         e, g = self.local.energy_and_gradient(positions, cell)

@@ -108,8 +108,29 @@ class Holder:
         box = cell.detach().contiguous() if cell is not None else None
         radial = torch.empty((self.numAtoms, self.radial_width), dtype=torch.float32, device=pos.device)
         angular = torch.empty((self.numAtoms, self.angular_width), dtype=torch.float32, device=pos.device)
+        # The reference has no neighbour limit (N x N table, CudaANISymmetryFunctions.cu:44); here rows have a capacity.  An overflow is
+        # detected right after the call and the call repeated with rows twice as long, so a result is never silently truncated.
+        # Nothing may synchronise while a CUDA graph is being captured: there the check is left to the next eager call.
+        capturing = torch.cuda.is_current_stream_capturing()
         with torch.cuda.device(pos.device):
-            check(lib.nnpops_ani_forward(self._h, ptr(pos), ptr(box), ptr(radial), ptr(angular), current_stream(pos.device)))
+            for attempt in range(9):
+                check(lib.nnpops_ani_forward(self._h, ptr(pos), ptr(box), ptr(radial), ptr(angular), current_stream(pos.device)))
+                if capturing:
+                    break
+                flags = self.overflowed()          # synchronises, like the reference's host read of the box
+                if not flags:
+                    break
+                if attempt == 8:
+                    raise RuntimeError("nnpops_b200: neighbour rows still overflow after growing them 8 times")
+                caps = list(self.caps)
+                if flags & 1:
+                    caps[0] = 2 * (caps[0] or 256)
+                if flags & 2:
+                    caps[1] = 2 * (caps[1] or 64)
+                self.caps = tuple(caps)
+                lib.nnpops_ani_destroy(self._h)
+                self._h = None
+                self._create(pos.device)
         return [radial, angular]
 
     def backward(self, grads: List[Tensor]) -> Tensor:

@@ -23,6 +23,7 @@ _SIGS = {
     "nnpops_ani_forward": [_vp, _vp, _vp, _vp, _vp, _vp],
     "nnpops_ani_backward": [_vp, _vp, _vp, _vp, _vp],
     "nnpops_ani_overflowed": [_vp, C.POINTER(_i)],
+    "nnpops_ani_overflow_poll": [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)],
     "nnpops_ani_work": [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _vp],
     "nnpops_ani_model_create": [C.POINTER(_vp), _i, _i, _f, _f, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _i],
     "nnpops_ani_model_create_sharded": [C.POINTER(_vp), _i, _i, _f, _f, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i],
@@ -33,6 +34,7 @@ _SIGS = {
     "nnpops_ani_model_work": [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_double), _vp],
     "nnpops_ani_model_info": [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(C.c_double)],
     "nnpops_ani_model_overflowed": [_vp, C.POINTER(_i)],
+    "nnpops_ani_model_overflow_poll": [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)],
     "nnpops_ani_model_timing_begin": [_vp, _i],
     "nnpops_ani_model_timing_end": [_vp, _vp, C.POINTER(_i)],
     "nnpops_launch_count": [C.POINTER(C.c_ulonglong)],

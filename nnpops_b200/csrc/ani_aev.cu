@@ -1130,6 +1130,8 @@ AniAev::AniAev(int numAtoms, int numSpecies, float rcr, float rca, const int* at
     NNP_CUDA_CHECK(cudaMalloc(&offAng_, sizeof(int) * na * (numSpecies + 1)));
     NNP_CUDA_CHECK(cudaMalloc(&flag_, sizeof(int)));
     NNP_CUDA_CHECK(cudaMemset(flag_, 0, sizeof(int)));
+    NNP_CUDA_CHECK(cudaMallocHost(&flagHost_, sizeof(int)));
+    *flagHost_ = 0;
     NNP_CUDA_CHECK(cudaMalloc(&counters_, 2 * sizeof(unsigned long long)));
     NNP_CUDA_CHECK(cudaStreamCreateWithFlags(&aux_, cudaStreamNonBlocking));
     NNP_CUDA_CHECK(cudaEventCreateWithFlags(&evFork_, cudaEventDisableTiming));
@@ -1139,6 +1141,7 @@ AniAev::AniAev(int numAtoms, int numSpecies, float rcr, float rca, const int* at
 AniAev::~AniAev() {
     cudaFree(tab_); cudaFree(species_); cudaFree(rowRad_); cudaFree(rowAng_); cudaFree(offRad_); cudaFree(offAng_);
     cudaFree(flag_); cudaFree(counters_);
+    if (flagHost_) cudaFreeHost(flagHost_);
     if (aux_) cudaStreamDestroy(aux_);
     if (evFork_) cudaEventDestroy(evFork_);
     if (evJoin_) cudaEventDestroy(evJoin_);
@@ -1184,6 +1187,9 @@ void AniAev::forward(const float* positions, const float* box, float* radial, in
         NNP_CUDA_CHECK(cudaEventRecord(evFork_, stream));
         NNP_CUDA_CHECK(cudaStreamWaitEvent(aux_, evFork_, 0));
     }
+    // 4 bytes to pinned memory behind the row kernel (on the side stream when there is one, off the critical path): overflowPoll()
+    // then sees a truncated row without anybody blocking
+    NNP_CUDA_CHECK(cudaMemcpyAsync(flagHost_, flag_, sizeof(int), cudaMemcpyDeviceToHost, rs));
     if (tabHost_.nRadial > 0) {
         const size_t smem = (size_t)kWPB * 2 * capR_ * sizeof(float);
         set_smem(ani_radial_fwd_kernel, smem);

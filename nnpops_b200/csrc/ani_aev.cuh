@@ -60,6 +60,12 @@ public:
                   cudaStream_t stream, cudaEvent_t* ev = nullptr);
     // synchronises; returns nonzero when a neighbour row overflowed its capacity during any call so far
     int overflowed();
+    // does not synchronise: the flag as of the last forward whose device work has completed (every forward copies it to pinned host
+    // memory behind the row kernel).  Lets callers that must not block -- CUDA-graph replay, the fused model -- report an overflow
+    // on their next call instead of never.
+    int overflowPoll() const { return flagHost_ ? *(volatile int*)flagHost_ : 0; }
+    int maxRadialNeighbors() const { return capR_; }
+    int maxAngularNeighbors() const { return capA_; }
 
     int numAtoms() const { return n_; }
     int numSpecies() const { return tabHost_.nSpecies; }
@@ -80,6 +86,7 @@ private:
     int* offRad_ = nullptr;      // [n][S+1]
     int* offAng_ = nullptr;      // [n][S+1]
     int* flag_ = nullptr;        // overflow flag
+    int* flagHost_ = nullptr;    // pinned host mirror of the flag
     unsigned long long* counters_ = nullptr;   // [2] scratch for countTriples / countRadialPairs
     const int* rowMap_ = nullptr;
     const unsigned char* owned_ = nullptr;

@@ -139,6 +139,15 @@ int nnpops_ani_overflowed(nnpops_ani_t h, int* flags) {
     });
 }
 
+int nnpops_ani_overflow_poll(nnpops_ani_t h, int* flags, int* max_radial_neighbors, int* max_angular_neighbors) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl, "invalid handle");
+        if (flags) *flags = h->impl->overflowPoll();
+        if (max_radial_neighbors) *max_radial_neighbors = h->impl->maxRadialNeighbors();
+        if (max_angular_neighbors) *max_angular_neighbors = h->impl->maxAngularNeighbors();
+    });
+}
+
 int nnpops_ani_work(nnpops_ani_t h, long long* triples, long long* radial_pairs, void* stream) {
     return guarded([&] {
         NNP_REQUIRE(h && h->impl, "invalid handle");
@@ -275,6 +284,15 @@ int nnpops_ani_model_info(nnpops_ani_model_t h, int* aev_length, int* active_fea
         if (aev_length) *aev_length = h->impl->aevLength();
         if (active_features) *active_features = h->impl->activeFeatures();
         if (mlp_flops_forward_executed) *mlp_flops_forward_executed = h->impl->mlp().flopsForward();
+    });
+}
+
+int nnpops_ani_model_overflow_poll(nnpops_ani_model_t h, int* flags, int* max_radial_neighbors, int* max_angular_neighbors) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl, "invalid handle");
+        if (flags) *flags = h->impl->aev().overflowPoll();
+        if (max_radial_neighbors) *max_radial_neighbors = h->impl->aev().maxRadialNeighbors();
+        if (max_angular_neighbors) *max_angular_neighbors = h->impl->aev().maxAngularNeighbors();
     });
 }
 

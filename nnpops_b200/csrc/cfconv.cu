@@ -351,6 +351,9 @@ public:
         NNP_CUDA_CHECK(cudaMalloc(&tabD_, sizeof(float) * (size_t)P_ * W_));
         const size_t smem = sizeof(double) * (2 * (size_t)G_ + 2 * (size_t)W_);
         NNP_REQUIRE(smem <= 48 * 1024, "width/numGaussians too large for the filter-table kernel");
+        // one-time set-up on the legacy default stream: the weights may have been staged on a non-blocking stream of the caller, which
+        // the default stream does not order against, so wait for the whole device first
+        NNP_CUDA_CHECK(cudaDeviceSynchronize());
         cf_table_kernel<<<P_, 128, smem>>>(P_, W_, G_, (double)cutoff, (double)gaussianWidth, activation, w1, b1, w2, b2, h, tabF_, tabD_);
         NNP_CUDA_CHECK(cudaGetLastError());
         NNP_CUDA_CHECK(cudaDeviceSynchronize());

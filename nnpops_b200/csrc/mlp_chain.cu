@@ -409,8 +409,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
                                 if (j == 1 && e == P.M - 1) mbar_arrive(xEmpty);
                             }
                         }
-                        if (needOp) {   // no chunk of this layer was ours: keep the barrier phases in step (xEmpty counts both issuers)
-                            opBits ^= (1u << ck) - 1u;
+                        if (needOp) {
+                            // no chunk of this layer was ours.  The operand barriers must still be OBSERVED phase by phase: a wait only
+                            // knows the parity of a phase, so an issuer that skipped one would take "two phases back" for "done" at its
+                            // next real wait and run ahead of the epilogue.  (xEmpty counts both issuers.)
+                            for (int kc = 0; kc < ck; kc++) {
+                                mbar_wait(opReady(kc), (opBits >> kc) & 1u);
+                                opBits ^= 1u << kc;
+                            }
                             if (j == 1 && e == P.M - 1) mbar_arrive(xEmpty);
                         }
                         if (j == 5 && !chainCommitted) mbar_arrive(chainDone);   // G1 had a single chunk and it was the other issuer's

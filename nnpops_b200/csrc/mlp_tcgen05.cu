@@ -23,6 +23,7 @@
 #include <tuple>
 #include "species_mlp.cuh"
 #include "tcgen05_util.cuh"
+#include "workspace_cache.cuh"
 
 namespace nnpops {
 
@@ -509,15 +510,7 @@ namespace {
 
 bool g_forceStreaming = std::getenv("NNPOPS_GEMM_STREAMING") != nullptr;   // A/B switch for measurements
 
-int num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        NNP_CUDA_CHECK(cudaGetDevice(&dev));
-        NNP_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    }
-    return n;
-}
+int num_sms() { return current_sm_count(); }
 
 }  // namespace
 
@@ -529,7 +522,11 @@ void launch_gemm_tcgen05(const GemmArgsH& a, cudaStream_t stream) {
     NNP_REQUIRE(a.N % 32 == 0, "tcgen05 GEMM: N must be a multiple of 32");
     NNP_REQUIRE(a.ldc % 8 == 0 && a.cBatchCols % 8 == 0 && a.ldact % 8 == 0 && a.actBatchCols % 8 == 0,
                 "tcgen05 GEMM: output leading dimensions must be multiples of 8");
-    static bool attrSet = false;
+    // the attribute belongs to the (function, device) pair: a process may build models on several GPUs
+    static bool attrSetOn[64] = {false};
+    int dev = 0;
+    NNP_CUDA_CHECK(cudaGetDevice(&dev));
+    bool& attrSet = attrSetOn[dev & 63];
     if (!attrSet) {
         NNP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_of(0)));
         NNP_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_of(1)));

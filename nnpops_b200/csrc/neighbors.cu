@@ -14,6 +14,7 @@
 #include <map>
 #include <mutex>
 #include "cell_list.cuh"
+#include "workspace_cache.cuh"
 
 namespace nnpops {
 
@@ -230,38 +231,31 @@ __global__ void pairs_backward_kernel(long long numPairs, const int* __restrict_
     }
 }
 
-struct Workspace {
+struct Workspace : WorkspaceBase {
     CellList cells;
     int* counts = nullptr;
     long long* offsets = nullptr;
     unsigned long long* found = nullptr;
+    ~Workspace() override {
+        cells.release();
+        cudaFree(counts); cudaFree(offsets); cudaFree(found);
+    }
 };
 
-std::mutex g_wsMutex;
-std::map<std::pair<int, int>, Workspace*> g_ws;   // (device, numAtoms) -> workspace; allocated outside CUDA-graph capture
+// (device, numAtoms, stream) -> workspace (workspace_cache.cuh: stream-keyed, graph-pinned, LRU)
+WorkspaceCache<Workspace, std::pair<int, int>> g_ws(32);
 
-Workspace& workspace(int n) {
+std::shared_ptr<Workspace> workspace(int n, cudaStream_t stream) {
     int dev = 0;
     NNP_CUDA_CHECK(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lock(g_wsMutex);
-    auto key = std::make_pair(dev, n);
-    auto it = g_ws.find(key);
-    if (it != g_ws.end()) return *it->second;
-    if (g_ws.size() >= 16) {   // keep the cache bounded
-        for (auto& kv : g_ws) {
-            kv.second->cells.release();
-            cudaFree(kv.second->counts); cudaFree(kv.second->offsets); cudaFree(kv.second->found);
-            delete kv.second;
-        }
-        g_ws.clear();
-    }
-    Workspace* ws = new Workspace;
-    ws->cells.init(n);
-    NNP_CUDA_CHECK(cudaMalloc(&ws->counts, sizeof(int) * (size_t)(n > 0 ? n : 1)));
-    NNP_CUDA_CHECK(cudaMalloc(&ws->offsets, sizeof(long long) * (size_t)(n > 0 ? n : 1)));
-    NNP_CUDA_CHECK(cudaMalloc(&ws->found, sizeof(unsigned long long)));
-    g_ws[key] = ws;
-    return *ws;
+    return g_ws.get(std::make_pair(dev, n), stream, [n]() {
+        Workspace* ws = new Workspace;
+        ws->cells.init(n);
+        NNP_CUDA_CHECK(cudaMalloc(&ws->counts, sizeof(int) * (size_t)(n > 0 ? n : 1)));
+        NNP_CUDA_CHECK(cudaMalloc(&ws->offsets, sizeof(long long) * (size_t)(n > 0 ? n : 1)));
+        NNP_CUDA_CHECK(cudaMalloc(&ws->found, sizeof(unsigned long long)));
+        return ws;
+    });
 }
 
 }  // namespace
@@ -273,12 +267,13 @@ void neighbor_pairs(const T* positions, const T* box, int n, T cutoff, long long
     NNP_REQUIRE(n > 0, "Expected the 1nd dimension size of \"positions\" to be more than 0");
     NNP_REQUIRE(cutoff > 0, "Expected \"cutoff\" to be positive");
     NNP_REQUIRE(maxNumPairs > 0 || maxNumPairs == -1, "Expected \"max_num_pairs\" to be positive or equal to -1");
-    Workspace& ws = workspace(n);
+    const std::shared_ptr<Workspace> wsHold = workspace(n, stream);
+    Workspace& ws = *wsHold;
     ws.cells.build<T>(positions, box, nullptr, (float)cutoff * 1.0001f + 1e-30f, stream);
     const int grid = (n + kWPB - 1) / kWPB;
     const bool allPairs = maxNumPairs == -1;
     const long long capacity = allPairs ? (long long)n * (n - 1) / 2 : maxNumPairs;
-    const int padGrid = (int)std::min<long long>((capacity + 255) / 256, 148LL * 16);
+    const int padGrid = (int)std::min<long long>((capacity + 255) / 256, (long long)current_sm_count() * 16);
     if (allPairs) {
         NNP_CUDA_CHECK(cudaMemsetAsync(ws.found, 0, sizeof(unsigned long long), stream));
         if (capacity > 0) pad_kernel<T><<<padGrid, 256, 0, stream>>>(capacity, ws.found, false, neighbors, deltas, distances);

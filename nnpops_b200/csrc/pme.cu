@@ -4,7 +4,9 @@
 // The FFTs are cuFFT plans cached per grid shape (the reference calls cuFFT through torch::fft::rfftn/irfftn, pmeCUDA.cu:354,395).
 #include <cufft.h>
 #include <map>
+#include <memory>
 #include <mutex>
+#include "workspace_cache.cuh"
 #include <tuple>
 #include "common.cuh"
 
@@ -273,61 +275,64 @@ pme_interpolate_kernel(int numAtoms, const float* __restrict__ pos, const float*
     }
 }
 
-struct PmeWorkspace {
-    int gx, gy, gz;
-    float* realGrid = nullptr;
-    float2* scratch = nullptr;     // copy of the half-complex grid for the C2R transform (cuFFT may overwrite its input)
-    double* energyAcc = nullptr;
-    cufftHandle r2c = 0, c2r = 0;
-};
-
-std::mutex g_pmeMutex;
-std::map<std::tuple<int, int, int, int>, PmeWorkspace*> g_pmeWs;
-double* g_directAcc[64] = {nullptr};
-
 #define NNP_CUFFT_CHECK(expr)                                                                                 \
     do {                                                                                                      \
         cufftResult r__ = (expr);                                                                             \
         if (r__ != CUFFT_SUCCESS) throw std::runtime_error("cuFFT error " + std::to_string((int)r__) + " at " __FILE__ ":" + std::to_string(__LINE__)); \
     } while (0)
 
-PmeWorkspace& pme_workspace(int gx, int gy, int gz) {
-    int dev = 0;
-    NNP_CUDA_CHECK(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lock(g_pmeMutex);
-    auto key = std::make_tuple(dev, gx, gy, gz);
-    auto it = g_pmeWs.find(key);
-    if (it != g_pmeWs.end()) return *it->second;
-    PmeWorkspace* ws = new PmeWorkspace;
-    ws->gx = gx; ws->gy = gy; ws->gz = gz;
-    const size_t nReal = (size_t)gx * gy * gz, nCplx = (size_t)gx * gy * (gz / 2 + 1);
-    NNP_CUDA_CHECK(cudaMalloc(&ws->realGrid, sizeof(float) * nReal));
-    NNP_CUDA_CHECK(cudaMalloc(&ws->scratch, sizeof(float2) * nCplx));
-    NNP_CUDA_CHECK(cudaMalloc(&ws->energyAcc, sizeof(double)));
-    NNP_CUFFT_CHECK(cufftPlan3d(&ws->r2c, gx, gy, gz, CUFFT_R2C));
-    NNP_CUFFT_CHECK(cufftPlan3d(&ws->c2r, gx, gy, gz, CUFFT_C2R));
-    g_pmeWs[key] = ws;
-    return *ws;
-}
-
-double* direct_acc() {
-    int dev = 0;
-    NNP_CUDA_CHECK(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lock(g_pmeMutex);
-    NNP_REQUIRE(dev < 64, "device index out of range");
-    if (!g_directAcc[dev]) NNP_CUDA_CHECK(cudaMalloc(&g_directAcc[dev], sizeof(double)));
-    return g_directAcc[dev];
-}
-
-int sm_count() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+// scratch of the reciprocal part, one per (device, grid, stream): the cuFFT plans are bound to the stream once, at creation
+struct PmeWorkspace : WorkspaceBase {
+    int gx, gy, gz;
+    float* realGrid = nullptr;
+    float2* scratch = nullptr;     // copy of the half-complex grid for the C2R transform (cuFFT may overwrite its input)
+    double* energyAcc = nullptr;
+    cufftHandle r2c = 0, c2r = 0;
+    cudaStream_t r2cStream = nullptr, c2rStream = nullptr;   // the stream each plan is currently bound to
+    ~PmeWorkspace() override {
+        cudaFree(realGrid); cudaFree(scratch); cudaFree(energyAcc);
+        if (r2c) cufftDestroy(r2c);
+        if (c2r) cufftDestroy(c2r);
     }
-    return n;
+};
+struct DirectWorkspace : WorkspaceBase {
+    double* acc = nullptr;
+    ~DirectWorkspace() override { cudaFree(acc); }
+};
+
+WorkspaceCache<PmeWorkspace, std::tuple<int, int, int, int>> g_pmeWs(16);
+WorkspaceCache<DirectWorkspace, int> g_directWs(64);
+
+std::shared_ptr<PmeWorkspace> pme_workspace(int gx, int gy, int gz, cudaStream_t stream) {
+    int dev = 0;
+    NNP_CUDA_CHECK(cudaGetDevice(&dev));
+    return g_pmeWs.get(std::make_tuple(dev, gx, gy, gz), stream, [=]() {
+        std::unique_ptr<PmeWorkspace> ws(new PmeWorkspace);
+        ws->gx = gx; ws->gy = gy; ws->gz = gz;
+        const size_t nReal = (size_t)gx * gy * gz, nCplx = (size_t)gx * gy * (gz / 2 + 1);
+        NNP_CUDA_CHECK(cudaMalloc(&ws->realGrid, sizeof(float) * nReal));
+        NNP_CUDA_CHECK(cudaMalloc(&ws->scratch, sizeof(float2) * nCplx));
+        NNP_CUDA_CHECK(cudaMalloc(&ws->energyAcc, sizeof(double)));
+        NNP_CUFFT_CHECK(cufftPlan3d(&ws->r2c, gx, gy, gz, CUFFT_R2C));
+        NNP_CUFFT_CHECK(cufftPlan3d(&ws->c2r, gx, gy, gz, CUFFT_C2R));
+        NNP_CUFFT_CHECK(cufftSetStream(ws->r2c, stream));
+        NNP_CUFFT_CHECK(cufftSetStream(ws->c2r, stream));
+        ws->r2cStream = ws->c2rStream = stream;
+        return ws.release();
+    });
 }
+
+std::shared_ptr<DirectWorkspace> direct_workspace(cudaStream_t stream) {
+    int dev = 0;
+    NNP_CUDA_CHECK(cudaGetDevice(&dev));
+    return g_directWs.get(dev, stream, []() {
+        std::unique_ptr<DirectWorkspace> ws(new DirectWorkspace);
+        NNP_CUDA_CHECK(cudaMalloc(&ws->acc, sizeof(double)));
+        return ws.release();
+    });
+}
+
+int sm_count() { return current_sm_count(); }
 
 }  // namespace
 
@@ -335,7 +340,8 @@ int sm_count() {
 void pme_direct(const float* positions, const float* charges, const int* neighbors, const float* deltas, const float* distances,
                 const int* exclusions, int numAtoms, long long numPairs, int maxExcl, float alpha, float coulomb, float* energy,
                 float* posDeriv, float* chargeDeriv, cudaStream_t stream) {
-    double* acc = direct_acc();
+    const std::shared_ptr<DirectWorkspace> accHold = direct_workspace(stream);
+    double* acc = accHold->acc;
     NNP_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double), stream));
     NNP_CUDA_CHECK(cudaMemsetAsync(posDeriv, 0, sizeof(float) * 3 * (size_t)numAtoms, stream));
     NNP_CUDA_CHECK(cudaMemsetAsync(chargeDeriv, 0, sizeof(float) * (size_t)numAtoms, stream));
@@ -381,9 +387,13 @@ void pme_spread(const float* positions, const float* charges, const float* box, 
 void pme_solve(float* realGrid, const float* box, int gx, int gy, int gz, float alpha, const float* xmod, const float* ymod,
                const float* zmod, float* energy, float* recipGrid, cudaStream_t stream) {
     NNP_REQUIRE(gx > 0 && gy > 0 && gz > 0, "The grid dimensions must be positive");
-    PmeWorkspace& ws = pme_workspace(gx, gy, gz);
+    const std::shared_ptr<PmeWorkspace> wsHold = pme_workspace(gx, gy, gz, stream);
+    PmeWorkspace& ws = *wsHold;
     NNP_CUDA_CHECK(cudaMemsetAsync(ws.energyAcc, 0, sizeof(double), stream));
-    NNP_CUFFT_CHECK(cufftSetStream(ws.r2c, stream));
+    if (ws.r2cStream != stream) {   // only when the workspace is shared with a capturing stream (workspace_cache.cuh)
+        NNP_CUFFT_CHECK(cufftSetStream(ws.r2c, stream));
+        ws.r2cStream = stream;
+    }
     NNP_CUFFT_CHECK(cufftExecR2C(ws.r2c, realGrid, reinterpret_cast<cufftComplex*>(recipGrid)));
     const long long total = (long long)gx * gy * (gz / 2 + 1);
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 8);
@@ -398,7 +408,8 @@ void pme_reciprocal_forward(const float* positions, const float* charges, const 
                             float* recipGrid, cudaStream_t stream) {
     NNP_REQUIRE(order == 4 || order == 5, "Only pmeOrder 4 or 5 is supported with CUDA");
     NNP_REQUIRE(gx > 0 && gy > 0 && gz > 0, "The grid dimensions must be positive");
-    PmeWorkspace& ws = pme_workspace(gx, gy, gz);
+    const std::shared_ptr<PmeWorkspace> wsHold = pme_workspace(gx, gy, gz, stream);
+    PmeWorkspace& ws = *wsHold;
     pme_spread(positions, charges, box, numAtoms, gx, gy, gz, order, coulomb, ws.realGrid, stream);
     pme_solve(ws.realGrid, box, gx, gy, gz, alpha, xmod, ymod, zmod, energy, recipGrid, stream);
 }
@@ -406,10 +417,14 @@ void pme_reciprocal_forward(const float* positions, const float* charges, const 
 void pme_reciprocal_backward(const float* positions, const float* charges, const float* box, int numAtoms, int gx, int gy, int gz, int order,
                              float coulomb, const float* recipGrid, float* posDeriv, float* chargeDeriv, cudaStream_t stream) {
     NNP_REQUIRE(order == 4 || order == 5, "Only pmeOrder 4 or 5 is supported with CUDA");
-    PmeWorkspace& ws = pme_workspace(gx, gy, gz);
+    const std::shared_ptr<PmeWorkspace> wsHold = pme_workspace(gx, gy, gz, stream);
+    PmeWorkspace& ws = *wsHold;
     const size_t nCplx = (size_t)gx * gy * (gz / 2 + 1);
     NNP_CUDA_CHECK(cudaMemcpyAsync(ws.scratch, recipGrid, sizeof(float2) * nCplx, cudaMemcpyDeviceToDevice, stream));
-    NNP_CUFFT_CHECK(cufftSetStream(ws.c2r, stream));
+    if (ws.c2rStream != stream) {
+        NNP_CUFFT_CHECK(cufftSetStream(ws.c2r, stream));
+        ws.c2rStream = stream;
+    }
     NNP_CUFFT_CHECK(cufftExecC2R(ws.c2r, reinterpret_cast<cufftComplex*>(ws.scratch), ws.realGrid));
     const float sqrtCoulomb = (float)std::sqrt((double)coulomb);
     if (numAtoms > 0) {

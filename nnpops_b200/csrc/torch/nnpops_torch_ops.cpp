@@ -12,6 +12,7 @@
 #include <torch/serialize/archive.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
+#include <c10/cuda/CUDAGraphsC10Utils.h>
 #include <sstream>
 #include "../../../include/nnpops_b200.h"
 
@@ -59,17 +60,7 @@ public:
         if (!impl) {
             device = positions.device();
             periodic = cellOpt.has_value();
-            std::vector<float> radialFn, angularFn;   // function order of SymmetryFunctions.cpp:110-120
-            for (const float eta : EtaR)
-                for (const float rs : ShfR) { radialFn.push_back(eta); radialFn.push_back(rs); }
-            for (const float eta : EtaA)
-                for (const float zeta : Zeta)
-                    for (const float rs : ShfA)
-                        for (const float thetas : ShfZ) { angularFn.push_back(eta); angularFn.push_back(rs); angularFn.push_back(zeta); angularFn.push_back(thetas); }
-            std::vector<int> species(atomSpecies.begin(), atomSpecies.end());
-            nRadial = (int)radialFn.size() / 2; nAngular = (int)angularFn.size() / 4;
-            check(nnpops_ani_create(&impl, (int)species.size(), (int)numSpecies, (float)Rcr, (float)Rca, species.data(), nRadial, radialFn.data(),
-                                    nAngular, angularFn.data(), 1, 0, 0));
+            createImpl();
         }
         if (positions.device() != device) throw std::runtime_error("The device of \"positions\" has changed");
         const Tensor pos = positions.contiguous();
@@ -77,9 +68,36 @@ public:
         const auto opt = torch::TensorOptions().device(device).dtype(torch::kFloat32);
         Tensor radial = torch::empty({n, numSpecies * nRadial}, opt);
         Tensor angular = torch::empty({n, numSpecies * (numSpecies + 1) / 2 * nAngular}, opt);
-        check(nnpops_ani_forward(impl, pos.data_ptr<float>(), cellOpt ? cell.data_ptr<float>() : nullptr, radial.data_ptr<float>(),
-                                 angular.data_ptr<float>(), stream_of(pos)));
+        // The reference keeps an N x N neighbour table and so has no neighbour limit (CudaANISymmetryFunctions.cu:44); here rows have a
+        // capacity.  A row that overflowed is detected right after the call and the call repeated with larger rows, so the result is
+        // never silently truncated.  While a CUDA graph is being captured nothing may synchronise: the check is skipped there and the
+        // flag polled on the next eager call instead.
+        const bool capturing = c10::cuda::currentStreamCaptureStatusMayInitCtx() != c10::cuda::CaptureStatus::None;
+        if (!capturing) raiseIfOverflowedEarlier();
+        for (int attempt = 0;; attempt++) {
+            check(nnpops_ani_forward(impl, pos.data_ptr<float>(), cellOpt ? cell.data_ptr<float>() : nullptr, radial.data_ptr<float>(),
+                                     angular.data_ptr<float>(), stream_of(pos)));
+            if (capturing) break;
+            int flags = 0;
+            check(nnpops_ani_overflowed(impl, &flags));   // synchronises, like the reference's host read of the box (SymmetryFunctions.cpp:104-108)
+            if (!flags) break;
+            TORCH_CHECK(attempt < 8, "nnpops_b200: neighbour rows still overflow after growing them 8 times");
+            if (flags & 1) maxRadial = 2 * (maxRadial > 0 ? maxRadial : 256);
+            if (flags & 2) maxAngular = 2 * (maxAngular > 0 ? maxAngular : 64);
+            nnpops_ani_destroy(impl);
+            impl = nullptr;
+            createImpl();
+        }
         return {radial, angular};
+    }
+
+    // row capacities in use (0 = library default) and whether any row has overflowed so far (blocks)
+    int64_t maxRadialNeighbors() const { return maxRadial; }
+    int64_t maxAngularNeighbors() const { return maxAngular; }
+    int64_t overflowed() {
+        int flags = 0;
+        if (impl) check(nnpops_ani_overflowed(impl, &flags));
+        return flags;
     }
 
     tensor_list backward(const tensor_list& grads) {
@@ -114,6 +132,27 @@ public:
     }
 
 private:
+    void createImpl() {
+        std::vector<float> radialFn, angularFn;   // function order of SymmetryFunctions.cpp:110-120
+        for (const float eta : EtaR)
+            for (const float rs : ShfR) { radialFn.push_back(eta); radialFn.push_back(rs); }
+        for (const float eta : EtaA)
+            for (const float zeta : Zeta)
+                for (const float rs : ShfA)
+                    for (const float thetas : ShfZ) { angularFn.push_back(eta); angularFn.push_back(rs); angularFn.push_back(zeta); angularFn.push_back(thetas); }
+        std::vector<int> species(atomSpecies.begin(), atomSpecies.end());
+        nRadial = (int)radialFn.size() / 2; nAngular = (int)angularFn.size() / 4;
+        check(nnpops_ani_create(&impl, (int)species.size(), (int)numSpecies, (float)Rcr, (float)Rca, species.data(), nRadial, radialFn.data(),
+                                nAngular, angularFn.data(), 1, maxRadial, maxAngular));
+    }
+    // an overflow recorded by a call that could not check for itself (graph capture / replay)
+    void raiseIfOverflowedEarlier() {
+        int flags = 0;
+        check(nnpops_ani_overflow_poll(impl, &flags, nullptr, nullptr));
+        TORCH_CHECK(!flags, "nnpops_b200: a neighbour row overflowed during an earlier call that could not be checked (CUDA graph); "
+                            "its AEVs were truncated. Run one eager forward before capturing so that the rows can grow.");
+    }
+
     int64_t numSpecies;
     double Rcr, Rca;
     std::vector<double> EtaR, ShfR, EtaA, Zeta, ShfA, ShfZ;
@@ -121,6 +160,7 @@ private:
     torch::Device device = torch::kCPU;
     bool periodic = false;
     int nRadial = 0, nAngular = 0;
+    int maxRadial = 0, maxAngular = 0;   // neighbour-row capacities handed to the library (0 = its defaults, 256 / 64); grown on overflow
     nnpops_ani_t impl = nullptr;
 };
 
@@ -150,6 +190,9 @@ public:
         require_cuda(weights, "weights");
         TORCH_CHECK(weights.dim() == 5 && vectors.dim() == 5 && biases.dim() == 5, "BatchedLinear expects 5-D tensors");
         TORCH_CHECK(weights.size(0) == 1 && weights.scalar_type() == torch::kFloat32, "BatchedLinear: weights must be float32 [1, N, M, out, in]");
+        // the reference is torch::matmul(weights, vectors) + biases (BatchedNN.cpp:34), which would broadcast over a leading batch of
+        // molecules; this kernel evaluates one molecule, so refuse a batch instead of silently computing molecule 0 only
+        TORCH_CHECK(vectors.size(0) == 1 && biases.size(0) == 1, "BatchedLinear: only one molecule per call is supported (leading dimension must be 1)");
         const int64_t N = weights.size(1), M = weights.size(2), nOut = weights.size(3), nIn = weights.size(4);
         TORCH_CHECK(vectors.size(1) == N && (vectors.size(2) == M || vectors.size(2) == 1) && vectors.size(3) == nIn && vectors.size(4) == 1,
                     "BatchedLinear: vectors must be [1, N, M or 1, in, 1]");
@@ -443,6 +486,12 @@ public:
                                           params.data_ptr<float>(), (int)mlpImpl, 0, 0));
         }
         if (positions.device() != device) throw std::runtime_error("The device of \"positions\" has changed");
+        {   // never blocks: a row that overflowed in an earlier evaluation is reported now (the fused path must stay asynchronous)
+            int flags = 0, capR = 0, capA = 0;
+            check(nnpops_ani_model_overflow_poll(impl, &flags, &capR, &capA));
+            TORCH_CHECK(!flags, "nnpops_b200: a neighbour row overflowed in an earlier evaluation (capacities ", capR, " radial / ", capA,
+                        " angular): energies and forces since then are wrong. The system is denser than the rows allow.");
+        }
         const Tensor pos = positions.contiguous();
         Tensor energy = torch::empty({1}, pos.options()), grad = torch::empty_like(pos);
         check(nnpops_ani_model_energy_grad(impl, pos.data_ptr<float>(), cellOpt ? cell.data_ptr<float>() : nullptr, energy.data_ptr<float>(),
@@ -510,6 +559,9 @@ TORCH_LIBRARY(NNPOpsANISymmetryFunctions, m) {
                          const std::vector<double>&, const std::vector<double>&, const std::vector<double>&, const std::vector<int64_t>&>())
         .def("forward", &AniHolder::forward)
         .def("backward", &AniHolder::backward)
+        .def("max_radial_neighbors", &AniHolder::maxRadialNeighbors)
+        .def("max_angular_neighbors", &AniHolder::maxAngularNeighbors)
+        .def("overflowed", &AniHolder::overflowed)
         .def_pickle([](const c10::intrusive_ptr<AniHolder>& self) -> std::string { return self->serialize(); },
                     [](const std::string& state) -> c10::intrusive_ptr<AniHolder> { return AniHolder::deserialize(state); });
     m.def("operation", ani_operation);
@@ -545,13 +597,20 @@ TORCH_LIBRARY(neighbors, m) {
     m.def("getNeighborPairs(Tensor positions, Scalar cutoff, Scalar max_num_neighbors, Tensor box_vectors, bool checkErrors) -> "
           "(Tensor neighbors, Tensor deltas, Tensor distances, Tensor num_pairs)");
 }
-TORCH_LIBRARY_IMPL(neighbors, AutogradCUDA, m) {
+// The same entry serves the AutogradCUDA and the CUDA key: torch::autograd::Function::apply records a graph only when one is needed
+// and the forward calls the C ABI directly (no re-dispatch), so calls under torch.inference_mode() / below autograd find a kernel too,
+// as they do with the reference's CUDA registration (getNeighborPairsCUDA.cu:198-206).
+#define NNPOPS_IMPL_BOTH(NS, BODY)                 \
+    TORCH_LIBRARY_IMPL(NS, AutogradCUDA, m) { BODY } \
+    TORCH_LIBRARY_IMPL(NS, CUDA, m) { BODY }
+
+NNPOPS_IMPL_BOTH(neighbors,
     m.impl("getNeighborPairs", [](const Tensor& positions, const torch::Scalar& cutoff, const torch::Scalar& maxNumPairs, const Tensor& boxVectors,
                                   bool checkErrors) {
         const tensor_list r = NeighborFunction::apply(positions, cutoff, maxNumPairs, boxVectors, checkErrors);
         return std::make_tuple(r[0], r[1], r[2], r[3]);
     });
-}
+)
 
 TORCH_LIBRARY(pme, m) {
     m.def("pme_direct(Tensor positions, Tensor charges, Tensor neighbors, Tensor deltas, Tensor distances, Tensor exclusions, Scalar alpha, "
@@ -559,7 +618,7 @@ TORCH_LIBRARY(pme, m) {
     m.def("pme_reciprocal(Tensor positions, Tensor charges, Tensor box_vectors, Scalar gridx, Scalar gridy, Scalar gridz, Scalar order, "
           "Scalar alpha, Scalar coulomb, Tensor xmoduli, Tensor ymoduli, Tensor zmoduli) -> Tensor");
 }
-TORCH_LIBRARY_IMPL(pme, AutogradCUDA, m) {
+NNPOPS_IMPL_BOTH(pme,
     m.impl("pme_direct", [](const Tensor& positions, const Tensor& charges, const Tensor& neighbors, const Tensor& deltas, const Tensor& distances,
                             const Tensor& exclusions, const torch::Scalar& alpha, const torch::Scalar& coulomb) {
         return PmeDirectFunction::apply(positions, charges, neighbors, deltas, distances, exclusions, alpha, coulomb);
@@ -569,4 +628,4 @@ TORCH_LIBRARY_IMPL(pme, AutogradCUDA, m) {
                                 const torch::Scalar& coulomb, const Tensor& xmoduli, const Tensor& ymoduli, const Tensor& zmoduli) {
         return PmeReciprocalFunction::apply(positions, charges, boxVectors, gridx, gridy, gridz, order, alpha, coulomb, xmoduli, ymoduli, zmoduli);
     });
-}
+)

@@ -207,3 +207,103 @@ def pme_direct(pos, charges, box, cutoff, alpha, coulomb, exclusions=None):
             dedr = pref * q[a1] * q[a2] * (erf(ar) - ar * math.exp(-ar * ar) * 2 / math.sqrt(math.pi)) / r ** 2
             dpos[a1] += dedr * dr; dpos[a2] -= dedr * dr
     return energy, dpos, dq
+
+
+# -------------------------------------------------------------------------------------------- vectorised PME restatement
+# Same arithmetic as _spline / pme_reciprocal above (src/pytorch/pme/pmeCPU.cpp:197-349), written with whole-array numpy
+# operations so that BASELINE config 5 (200 000 charges, 128^3 grid, order 5) finishes in seconds.  tests/ pins it to the loop
+# version on small systems.
+def _spline_vec(pos, box, recip, grid, order):
+    p = np.array(pos, np.float64)
+    b = np.asarray(box, np.float64)
+    for i in (2, 1, 0):
+        p = p - np.floor(p[:, i] * recip[i, i])[:, None] * b[i][None, :]
+    t = p @ recip
+    t = (t - np.floor(t)) * np.asarray(grid)
+    ti = t.astype(np.int64)
+    dr = t - ti
+    gi = ti % np.asarray(grid)
+    n = len(p)
+    data = np.zeros((n, order, 3)); ddata = np.zeros((n, order, 3))
+    d = np.zeros((n, order, 3))
+    d[:, 0], d[:, 1] = 1 - dr, dr
+    for j in range(3, order + 1):
+        if j == order:
+            ddata[:, 0] = -d[:, 0]
+            for k in range(1, order):
+                ddata[:, k] = d[:, k - 1] - d[:, k]
+        new = np.zeros_like(d)
+        for m in range(j):
+            lo = d[:, m - 1] if m > 0 else 0.0
+            hi = d[:, m] if m < j - 1 else 0.0
+            new[:, m] = ((dr + (j - 1 - m)) * lo + ((m + 1) - dr) * hi) / (j - 1)
+        d = new
+    data[:] = d
+    return gi, data, ddata
+
+
+def pme_reciprocal_vec(pos, charges, box, grid, order, alpha, coulomb):
+    """Vectorised pme_reciprocal: -> (energy incl. self term, dE/dpos [N,3], dE/dq [N]) in float64."""
+    pos = np.asarray(pos, np.float64); q = np.asarray(charges, np.float64); box = np.asarray(box, np.float64)
+    gx, gy, gz = grid
+    recip = _recip_box(box)
+    sc = math.sqrt(coulomb)
+    gi, data, ddata = _spline_vec(pos, box, recip, grid, order)
+    o = np.arange(order)
+    ix = (gi[:, 0, None] + o) % gx; iy = (gi[:, 1, None] + o) % gy; iz = (gi[:, 2, None] + o) % gz          # [N, order]
+    flat = (ix[:, :, None, None] * gy + iy[:, None, :, None]) * gz + iz[:, None, None, :]                      # [N, o, o, o]
+    w = data[:, :, 0][:, :, None, None] * data[:, :, 1][:, None, :, None] * data[:, :, 2][:, None, None, :]
+    Q = np.bincount(flat.ravel(), weights=(w * (q * sc)[:, None, None, None]).ravel(), minlength=gx * gy * gz).reshape(grid)
+    F = np.fft.rfftn(Q)
+    xm, ym, zm = pme_moduli(order, grid)
+    kx = np.arange(gx); ky = np.arange(gy); kz = np.arange(gz // 2 + 1)
+    mx = np.where(kx < (gx + 1) // 2, kx, kx - gx)[:, None, None].astype(np.float64)
+    my = np.where(ky < (gy + 1) // 2, ky, ky - gy)[None, :, None].astype(np.float64)
+    mz = np.where(kz < (gz + 1) // 2, kz, kz - gz)[None, None, :].astype(np.float64)
+    hx = mx * recip[0, 0]; hy = mx * recip[1, 0] + my * recip[1, 1]; hz = mx * recip[2, 0] + my * recip[2, 1] + mz * recip[2, 2]
+    m2 = hx * hx + hy * hy + hz * hz
+    scale_factor = math.pi * box[0, 0] * box[1, 1] * box[2, 2]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        e = np.exp(-(math.pi ** 2 / alpha ** 2) * m2) / (m2 * scale_factor * np.asarray(xm)[:, None, None] * np.asarray(ym)[None, :, None] *
+                                                        np.asarray(zm)[None, None, : gz // 2 + 1])
+    e[0, 0, 0] = 0.0
+    wk = np.where((kz > 0) & (kz <= (gz - 1) // 2), 2.0, 1.0)[None, None, :]
+    energy = float(np.sum(wk * e * np.abs(F) ** 2))
+    phi = np.fft.irfftn(F * e, s=grid, axes=(0, 1, 2), norm="forward").ravel()
+    g = phi[flat]                                                                                                # [N, o, o, o]
+    d0 = np.einsum("nxyz,nx,ny,nz->n", g, ddata[:, :, 0], data[:, :, 1], data[:, :, 2])
+    d1 = np.einsum("nxyz,nx,ny,nz->n", g, data[:, :, 0], ddata[:, :, 1], data[:, :, 2])
+    d2 = np.einsum("nxyz,nx,ny,nz->n", g, data[:, :, 0], data[:, :, 1], ddata[:, :, 2])
+    s = np.einsum("nxyz,nx,ny,nz->n", g, data[:, :, 0], data[:, :, 1], data[:, :, 2])
+    dpos = np.stack([q * sc * (d0 * gx * recip[0, 0]),
+                     q * sc * (d0 * gx * recip[1, 0] + d1 * gy * recip[1, 1]),
+                     q * sc * (d0 * gx * recip[2, 0] + d1 * gy * recip[2, 1] + d2 * gz * recip[2, 2])], axis=1)
+    self_energy = -np.sum(q ** 2) * coulomb * alpha / math.sqrt(math.pi)
+    dq_self = -2 * q * coulomb * alpha / math.sqrt(math.pi)
+    return 0.5 * energy + self_energy, dpos, s * sc + dq_self
+
+
+def pme_direct_sampled(pos, charges, box_edge, cutoff, alpha, coulomb, sample):
+    """Direct-space PME of a CUBIC periodic box restricted to the atoms `sample`: -> (dE/dpos [len(sample), 3], dE/dq [len(sample)],
+    per-atom energy share) in float64, neighbours from a periodic KD-tree (pmeCPU.cpp:105-157, no exclusions).  For systems too
+    large for the all-pairs loop of pme_direct."""
+    from scipy.spatial import cKDTree
+    from scipy.special import erfc as erfc_v
+    pos = np.asarray(pos, np.float64); q = np.asarray(charges, np.float64)
+    L = float(box_edge)
+    w = np.mod(pos, L)
+    tree = cKDTree(w, boxsize=L)
+    dpos = np.zeros((len(sample), 3)); dq = np.zeros(len(sample)); eshare = np.zeros(len(sample))
+    for k, i in enumerate(sample):
+        nb = np.array([j for j in tree.query_ball_point(w[i], cutoff) if j != i], np.int64)
+        d = w[i] - w[nb]
+        d -= np.round(d / L) * L                      # delta = pos[i] - pos[j], minimum image
+        r = np.sqrt((d * d).sum(1))
+        keep = r < cutoff
+        nb, d, r = nb[keep], d[keep], r[keep]
+        ar = alpha * r; pref = coulomb / r
+        eshare[k] = 0.5 * np.sum(pref * erfc_v(ar) * q[i] * q[nb])
+        dq[k] = np.sum(pref * erfc_v(ar) * q[nb])
+        dedr = pref * q[i] * q[nb] * (erfc_v(ar) + ar * np.exp(-ar * ar) * 2 / math.sqrt(math.pi)) / r ** 2
+        dpos[k] = -(dedr[:, None] * d).sum(0)
+    return dpos, dq, eshare

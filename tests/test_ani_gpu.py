@@ -322,3 +322,66 @@ def test_full_size_box_rows_match_oracle_on_local_clusters():
         worst = max(worst, np.abs(aev[i] - row0).max() / np.abs(row0).max())
     print("full-size AEV rows vs oracle clusters: worst rel err %.2e, triples %d, pairs %d" % (worst, triples, pairs))
     assert worst < 2e-5   # the cluster uses re-centred coordinates, so deltas differ from the box arithmetic by fp32 round-off
+
+
+@pytest.mark.parametrize("hidden,ensemble", [(ANI2X_HIDDEN, 8), ([(64, 64, 32)] * 7, 2), ([(96, 32, 64)] * 7, 3), ([(256, 192, 160)] * 7, 1)])
+def test_fused_chain_kernel_matches_per_layer_path(hidden, ensemble, monkeypatch):
+    """The one-kernel layer chain (csrc/mlp_chain.cu: activations in tensor / shared memory, two MMA issuers) against the per-layer
+    tcgen05 GEMMs it replaces (NNPOPS_NO_CHAIN=1), on a water box with several 128-atom tiles per species: widths that give one,
+    two, three and four 64-column chunks per layer and odd/even chunk counts per chain; repeated evaluations must agree too (the
+    barrier phases of the persistent kernel carry over from tile to tile and member to member)."""
+    from nnpops_b200.OptimizedTorchANI import FusedANI
+    n = 3000
+    pos, L = lattice(n, 2.154, 0.3, 3000)
+    species = water_species(n)
+    nets = random_networks(7, hidden, ensemble, 1008, 7)
+    args = (7, 5.2, 3.5, ANI2X["EtaR"], ANI2X["ShfR"], ANI2X["EtaA"], ANI2X["Zeta"], ANI2X["ShfA"], ANI2X["ShfZ"], species, nets)
+    p, b = dev(pos), dev(cubic_box(L))
+    monkeypatch.setenv("NNPOPS_NO_CHAIN", "1")
+    e0, g0 = FusedANI(*args).energy_and_gradient(p, b)
+    monkeypatch.delenv("NNPOPS_NO_CHAIN")
+    m = FusedANI(*args)
+    e0 = float(e0.cpu()[0]); g0 = g0.cpu().numpy()
+    for rep in range(6):
+        e, g = m.energy_and_gradient(p, b)
+        err_e, err_g = abs(float(e.cpu()[0]) - e0) / abs(e0), rel_err(g.cpu().numpy(), g0)
+        assert err_e < 2e-6 and err_g < 5e-6, (rep, err_e, err_g)
+    assert m.overflowed() == 0
+
+
+def test_neighbour_rows_grow_instead_of_truncating():
+    """The reference has no neighbour limit (N x N table, CudaANISymmetryFunctions.cu:44).  A system denser than the default row
+    capacities (256 radial / 64 angular) must still give the oracle's AEVs through the drop-in Holder (ctypes mirror and
+    torch.classes): the rows are grown and the call repeated.  The asynchronous fused model cannot repeat a call, so it raises on
+    the NEXT one."""
+    from nnpops_b200 import torch_ops
+    from nnpops_b200.OptimizedTorchANI import FusedANI
+    from nnpops_b200.SymmetryFunctions import Holder
+    n = 400
+    pos, L = lattice(n, 1.5, 0.3, 123)              # 0.3 atoms / A^3: about 53 angular neighbours on average, more than 64 for some
+    species = np.random.default_rng(4).integers(0, 2, n).astype(np.int32)
+    box = cubic_box(L)
+    rfn, afn = ani2x_tables()
+    r0, a0 = O.ani_forward(pos, species, 2, 5.1, 3.5, rfn, afn, box=box)
+    h = Holder.from_function_lists(2, 5.1, 3.5, rfn, afn, list(species))
+    r, a = h.forward(dev(pos), dev(box))
+    assert h.caps[1] > 64 and h.overflowed() == 0
+    assert rel_err(r.cpu().numpy(), r0) < TOL and rel_err(a.cpu().numpy(), a0) < TOL
+    torch_ops.load()
+    th = torch.classes.NNPOpsANISymmetryFunctions.Holder(2, 5.1, 3.5, ANI2X["EtaR"], ANI2X["ShfR"], ANI2X["EtaA"], ANI2X["Zeta"], ANI2X["ShfA"],
+                                                         ANI2X["ShfZ"], [int(s) for s in species])
+    r, a = torch.ops.NNPOpsANISymmetryFunctions.operation(th, dev(pos), dev(box))
+    assert th.max_angular_neighbors() > 64 and th.overflowed() == 0
+    assert rel_err(r.cpu().numpy(), r0) < TOL and rel_err(a.cpu().numpy(), a0) < TOL
+    nets = random_networks(2, [(32, 32, 32)] * 2, 1, 2 * 16 + 3 * 32, 5)
+    m = FusedANI(2, 5.1, 3.5, ANI2X["EtaR"], ANI2X["ShfR"], ANI2X["EtaA"], ANI2X["Zeta"], ANI2X["ShfA"], ANI2X["ShfZ"], species, nets)
+    m.energy_and_gradient(dev(pos), dev(box))
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match="overflowed"):
+        m.energy_and_gradient(dev(pos), dev(box))
+    big = FusedANI(2, 5.1, 3.5, ANI2X["EtaR"], ANI2X["ShfR"], ANI2X["EtaA"], ANI2X["Zeta"], ANI2X["ShfA"], ANI2X["ShfZ"], species, nets,
+                   max_angular_neighbors=160)
+    big.energy_and_gradient(dev(pos), dev(box))
+    torch.cuda.synchronize()
+    big.energy_and_gradient(dev(pos), dev(box))
+    assert big.overflowed() == 0

@@ -38,3 +38,22 @@ def test_pme_openmm_golden(case):
     assert np.allclose(c["erecip"], e_r, rtol=1e-4)
     assert np.allclose(c["expected_ddirect"], f_d, rtol=1e-4, atol=1e-4)
     assert np.allclose(c["expected_drecip"], f_r, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("order", [4, 5])
+def test_vectorised_pme_oracle_equals_loop_version(order):
+    """pme_reciprocal_vec (used at BASELINE config 5 size) is the same arithmetic as the loop restatement pinned above, and
+    pme_direct_sampled equals pme_direct on the sampled atoms of a cubic box."""
+    rng = np.random.default_rng(order)
+    n = 40
+    box = np.array([[3.0, 0, 0], [0.4, 3.1, 0], [-0.3, 0.5, 2.9]])
+    pos = rng.uniform(-0.5, 1.5, (n, 3)) @ box
+    q = rng.uniform(-0.5, 0.5, n); q -= q.mean()
+    a = NP.pme_reciprocal(pos, q, box, (12, 10, 14), order, 3.2, 138.935)
+    b = NP.pme_reciprocal_vec(pos, q, box, (12, 10, 14), order, 3.2, 138.935)
+    assert abs(a[0] - b[0]) <= 1e-12 * abs(a[0]) and np.allclose(a[1], b[1], rtol=1e-10, atol=1e-10) and np.allclose(a[2], b[2], rtol=1e-10, atol=1e-10)
+    L = 3.0
+    e, dp, dq = NP.pme_direct(pos, q, np.eye(3) * L, 1.2, 3.2, 138.935)
+    s = np.arange(0, n, 5)
+    dps, dqs, es = NP.pme_direct_sampled(pos, q, L, 1.2, 3.2, 138.935, s)
+    assert np.allclose(dps, dp[s], rtol=1e-10, atol=1e-10) and np.allclose(dqs, dq[s], rtol=1e-10, atol=1e-10)
