@@ -4,7 +4,7 @@ Importing the package loads the hand-written CUDA library (libnnpops_b200.so) th
 been built.  Sub-modules mirror the reference's Python surface (src/pytorch/*.py):
 
     nnpops_b200.SymmetryFunctions   TorchANISymmetryFunctions        (reference: SymmetryFunctions.py)
-    nnpops_b200.BatchedNN           TorchANIBatchedNN, batchedLinear (reference: BatchedNN.py)
+    (BatchedNN.py has no mirror: the reference's own file runs unchanged on the NNPOpsBatchedNN::BatchedLinear op of libNNPOpsPyTorch.so)
     nnpops_b200.OptimizedTorchANI   OptimizedTorchANI, FusedANI      (reference: OptimizedTorchANI.py)
     nnpops_b200.neighbors           getNeighborPairs                 (reference: neighbors/getNeighborPairs.py)
     nnpops_b200.CFConv / CFConvNeighbors                             (reference: CFConv.py, CFConvNeighbors.py)

@@ -1,6 +1,7 @@
-"""The reference's module chain on a torchani stand-in: OptimizedTorchANI (fused) and the literal
-TorchANISymmetryFunctions + TorchANIBatchedNN path, both against oracle AEV + ATen MLP (cf. TestOptimizedTorchANI.py:59-100,
-TestBatchedNN.py:49-82 of the reference, which compare against torchani itself)."""
+"""This package's OptimizedTorchANI (same constructor as the reference's, built on the fused model) on a torchani stand-in, against
+oracle AEV + ATen MLP (cf. TestOptimizedTorchANI.py:59-100 of the reference, which compares against torchani itself).  The literal
+chain -- the reference's own SymmetryFunctions.py + BatchedNN.py on the drop-in ops -- is run from the reference's files in
+tests/test_reference_package_gpu.py."""
 import numpy as np
 import pytest
 import torch
@@ -23,11 +24,8 @@ def reference_values(model, pos, species):
     return e0 + sae, g0
 
 
-@pytest.mark.parametrize("path", ["fused", "literal"])
-def test_module_chain(path):
+def test_module_chain():
     from nnpops_b200.OptimizedTorchANI import OptimizedTorchANI
-    from nnpops_b200.SymmetryFunctions import TorchANISymmetryFunctions
-    from nnpops_b200.BatchedNN import TorchANIBatchedNN
     n = 46   # size of the reference's benchmark ligand 2iuz
     pos, _ = lattice(n, 1.9, 0.3, 46)
     species = np.random.default_rng(3).integers(0, 7, n)
@@ -35,14 +33,8 @@ def test_module_chain(path):
     model = Model(HIDDEN, 4, seed=11)
     e_ref, g_ref = reference_values(model, pos, species)
     p = torch.tensor(pos, device="cuda").unsqueeze(0).requires_grad_(True)
-    if path == "fused":
-        nnp = OptimizedTorchANI(model, numbers.cuda())
-        energy = nnp((numbers.cuda(), p)).energies
-    else:
-        aev = TorchANISymmetryFunctions(model.species_converter, model.aev_computer, numbers)
-        nn_ = TorchANIBatchedNN(model.species_converter, model.neural_networks, numbers).to("cuda")
-        sp = model.species_converter((numbers, torch.empty(0))).species.cuda()
-        energy = nn_(aev((sp, p))).energies + model.energy_shifter.sae(sp.cpu()).cuda()
+    nnp = OptimizedTorchANI(model, numbers.cuda())
+    energy = nnp((numbers.cuda(), p)).energies
     energy.sum().backward()
     e = float(energy.detach().cpu().double()[0])
     assert abs(e - e_ref) < 5e-6 * abs(e_ref)
