@@ -134,6 +134,10 @@ class FusedANI(torch.nn.Module):
                                                     current_stream(self.device_)))
 
     def forward(self, positions: Tensor, cell: Optional[Tensor] = None) -> Tensor:
+        """positions [N, 3] -> energy [1]; a batch of conformers of the same system [B, N, 3] -> energies [B] (evaluated one after the
+        other on the same stream; the reference rejects batches, SymmetryFunctions.py:110-111).  Forces by autograd."""
+        if positions.dim() == 3:
+            return torch.cat([_EnergyGrad.apply(self, positions[b], cell) for b in range(positions.shape[0])])
         return _EnergyGrad.apply(self, positions, cell)
 
     # -- introspection for tests / benchmarks
@@ -208,15 +212,6 @@ class ShardedFusedANI(torch.nn.Module):
                       else FusedANI(*args, shard=(self.rank, self.world), **kwargs))
         self._packed = None
 
-    def _raise_if_overflowed(self):
-        """Never blocks: a neighbour row that overflowed in an EARLIER evaluation is reported now (the reference has no neighbour
-        limit; this path must stay asynchronous, so it cannot check the evaluation it is about to launch)."""
-        f, r, a = C.c_int(0), C.c_int(0), C.c_int(0)
-        check(lib.nnpops_ani_model_overflow_poll(self._h, C.byref(f), C.byref(r), C.byref(a)))
-        if f.value:
-            raise RuntimeError("nnpops_b200: a neighbour row overflowed in an earlier evaluation (capacities %d radial / %d angular): "
-                               "results since then are wrong. Pass larger max_radial_neighbors / max_angular_neighbors." % (r.value, a.value))
-
     def energy_and_gradient(self, positions: Tensor, cell: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
         e, g = self.local.energy_and_gradient(positions, cell)
         if self.world == 1:
@@ -283,15 +278,16 @@ class OptimizedTorchANI(torch.nn.Module):
     def forward(self, species_coordinates: Tuple[Tensor, Tensor], cell: Optional[Tensor] = None,
                 pbc: Optional[Tensor] = None) -> SpeciesEnergies:
         _, coordinates = species_coordinates
-        if coordinates.shape[0] != 1:
-            raise ValueError('Batched computation of molecules is not supported')
         if cell is not None:
             if pbc is None:
                 raise ValueError('"pbc" has to be defined')
             if pbc.tolist() != [True, True, True]:
                 raise ValueError('Only fully periodic systems are supported, i.e. pbc = [True, True, True]')
-        energies = self.fused(coordinates[0], cell)
-        return SpeciesEnergies(self.species, energies.double() + self.self_energies.to(energies.device))
+        # A batch is a set of conformers of the system this module was built for (one Holder = one list of species,
+        # SymmetryFunctions.cpp:52-92): coordinates [B, N, 3] -> energies [B].  The reference stops at B = 1 (SymmetryFunctions.py:110-111).
+        batch = coordinates.shape[0]
+        energies = self.fused(coordinates if batch > 1 else coordinates[0], cell)
+        return SpeciesEnergies(self.species.expand(batch, -1), energies.double() + self.self_energies.to(energies.device))
 
 
 class ScriptableFusedANI(torch.nn.Module):
@@ -312,4 +308,9 @@ class ScriptableFusedANI(torch.nn.Module):
                                                           {"simt": 0, "tcgen05": 1}[mlp_impl])
 
     def forward(self, positions: Tensor, cell: Optional[Tensor] = None) -> Tensor:
+        if positions.dim() == 3:      # a batch of conformers of the same system: [B, N, 3] -> energies [B]
+            out: List[Tensor] = []
+            for b in range(positions.shape[0]):
+                out.append(torch.ops.NNPOpsFusedANI.operation(self.holder, positions[b], cell))
+            return torch.cat(out)
         return torch.ops.NNPOpsFusedANI.operation(self.holder, positions, cell)

@@ -340,7 +340,10 @@ public:
         NNP_REQUIRE(width > 0 && numGaussians > 1, "width must be positive and numGaussians > 1");
         NNP_REQUIRE(cutoff > 0 && gaussianWidth > 0, "cutoff and gaussianWidth must be positive");
         NNP_REQUIRE(activation == 0 || activation == 1, "activation must be 0 (shifted softplus) or 1 (tanh)");
-        const int pps = pointsPerSigma > 0 ? pointsPerSigma : 32;
+        // table step = sigma / 128: the cubic Hermite value error goes as h^4 and the error of its derivative (the force) as h^3; at
+        // sigma / 32 the position gradient of the 100 000-atom box was 1.5e-5 off the fp64 oracle, at sigma / 128 it is 64 x closer
+        // (6 401 rows x W for sigma 0.2 / cutoff 10: still L2-resident)
+        const int pps = pointsPerSigma > 0 ? pointsPerSigma : 128;
         long long P = (long long)std::ceil((double)pps * cutoff / gaussianWidth) + 1;
         if (P < 256) P = 256;
         if (P > 65536) P = 65536;

@@ -582,13 +582,27 @@ TORCH_LIBRARY(NNPOpsCFConv, m) {
         .def(torch::init<double, const std::string&, const Tensor&, const Tensor&, const Tensor&, const Tensor&>())
         .def("forward", &CFConvHolder::forward)
         .def("backward", &CFConvHolder::backward)
+        // the state is the string the reference writes (CFConv.cpp:191-225: an OutputArchive with these six keys), so archives saved by
+        // either library load on the other
         .def_pickle(
-            [](const c10::intrusive_ptr<CFConvHolder>& self) -> std::tuple<double, std::string, Tensor, Tensor, Tensor, Tensor> {
-                return std::make_tuple(self->gaussianWidth, self->activation, self->weights1, self->biases1, self->weights2, self->biases2);
+            [](const c10::intrusive_ptr<CFConvHolder>& self) -> std::string {
+                torch::serialize::OutputArchive ar;
+                ar.write("gaussianWidth", self->gaussianWidth); ar.write("activation", self->activation);
+                ar.write("weights1", self->weights1.cpu()); ar.write("biases1", self->biases1.cpu());
+                ar.write("weights2", self->weights2.cpu()); ar.write("biases2", self->biases2.cpu());
+                std::stringstream ss;
+                ar.save_to(ss);
+                return ss.str();
             },
-            [](std::tuple<double, std::string, Tensor, Tensor, Tensor, Tensor> st) -> c10::intrusive_ptr<CFConvHolder> {
-                return c10::make_intrusive<CFConvHolder>(std::get<0>(st), std::get<1>(st), std::get<2>(st), std::get<3>(st), std::get<4>(st),
-                                                         std::get<5>(st));
+            [](const std::string& state) -> c10::intrusive_ptr<CFConvHolder> {
+                std::stringstream ss(state);
+                torch::serialize::InputArchive ar;
+                ar.load_from(ss, torch::kCPU);
+                torch::IValue gaussianWidth, activation;
+                Tensor w1, b1, w2, b2;
+                ar.read("gaussianWidth", gaussianWidth); ar.read("activation", activation);
+                ar.read("weights1", w1); ar.read("biases1", b1); ar.read("weights2", w2); ar.read("biases2", b2);
+                return c10::make_intrusive<CFConvHolder>(gaussianWidth.toDouble(), activation.toStringRef(), w1, b1, w2, b2);
             });
     m.def("operation", cfconv_operation);
 }

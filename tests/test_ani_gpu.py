@@ -358,7 +358,7 @@ def test_neighbour_rows_grow_instead_of_truncating():
     from nnpops_b200.OptimizedTorchANI import FusedANI
     from nnpops_b200.SymmetryFunctions import Holder
     n = 400
-    pos, L = lattice(n, 1.5, 0.3, 123)              # 0.3 atoms / A^3: about 53 angular neighbours on average, more than 64 for some
+    pos, L = lattice(n, 1.25, 0.3, 123)             # 0.4 atoms / A^3: about 72 angular neighbours on average, more than the default 64
     species = np.random.default_rng(4).integers(0, 2, n).astype(np.int32)
     box = cubic_box(L)
     rfn, afn = ani2x_tables()
@@ -380,7 +380,7 @@ def test_neighbour_rows_grow_instead_of_truncating():
     with pytest.raises(RuntimeError, match="overflowed"):
         m.energy_and_gradient(dev(pos), dev(box))
     big = FusedANI(2, 5.1, 3.5, ANI2X["EtaR"], ANI2X["ShfR"], ANI2X["EtaA"], ANI2X["Zeta"], ANI2X["ShfA"], ANI2X["ShfZ"], species, nets,
-                   max_angular_neighbors=160)
+                   max_radial_neighbors=512, max_angular_neighbors=192)
     big.energy_and_gradient(dev(pos), dev(box))
     torch.cuda.synchronize()
     big.energy_and_gradient(dev(pos), dev(box))

@@ -39,3 +39,33 @@ def test_module_chain():
     e = float(energy.detach().cpu().double()[0])
     assert abs(e - e_ref) < 5e-6 * abs(e_ref)
     assert rel_err(p.grad.cpu().numpy()[0], g_ref) < 1e-5
+
+
+def test_batch_of_conformers():
+    """the scalable modules take a batch of conformers of one system, coordinates [B, N, 3] -> energies [B] (the
+    reference raises at B > 1, SymmetryFunctions.py:110-111); energies and autograd forces equal the one-at-a-time evaluations, also
+    through the TorchScript class."""
+    from nnpops_b200.OptimizedTorchANI import OptimizedTorchANI, ScriptableFusedANI
+    n, B = 46, 3
+    species = np.random.default_rng(3).integers(0, 7, n)
+    model = Model(HIDDEN, 2, seed=5)
+    numbers = torch.tensor([[model.species_converter.ELEMENTS[s] for s in species]])
+    confs = np.stack([lattice(n, 1.9, 0.3, 100 + b)[0] for b in range(B)])
+    nnp = OptimizedTorchANI(model, numbers.cuda())
+    p = torch.tensor(confs, device="cuda", requires_grad=True)
+    out = nnp((numbers.cuda().expand(B, -1), p))
+    assert out.energies.shape == (B,) and out.species.shape == (B, n)
+    out.energies.sum().backward()
+    for b in range(B):
+        q = torch.tensor(confs[b:b + 1], device="cuda", requires_grad=True)
+        e = nnp((numbers.cuda(), q)).energies
+        e.sum().backward()
+        assert abs(float(e[0]) - float(out.energies[b])) <= 1e-9 * abs(float(e[0]))
+        assert rel_err(p.grad[b].cpu().numpy(), q.grad[0].cpu().numpy()) < 1e-6
+    nets = model.networks_numpy()
+    sm = torch.jit.script(ScriptableFusedANI(7, 5.1, 3.5, ANI2X["EtaR"], ANI2X["ShfR"], ANI2X["EtaA"], ANI2X["Zeta"], ANI2X["ShfA"], ANI2X["ShfZ"],
+                                             [int(s) for s in species], nets))
+    eb = sm(torch.tensor(confs, device="cuda"), None)
+    sae = float(model.energy_shifter.sae(torch.tensor(species)[None])[0])
+    assert eb.shape == (B,)
+    assert np.allclose(eb.double().cpu().numpy() + sae, out.energies.detach().cpu().numpy(), rtol=1e-6)
