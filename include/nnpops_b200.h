@@ -100,6 +100,8 @@ NNPOPS_API int nnpops_ani_model_work(nnpops_ani_model_t h, long long* triples, l
 /* mlp_flops_forward above counts the network on the model's full AEV length (the algorithmic figure).  The fused model evaluates
  * the AEV and the first layer only on the columns whose neighbour species occur in the system (the others are identically zero):
  * aev_length = full length, active_features = columns kept, mlp_flops_forward_executed = flops actually issued per forward. */
+/* *fused = 1 when the network runs as the one-kernel layer chain (csrc/mlp_chain.cu), 0 for the per-layer GEMM launches */
+NNPOPS_API int nnpops_ani_model_mlp_fused(nnpops_ani_model_t h, int* fused);
 NNPOPS_API int nnpops_ani_model_info(nnpops_ani_model_t h, int* aev_length, int* active_features, double* mlp_flops_forward_executed);
 NNPOPS_API int nnpops_ani_model_overflowed(nnpops_ani_model_t h, int* flags);
 NNPOPS_API int nnpops_ani_model_overflow_poll(nnpops_ani_model_t h, int* flags, int* max_radial_neighbors, int* max_angular_neighbors);
@@ -205,6 +207,8 @@ NNPOPS_API int nnpops_cfconv_backprop(nnpops_cfconv_t h, nnpops_cfconv_neighbors
 
 /* development aid: mean milliseconds of one tcgen05 GEMM shape (C[m, batch*n] = A.B^T per batch member) on synthetic operands;
  * mode = epilogue (0 fp32, 1 bias+CELU, 2 celu' mask, 3 last hidden layer); streaming != 0 disables the resident-B variant */
+/* measured fp32 FMA throughput of the current device in TFLOP/s (denominator of the AEV kernels' arithmetic roofline) */
+NNPOPS_API int nnpops_debug_fma_peak(double* tflops);
 NNPOPS_API int nnpops_debug_gemm_bench(int m, int n, int k, int batch, int mode, int streaming, int iters, double* ms);
 
 #ifdef __cplusplus

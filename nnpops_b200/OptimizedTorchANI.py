@@ -166,8 +166,10 @@ class FusedANI(torch.nn.Module):
         check(lib.nnpops_ani_model_work(self._h, C.byref(t), C.byref(p), C.byref(fl), current_stream(self.device_)))
         full, active, ex = C.c_int(0), C.c_int(0), C.c_double(0)
         check(lib.nnpops_ani_model_info(self._h, C.byref(full), C.byref(active), C.byref(ex)))
+        fused = C.c_int(0)
+        check(lib.nnpops_ani_model_mlp_fused(self._h, C.byref(fused)))
         return {"triples": t.value, "radial_pairs": p.value, "mlp_flops_forward": fl.value, "aev_length": full.value,
-                "active_features": active.value, "mlp_flops_forward_executed": ex.value}
+                "active_features": active.value, "mlp_flops_forward_executed": ex.value, "mlp_fused": bool(fused.value)}
 
     STAGES = ("cells+rows", "radial_fwd", "angular_fwd", "mlp_fwd", "mlp_bwd", "radial_bwd", "angular_bwd")
 

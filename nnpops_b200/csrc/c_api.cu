@@ -1,5 +1,6 @@
 // extern "C" boundary of libnnpops_b200.so; see include/nnpops_b200.h for the contract of every entry point.
 #include "../../include/nnpops_b200.h"
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include "ani_model.cuh"
@@ -278,6 +279,13 @@ int nnpops_ani_model_work(nnpops_ani_model_t h, long long* triples, long long* r
     });
 }
 
+int nnpops_ani_model_mlp_fused(nnpops_ani_model_t h, int* fused) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl && fused, "invalid argument");
+        *fused = h->impl->mlp().fused() ? 1 : 0;
+    });
+}
+
 int nnpops_ani_model_info(nnpops_ani_model_t h, int* aev_length, int* active_features, double* mlp_flops_forward_executed) {
     return guarded([&] {
         NNP_REQUIRE(h && h->impl, "invalid handle");
@@ -478,6 +486,50 @@ int nnpops_cfconv_backprop(nnpops_cfconv_t h, nnpops_cfconv_neighbors_t neighbor
     return guarded([&] {
         NNP_REQUIRE(h && h->impl && neighbors && neighbors->impl, "invalid handle");
         cfconv_backprop(h->impl, neighbors->impl, input, output_grad, input_grad, position_grad, (cudaStream_t)stream);
+    });
+}
+
+// fp32 FMA throughput of the device, measured: the denominator of the AEV kernels' arithmetic roofline (bench.py reports it next to the
+// figure derived from SM count x 128 lanes x 2 x clock).  8 independent FMA chains per thread, 2048 threads per SM.
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 12345.678f) out[0] = s;   // never true: keeps the chains alive
+}
+
+int nnpops_debug_fma_peak(double* tflops) {
+    return guarded([&] {
+        require_device();
+        NNP_REQUIRE(tflops != nullptr, "tflops must not be NULL");
+        int dev = 0, sms = 0;
+        NNP_CUDA_CHECK(cudaGetDevice(&dev));
+        NNP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        float* out = nullptr;
+        NNP_CUDA_CHECK(cudaMalloc(&out, sizeof(float)));
+        const int iters = 4096, grid = sms * 8;
+        cudaEvent_t e0, e1;
+        NNP_CUDA_CHECK(cudaEventCreate(&e0)); NNP_CUDA_CHECK(cudaEventCreate(&e1));
+        fma_peak_kernel<<<grid, 256>>>(out, 64, 0.999f, 0.001f);   // warm-up
+        double best = 0.0;
+        for (int rep = 0; rep < 5; rep++) {
+            NNP_CUDA_CHECK(cudaEventRecord(e0));
+            fma_peak_kernel<<<grid, 256>>>(out, iters, 0.999f, 0.001f);
+            NNP_CUDA_CHECK(cudaEventRecord(e1));
+            NNP_CUDA_CHECK(cudaEventSynchronize(e1));
+            float ms = 0.0f;
+            NNP_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+            const double flops = 2.0 * 8 * 16 * (double)iters * 256.0 * grid;
+            best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+        *tflops = best;
     });
 }
 
