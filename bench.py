@@ -225,6 +225,13 @@ def run_ours(args):
         sustained = {"value": round(world * reps / (s_ms / 1e3), 4), "unit": UNIT, "steps": reps, "seconds": round(s_ms / 1e3, 3),
                      "clocks": s_sampler.stop() if rank == 0 else None}
 
+    # ---- N > 1: the strong-scaling curve that matters -- ONE box over all GPUs by spatial decomposition with ghost halos
+    box = None
+    if world > 1 and not args.no_box:
+        del model
+        torch.cuda.empty_cache()
+        box = measure_box(args, dist, dev, nets, rank, world, local)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -320,6 +327,8 @@ def run_ours(args):
         "clocks": clocks,
         "sustained": sustained,
     }
+    if box is not None:
+        out["box"] = box
     if fp32_measured:
         out["fp32_fma_peak_measured_tflops"] = fp32_measured
     if world == 1 and not args.no_cpu_baseline:
@@ -362,13 +371,58 @@ def forces_check(nets, mlp_impl, local, n_atoms=6000):
             "energy_rel": abs(e - e0) / abs(e0), "tolerance": 1e-5}
 
 
-def run_box(args):
-    """One 50 000-atom box evaluated cooperatively by all ranks (variant ii): strong scaling.  Every rank holds the
-    positions; a step = owned-centre AEV + MLP + backward on every rank, then ONE NCCL all-reduce of the packed gradient + energy."""
+def measure_box(args, dist, dev, nets, rank, world, local):
+    """ONE box evaluated cooperatively by all ranks: spatial domain decomposition into bricks with ghost-atom halos (SURVEY 8e
+    variant i, nnpops_b200/halo.py) -- strong scaling.  Every rank keeps the positions of ITS atoms on its device; a step = forward
+    halo (grouped NCCL send/recv of ghost positions) -> brick-local fused model -> reverse halo (ghost gradient rows back to the
+    owners) -> all-reduce of the energy.  Device-event time, MAX over ranks."""
     import torch
-    from systems import ANI2X, ANI2X_HIDDEN, ANI2X_ENSEMBLE, water_species
+    from systems import ANI2X, water_species
+    from nnpops_b200.halo import HaloBoxANI
+    n = args.atoms
+    species = water_species(n)
+    pool = 2
+    models, pos_own, boxes = [], [], []
+    for c in range(pool):                                   # the SAME conformers on every rank; one halo plan + local model per conformer
+        pos, box = make_conformer(n, c)
+        m = HaloBoxANI(7, 5.2, ANI2X["Rca"], ANI2X["EtaR"], ANI2X["ShfR"], ANI2X["EtaA"], ANI2X["Zeta"], ANI2X["ShfA"], ANI2X["ShfZ"], species,
+                       nets, pos, box, mlp_impl=args.mlp, device="cuda:%d" % local)
+        models.append(m)
+        pos_own.append(torch.tensor(pos[m.plan.owned[rank]], device=dev))
+        boxes.append(torch.tensor(box, device=dev))
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        e, g = models[i % pool].energy_and_gradient(pos_own[i % pool], boxes[i % pool])
+    sync_all()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        e, g = models[i % pool].energy_and_gradient(pos_own[i % pool], boxes[i % pool])
+    t1.record()
+    sync_all()
+    ms_total = max_over_ranks(t0.elapsed_time(t1), dist, dev)
+    counts = torch.tensor([models[0].n_owned, models[0].n_ghost, models[0].halo_bytes_forward + models[0].halo_bytes_reverse], dtype=torch.float64, device=dev)
+    mx = counts.clone()
+    if dist is not None:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    return {"value": round(args.steps / (ms_total / 1e3), 4), "unit": UNIT, "ms_per_step": round(ms_total / args.steps, 4), "scaling": "strong",
+            "decomposition": "bricks %s with ghost halos of Rcr = 5.2 A, one brick per GPU" % (models[0].plan.grid,),
+            "atoms_owned_max": int(mx[0]), "ghost_atoms_max": int(mx[1]), "halo_bytes_per_step_per_gpu_max": int(mx[2]),
+            "collectives": "2 grouped ncclSend/ncclRecv phases (positions out, ghost gradient rows back) + 1 scalar all-reduce per step",
+            "energy": float(e.cpu()[0])}
+
+
+def run_box(args):
+    """--mode box: only the strong-scaling measurement of ONE box (see measure_box), as its own JSON line."""
+    import torch
+    from systems import ANI2X_HIDDEN, ANI2X_ENSEMBLE
     from mlp_ref import random_networks
-    from nnpops_b200.OptimizedTorchANI import ShardedFusedANI
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dist = None
@@ -377,45 +431,21 @@ def run_box(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    n = args.atoms
     nets = random_networks(7, ANI2X_HIDDEN, ANI2X_ENSEMBLE, 1008, seed=42)
-    model = ShardedFusedANI(7, 5.2, ANI2X["Rca"], ANI2X["EtaR"], ANI2X["ShfR"], ANI2X["EtaA"], ANI2X["Zeta"], ANI2X["ShfA"], ANI2X["ShfZ"],
-                            water_species(n), nets, mlp_impl=args.mlp, device="cuda:%d" % local)
-    pool = 4
-    confs = [make_conformer(n, c) for c in range(pool)]            # the SAME conformers on every rank
-    d_pos = [torch.tensor(p, device=dev) for p, _ in confs]
-    d_box = [torch.tensor(b, device=dev) for _, b in confs]
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    for i in range(args.warmup):
-        e, g = model.energy_and_gradient(d_pos[i % pool], d_box[i % pool])
-    sync_all()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for i in range(args.steps):
-        e, g = model.energy_and_gradient(d_pos[i % pool], d_box[i % pool])
-    t1.record()
-    sync_all()
+    box = measure_box(args, dist, dev, nets, rank, world, local)
     clocks = sampler.stop() if rank == 0 else None
-    ms_total = max_over_ranks(t0.elapsed_time(t1), dist, dev)
     if rank == 0:
         args.quiet.restore()
         print(json.dumps({
-            "metric": METRIC, "value": round(args.steps / (ms_total / 1e3), 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ONE %d-atom periodic water box per step sharded over %d GPU(s): centres i %% world == rank per GPU, all "
-                                   "atoms as neighbour candidates, one all-reduce (NCCL) of 12 N + 4 bytes per step" % (n, world),
-                       "atoms": n, "mode": "box", "mlp_impl": args.mlp, "allreduce_bytes_per_step": 12 * n + 4},
-            "energy": float(e.cpu()[0]), "clocks": clocks}), flush=True)
+            "metric": METRIC, "value": box["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": box["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "ONE %d-atom periodic water box per step over %d GPU(s): %s" % (args.atoms, world, box["decomposition"]),
+                       "atoms": args.atoms, "mode": "box", "mlp_impl": args.mlp},
+            "box": box, "clocks": clocks}), flush=True)
     if dist is not None:
         os.dup2(2, 1)
         dist.destroy_process_group()
@@ -578,10 +608,11 @@ def main():
     ap.add_argument("--atoms", type=int, default=50000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sustain", type=float, default=3.0, help="seconds of the extra sustained leg (0 = skip)")
+    ap.add_argument("--no-box", action="store_true", help="N > 1: skip the extra one-box strong-scaling measurement")
     ap.add_argument("--no-model-check", action="store_true", help="--impl reference: skip the one real full-size AEV evaluation (~80 s)")
     ap.add_argument("--mode", default="conformers", choices=["conformers", "box"],
-                    help="conformers: independent conformers per GPU, no collective (BASELINE config 3, the default); box: ONE box "
-                         "sharded over the GPUs (owned centres per rank, one all-reduce of energy + gradient per step: strong scaling)")
+                    help="conformers: independent conformers per GPU, no collective (BASELINE config 3, the default; with N > 1 the line "
+                         "also carries a \"box\" key); box: only ONE box over the GPUs by bricks with ghost halos (strong scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -82,6 +82,14 @@ NNPOPS_API int nnpops_ani_model_create_sharded(nnpops_ani_model_t* out, int num_
                             const int* atom_species, int n_radial, const float* radial_fn, int n_angular, const float* angular_fn,
                             int ensemble_size, int num_layers, const int* dims, const float* params, int mlp_impl,
                             int max_radial_neighbors, int max_angular_neighbors, int shard_rank, int shard_count);
+/* Spatial domain decomposition (one box over several GPUs, SURVEY.md section 8e variant i): the model of ONE rank's brick.  The atoms are
+ * the brick's own atoms plus the ghost atoms within the radial cutoff around it; owned[i] != 0 marks the atoms whose AEV and network
+ * this rank evaluates (host unsigned char [num_atoms]).  Energy and dE/dx are PARTIAL: the gradient rows of the ghosts go back to their
+ * owners and the energies are summed (nnpops_b200.OptimizedTorchANI.HaloBoxANI does both over NCCL).  The reference is single-device. */
+NNPOPS_API int nnpops_ani_model_create_owned(nnpops_ani_model_t* out, int num_atoms, int num_species, float radial_cutoff, float angular_cutoff,
+                                  const int* atom_species, int n_radial, const float* radial_fn, int n_angular, const float* angular_fn,
+                                  int ensemble_size, int num_layers, const int* dims, const float* params, int mlp_impl,
+                                  int max_radial_neighbors, int max_angular_neighbors, const unsigned char* owned);
 NNPOPS_API void nnpops_ani_model_destroy(nnpops_ani_model_t h);
 /* energy: device float[1] (sum over atoms of the ensemble-mean atomic energies, no self-energy shift);
  * position_grad: device float [num_atoms][3] = dE/dx */

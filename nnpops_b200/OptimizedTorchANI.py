@@ -67,7 +67,7 @@ class FusedANI(torch.nn.Module):
 
     def __init__(self, num_species: int, Rcr: float, Rca: float, EtaR, ShfR, EtaA, Zeta, ShfA, ShfZ, species: Sequence[int],
                  networks, mlp_impl: str = "tcgen05", device: str = "cuda", max_radial_neighbors: int = 0,
-                 max_angular_neighbors: int = 0, shard: Tuple[int, int] = (0, 1)):
+                 max_angular_neighbors: int = 0, shard: Tuple[int, int] = (0, 1), owned: Optional[Sequence[int]] = None):
         super().__init__()
         self.num_atoms = len(species)
         self.num_species = int(num_species)
@@ -79,10 +79,20 @@ class FusedANI(torch.nn.Module):
         sp = np.ascontiguousarray(species, np.int32)
         h = C.c_void_p()
         with torch.cuda.device(self.device_):
-            check(lib.nnpops_ani_model_create_sharded(C.byref(h), self.num_atoms, self.num_species, float(Rcr), float(Rca), ptr(sp),
-                                                      len(radial_fn), ptr(radial_fn), len(angular_fn), ptr(angular_fn), len(networks[0]),
-                                                      dims.shape[1] - 1, ptr(dims), ptr(params), {"simt": 0, "tcgen05": 1}[mlp_impl],
-                                                      max_radial_neighbors, max_angular_neighbors, int(shard[0]), int(shard[1])))
+            if owned is not None:
+                # spatial decomposition (nnpops_b200.halo.HaloBoxANI): the atoms are a brick's own atoms + its ghosts; only the atoms with
+                # owned[i] != 0 are centres, energy and gradient are this rank's PARTIAL results
+                mask = np.ascontiguousarray(owned, np.uint8)
+                assert mask.shape == (self.num_atoms,)
+                check(lib.nnpops_ani_model_create_owned(C.byref(h), self.num_atoms, self.num_species, float(Rcr), float(Rca), ptr(sp),
+                                                        len(radial_fn), ptr(radial_fn), len(angular_fn), ptr(angular_fn), len(networks[0]),
+                                                        dims.shape[1] - 1, ptr(dims), ptr(params), {"simt": 0, "tcgen05": 1}[mlp_impl],
+                                                        max_radial_neighbors, max_angular_neighbors, ptr(mask)))
+            else:
+                check(lib.nnpops_ani_model_create_sharded(C.byref(h), self.num_atoms, self.num_species, float(Rcr), float(Rca), ptr(sp),
+                                                          len(radial_fn), ptr(radial_fn), len(angular_fn), ptr(angular_fn), len(networks[0]),
+                                                          dims.shape[1] - 1, ptr(dims), ptr(params), {"simt": 0, "tcgen05": 1}[mlp_impl],
+                                                          max_radial_neighbors, max_angular_neighbors, int(shard[0]), int(shard[1])))
         self.shard = (int(shard[0]), int(shard[1]))
         self._h = h
         self.mlp_impl = mlp_impl

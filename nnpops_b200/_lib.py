@@ -27,6 +27,7 @@ _SIGS = {
     "nnpops_ani_work": [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _vp],
     "nnpops_ani_model_create": [C.POINTER(_vp), _i, _i, _f, _f, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _i],
     "nnpops_ani_model_create_sharded": [C.POINTER(_vp), _i, _i, _f, _f, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i],
+    "nnpops_ani_model_create_owned": [C.POINTER(_vp), _i, _i, _f, _f, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp],
     "nnpops_ani_model_energy_grad": [_vp, _vp, _vp, _vp, _vp, _vp],
     "nnpops_ani_model_energy_grad_host": [_vp, _vp, _vp, _vp, _vp, _vp],
     "nnpops_ani_model_buffers": [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i), _vp],

@@ -38,14 +38,18 @@ void AniModel::readFeatures(int which, float* out, cudaStream_t stream) {
 // columns, a 5-element protein 560.  NNPOPS_DENSE_AEV=1 (or compact = false) disables it.
 AniModel::AniModel(int numAtoms, int numSpecies, float rcr, float rca, const int* atomSpecies, int nRadial, const float* radialFn,
                    int nAngular, const float* angularFn, int ensemble, int numLayers, const int* dims, const float* params,
-                   int maxRadialNeighbors, int maxAngularNeighbors, bool compact, int shardRank, int shardCount)
+                   int maxRadialNeighbors, int maxAngularNeighbors, bool compact, int shardRank, int shardCount, const unsigned char* ownedMask)
     : n_(numAtoms) {
     NNP_REQUIRE(numSpecies >= 1 && numSpecies <= kAniMaxSpecies, "unsupported number of species");
     NNP_REQUIRE(shardCount >= 1 && shardRank >= 0 && shardRank < shardCount, "shard rank must be in [0, shard count)");
     // One box sharded over several GPUs: atom i is a CENTRE of rank i mod shardCount (interleaved ownership balances species and
     // density without any knowledge of the geometry); every atom stays a neighbour candidate on every rank.
+    // Spatial decomposition with ghost halos passes the ownership explicitly: the atoms of this rank's brick are centres, the ghosts
+    // around it are neighbour candidates only (ownedMask, host [numAtoms]).
     std::vector<unsigned char> owned(numAtoms > 0 ? numAtoms : 1, 1);
-    if (shardCount > 1)
+    if (ownedMask != nullptr)
+        for (int i = 0; i < numAtoms; i++) owned[i] = ownedMask[i] ? 1 : 0;
+    else if (shardCount > 1)
         for (int i = 0; i < numAtoms; i++) owned[i] = (i % shardCount == shardRank) ? 1 : 0;
     const int S = numSpecies, L = numLayers;
     const int nFeatFull = S * nRadial + S * (S + 1) / 2 * nAngular;
@@ -123,7 +127,7 @@ AniModel::AniModel(int numAtoms, int numSpecies, float rcr, float rca, const int
     // centres of other ranks have empty neighbour rows; whatever the AEV kernels store for them lands in the spare row nOwned
     for (int i = 0; i < numAtoms; i++) rowOfAtom_[i] = owned[i] ? cursor[speciesC[i]]++ : nOwned;
     const size_t na = (size_t)nOwned + 1;
-    if (shardCount > 1) {
+    if (shardCount > 1 || ownedMask != nullptr) {
         NNP_CUDA_CHECK(cudaMalloc(&owned_, owned.size()));
         NNP_CUDA_CHECK(cudaMemcpy(owned_, owned.data(), owned.size(), cudaMemcpyHostToDevice));
     }

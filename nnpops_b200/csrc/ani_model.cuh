@@ -12,7 +12,8 @@ class AniModel {
 public:
     AniModel(int numAtoms, int numSpecies, float rcr, float rca, const int* atomSpecies, int nRadial, const float* radialFn,
              int nAngular, const float* angularFn, int ensemble, int numLayers, const int* dims, const float* params,
-             int maxRadialNeighbors, int maxAngularNeighbors, bool compact = true, int shardRank = 0, int shardCount = 1);
+             int maxRadialNeighbors, int maxAngularNeighbors, bool compact = true, int shardRank = 0, int shardCount = 1,
+             const unsigned char* ownedMask = nullptr);
     ~AniModel();
     // energy: device float[1]; positionGrad: device [n][3] = dE/dx (forces = -positionGrad)
     void energyAndGradient(const float* positions, const float* box, float* energy, float* positionGrad, cudaStream_t stream);

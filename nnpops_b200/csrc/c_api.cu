@@ -188,6 +188,28 @@ int nnpops_ani_model_create_sharded(nnpops_ani_model_t* out, int num_atoms, int 
     });
 }
 
+int nnpops_ani_model_create_owned(nnpops_ani_model_t* out, int num_atoms, int num_species, float radial_cutoff, float angular_cutoff,
+                                  const int* atom_species, int n_radial, const float* radial_fn, int n_angular, const float* angular_fn,
+                                  int ensemble_size, int num_layers, const int* dims, const float* params, int mlp_impl,
+                                  int max_radial_neighbors, int max_angular_neighbors, const unsigned char* owned) {
+    return guarded([&] {
+        require_device();
+        NNP_REQUIRE(out != nullptr && owned != nullptr, "out and owned must not be NULL");
+        auto* h = new nnpops_ani_model;
+        try {
+            h->impl = new AniModel(num_atoms, num_species, radial_cutoff, angular_cutoff, atom_species, n_radial, radial_fn, n_angular,
+                                   angular_fn, ensemble_size, num_layers, dims, params, max_radial_neighbors, max_angular_neighbors, true, 0, 1,
+                                   owned);
+            h->impl->mlp().setImpl(mlp_impl == 1 ? MlpImpl::Tcgen05 : MlpImpl::Simt);
+            h->n = num_atoms;
+        } catch (...) {
+            delete h;
+            throw;
+        }
+        *out = h;
+    });
+}
+
 void nnpops_ani_model_destroy(nnpops_ani_model_t h) {
     if (!h) return;
     if (h->graphExec) cudaGraphExecDestroy(h->graphExec);

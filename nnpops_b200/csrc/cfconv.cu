@@ -92,7 +92,7 @@ __global__ void cf_scan_kernel(const int* __restrict__ counts, int n, int* __res
 // One CTA per table point r_p = p*h: Gaussians -> dense1 -> activation -> dense2 -> cutoff, value and d/dr, in fp64.
 __global__ void cf_table_kernel(int P, int W, int G, double rc, double sigma, int activation, const float* __restrict__ w1,
                                 const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2, double h,
-                                float* __restrict__ tabF, float* __restrict__ tabD) {
+                                double* __restrict__ tabF64, float* __restrict__ tabD) {
     extern __shared__ double sh[];
     double *gs = sh, *dgs = gs + G, *y1 = dgs + G, *dy1 = y1 + W;
     const int p = blockIdx.x;
@@ -116,9 +116,19 @@ __global__ void cf_table_kernel(int P, int W, int G, double rc, double sigma, in
     for (int i = threadIdx.x; i < W; i += blockDim.x) {
         double s = b2[i], ds = 0;
         for (int j = 0; j < W; j++) { s += y1[j] * (double)w2[(size_t)i * W + j]; ds += dy1[j] * (double)w2[(size_t)i * W + j]; }
-        tabF[(size_t)p * W + i] = (float)(fc * s);
+        tabF64[(size_t)p * W + i] = fc * s;
         tabD[(size_t)p * W + i] = (float)((dfc * s + fc * ds) * h);   // derivative pre-multiplied by the grid spacing
     }
+}
+
+// fp32 value table and the table of forward differences G[p] = f[p + 1] - f[p], formed in fp64.  The interpolant is evaluated as
+// f0 + h01 * G + ... and its derivative as g01 * G + ...: with f1 - f0 taken from two rounded fp32 entries instead, the derivative
+// (the force) loses |f| * eps / h to cancellation -- 1.5e-5 of the position gradient at h = sigma / 32, 6e-5 at sigma / 128.
+__global__ void cf_table_finish_kernel(int P, int W, const double* __restrict__ tabF64, float* __restrict__ tabF, float* __restrict__ tabG) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)P * W) return;
+    tabF[i] = (float)tabF64[i];
+    tabG[i] = i + W < (size_t)P * W ? (float)(tabF64[i + W] - tabF64[i]) : 0.0f;
 }
 
 // ------------------------------------------------------------------------------------------------------------------ compute
@@ -133,9 +143,10 @@ __device__ __forceinline__ Hermite hermite(float r, float invH, int P) {
     const float t = r * invH;
     b.idx = min((int)t, P - 2);
     const float u = t - (float)b.idx, u2 = u * u, om = 1.0f - u;
-    b.h00 = (1.0f + 2.0f * u) * om * om; b.h10 = u * om * om; b.h01 = u2 * (3.0f - 2.0f * u); b.h11 = u2 * (u - 1.0f);
-    b.g00 = (6.0f * u2 - 6.0f * u) * invH; b.g10 = (3.0f * u2 - 4.0f * u + 1.0f) * invH;
-    b.g01 = -b.g00; b.g11 = (3.0f * u2 - 2.0f * u) * invH;
+    // h00 = 1 - h01 and g00 = -g01: the value is f0 + h01 (f1 - f0) + h10 d0 + h11 d1 with the difference read from its own table
+    b.h00 = 1.0f; b.h10 = u * om * om; b.h01 = u2 * (3.0f - 2.0f * u); b.h11 = u2 * (u - 1.0f);
+    b.g00 = 0.0f; b.g10 = (3.0f * u2 - 4.0f * u + 1.0f) * invH;
+    b.g01 = (6.0f * u - 6.0f * u2) * invH; b.g11 = (3.0f * u2 - 2.0f * u) * invH;
     return b;
 }
 
@@ -145,7 +156,7 @@ template <int KF>
 __global__ void __launch_bounds__(kWPB * 32)
 cf_forward_kernel(int n, int W, const float4* __restrict__ sorted, const int* __restrict__ sortedOrig, const Geom* __restrict__ geom,
                   const int* __restrict__ rowPtr, const int* __restrict__ nbr, const float* __restrict__ tabF, const float* __restrict__ tabD,
-                  float invH, int P, const float* __restrict__ x, float* __restrict__ out) {
+                  const float* __restrict__ tabG, float invH, int P, const float* __restrict__ x, float* __restrict__ out) {
     __shared__ Geom g;
     if (threadIdx.x == 0) g = *geom;
     __syncthreads();
@@ -177,12 +188,13 @@ cf_forward_kernel(int n, int W, const float4* __restrict__ sorted, const int* __
                 const Hermite hb = hermite(rt, invH, P);
                 const float* f0 = tabF + (size_t)hb.idx * W;
                 const float* d0 = tabD + (size_t)hb.idx * W;
+                const float* g0 = tabG + (size_t)hb.idx * W;
                 const float* xr = x + (size_t)ot * W;
 #pragma unroll
                 for (int k = 0; k < KF; k++) {
                     const int c = c0 + lane + 32 * k;
                     if (c < W) {
-                        const float f = hb.h00 * f0[c] + hb.h10 * d0[c] + hb.h01 * f0[W + c] + hb.h11 * d0[W + c];
+                        const float f = f0[c] + hb.h10 * d0[c] + hb.h01 * g0[c] + hb.h11 * d0[W + c];
                         acc[k] = fmaf(f, xr[c], acc[k]);
                     }
                 }
@@ -202,7 +214,7 @@ template <int KF>
 __global__ void __launch_bounds__(kWPB * 32)
 cf_backward_kernel(int n, int W, const float4* __restrict__ sorted, const int* __restrict__ sortedOrig, const Geom* __restrict__ geom,
                    const int* __restrict__ rowPtr, const int* __restrict__ nbr, const float* __restrict__ tabF, const float* __restrict__ tabD,
-                   float invH, int P, const float* __restrict__ x, const float* __restrict__ go, float* __restrict__ inputGrad,
+                   const float* __restrict__ tabG, float invH, int P, const float* __restrict__ x, const float* __restrict__ go, float* __restrict__ inputGrad,
                    float* __restrict__ posGrad) {
     __shared__ Geom g;
     if (threadIdx.x == 0) g = *geom;
@@ -244,6 +256,7 @@ cf_backward_kernel(int n, int W, const float4* __restrict__ sorted, const int* _
                 const Hermite hb = hermite(rt, invH, P);
                 const float* f0 = tabF + (size_t)hb.idx * W;
                 const float* d0 = tabD + (size_t)hb.idx * W;
+                const float* g0 = tabG + (size_t)hb.idx * W;
                 const float* xr = x + (size_t)ot * W;
                 const float* gr = go + (size_t)ot * W;
                 float wsum = 0.0f;
@@ -251,9 +264,9 @@ cf_backward_kernel(int n, int W, const float4* __restrict__ sorted, const int* _
                 for (int k = 0; k < KF; k++) {
                     const int c = c0 + lane + 32 * k;
                     if (c < W) {
-                        const float a0 = f0[c], a1 = d0[c], a2 = f0[W + c], a3 = d0[W + c];
-                        const float f = hb.h00 * a0 + hb.h10 * a1 + hb.h01 * a2 + hb.h11 * a3;
-                        const float df = hb.g00 * a0 + hb.g10 * a1 + hb.g01 * a2 + hb.g11 * a3;
+                        const float a0 = f0[c], a1 = d0[c], a2 = g0[c], a3 = d0[W + c];   // f[p], h f'[p], f[p + 1] - f[p], h f'[p + 1]
+                        const float f = a0 + hb.h10 * a1 + hb.h01 * a2 + hb.h11 * a3;
+                        const float df = hb.g10 * a1 + hb.g01 * a2 + hb.g11 * a3;
                         const float gj = gr[c];
                         acc[k] = fmaf(f, gj, acc[k]);
                         wsum = fmaf(df, xr[c] * gi[k] + xi[k] * gj, wsum);
@@ -340,10 +353,9 @@ public:
         NNP_REQUIRE(width > 0 && numGaussians > 1, "width must be positive and numGaussians > 1");
         NNP_REQUIRE(cutoff > 0 && gaussianWidth > 0, "cutoff and gaussianWidth must be positive");
         NNP_REQUIRE(activation == 0 || activation == 1, "activation must be 0 (shifted softplus) or 1 (tanh)");
-        // table step = sigma / 128: the cubic Hermite value error goes as h^4 and the error of its derivative (the force) as h^3; at
-        // sigma / 32 the position gradient of the 100 000-atom box was 1.5e-5 off the fp64 oracle, at sigma / 128 it is 64 x closer
-        // (6 401 rows x W for sigma 0.2 / cutoff 10: still L2-resident)
-        const int pps = pointsPerSigma > 0 ? pointsPerSigma : 128;
+        // table step = sigma / 64: the cubic Hermite value error goes as h^4, the error of its derivative (the force) as h^3
+        // (3 201 rows x W x 3 tables for sigma 0.2 / cutoff 10: L2-resident)
+        const int pps = pointsPerSigma > 0 ? pointsPerSigma : 64;
         long long P = (long long)std::ceil((double)pps * cutoff / gaussianWidth) + 1;
         if (P < 256) P = 256;
         if (P > 65536) P = 65536;
@@ -352,24 +364,29 @@ public:
         invH_ = (float)(1.0 / h);
         NNP_CUDA_CHECK(cudaMalloc(&tabF_, sizeof(float) * (size_t)P_ * W_));
         NNP_CUDA_CHECK(cudaMalloc(&tabD_, sizeof(float) * (size_t)P_ * W_));
+        NNP_CUDA_CHECK(cudaMalloc(&tabG_, sizeof(float) * (size_t)P_ * W_));
+        double* f64 = nullptr;
+        NNP_CUDA_CHECK(cudaMalloc(&f64, sizeof(double) * (size_t)P_ * W_));
         const size_t smem = sizeof(double) * (2 * (size_t)G_ + 2 * (size_t)W_);
         NNP_REQUIRE(smem <= 48 * 1024, "width/numGaussians too large for the filter-table kernel");
         // one-time set-up on the legacy default stream: the weights may have been staged on a non-blocking stream of the caller, which
         // the default stream does not order against, so wait for the whole device first
         NNP_CUDA_CHECK(cudaDeviceSynchronize());
-        cf_table_kernel<<<P_, 128, smem>>>(P_, W_, G_, (double)cutoff, (double)gaussianWidth, activation, w1, b1, w2, b2, h, tabF_, tabD_);
+        cf_table_kernel<<<P_, 128, smem>>>(P_, W_, G_, (double)cutoff, (double)gaussianWidth, activation, w1, b1, w2, b2, h, f64, tabD_);
+        cf_table_finish_kernel<<<(unsigned)(((size_t)P_ * W_ + 255) / 256), 256>>>(P_, W_, f64, tabF_, tabG_);
         NNP_CUDA_CHECK(cudaGetLastError());
         NNP_CUDA_CHECK(cudaDeviceSynchronize());
+        cudaFree(f64);
     }
-    ~CFConvFilter() { cudaFree(tabF_); cudaFree(tabD_); }
+    ~CFConvFilter() { cudaFree(tabF_); cudaFree(tabD_); cudaFree(tabG_); }
 
     void compute(const CFConvNeighborList& nb, const float* input, float* output, cudaStream_t stream) const {
         check(nb);
         if (nb.n_ == 0) return;
         const int grid = (nb.n_ + kWPB - 1) / kWPB;
-        if (W_ <= 32) cf_forward_kernel<1><<<grid, kWPB * 32, 0, stream>>>(nb.n_, W_, nb.cells_.sorted, nb.cells_.sortedOrig, nb.cells_.geom, nb.rowPtr_, nb.nbr_, tabF_, tabD_, invH_, P_, input, output);
-        else if (W_ <= 64) cf_forward_kernel<2><<<grid, kWPB * 32, 0, stream>>>(nb.n_, W_, nb.cells_.sorted, nb.cells_.sortedOrig, nb.cells_.geom, nb.rowPtr_, nb.nbr_, tabF_, tabD_, invH_, P_, input, output);
-        else cf_forward_kernel<4><<<grid, kWPB * 32, 0, stream>>>(nb.n_, W_, nb.cells_.sorted, nb.cells_.sortedOrig, nb.cells_.geom, nb.rowPtr_, nb.nbr_, tabF_, tabD_, invH_, P_, input, output);
+        if (W_ <= 32) cf_forward_kernel<1><<<grid, kWPB * 32, 0, stream>>>(nb.n_, W_, nb.cells_.sorted, nb.cells_.sortedOrig, nb.cells_.geom, nb.rowPtr_, nb.nbr_, tabF_, tabD_, tabG_, invH_, P_, input, output);
+        else if (W_ <= 64) cf_forward_kernel<2><<<grid, kWPB * 32, 0, stream>>>(nb.n_, W_, nb.cells_.sorted, nb.cells_.sortedOrig, nb.cells_.geom, nb.rowPtr_, nb.nbr_, tabF_, tabD_, tabG_, invH_, P_, input, output);
+        else cf_forward_kernel<4><<<grid, kWPB * 32, 0, stream>>>(nb.n_, W_, nb.cells_.sorted, nb.cells_.sortedOrig, nb.cells_.geom, nb.rowPtr_, nb.nbr_, tabF_, tabD_, tabG_, invH_, P_, input, output);
         count_launch();
         NNP_CUDA_CHECK(cudaGetLastError());
     }
@@ -378,9 +395,9 @@ public:
         check(nb);
         if (nb.n_ == 0) return;
         const int grid = (nb.n_ + kWPB - 1) / kWPB;
-        if (W_ <= 32) cf_backward_kernel<1><<<grid, kWPB * 32, 0, stream>>>(nb.n_, W_, nb.cells_.sorted, nb.cells_.sortedOrig, nb.cells_.geom, nb.rowPtr_, nb.nbr_, tabF_, tabD_, invH_, P_, input, outputGrad, inputGrad, posGrad);
-        else if (W_ <= 64) cf_backward_kernel<2><<<grid, kWPB * 32, 0, stream>>>(nb.n_, W_, nb.cells_.sorted, nb.cells_.sortedOrig, nb.cells_.geom, nb.rowPtr_, nb.nbr_, tabF_, tabD_, invH_, P_, input, outputGrad, inputGrad, posGrad);
-        else cf_backward_kernel<4><<<grid, kWPB * 32, 0, stream>>>(nb.n_, W_, nb.cells_.sorted, nb.cells_.sortedOrig, nb.cells_.geom, nb.rowPtr_, nb.nbr_, tabF_, tabD_, invH_, P_, input, outputGrad, inputGrad, posGrad);
+        if (W_ <= 32) cf_backward_kernel<1><<<grid, kWPB * 32, 0, stream>>>(nb.n_, W_, nb.cells_.sorted, nb.cells_.sortedOrig, nb.cells_.geom, nb.rowPtr_, nb.nbr_, tabF_, tabD_, tabG_, invH_, P_, input, outputGrad, inputGrad, posGrad);
+        else if (W_ <= 64) cf_backward_kernel<2><<<grid, kWPB * 32, 0, stream>>>(nb.n_, W_, nb.cells_.sorted, nb.cells_.sortedOrig, nb.cells_.geom, nb.rowPtr_, nb.nbr_, tabF_, tabD_, tabG_, invH_, P_, input, outputGrad, inputGrad, posGrad);
+        else cf_backward_kernel<4><<<grid, kWPB * 32, 0, stream>>>(nb.n_, W_, nb.cells_.sorted, nb.cells_.sortedOrig, nb.cells_.geom, nb.rowPtr_, nb.nbr_, tabF_, tabD_, tabG_, invH_, P_, input, outputGrad, inputGrad, posGrad);
         count_launch();
         NNP_CUDA_CHECK(cudaGetLastError());
     }
@@ -396,6 +413,7 @@ private:
     float cutoff_, invH_;
     float* tabF_ = nullptr;
     float* tabD_ = nullptr;
+    float* tabG_ = nullptr;   // forward differences of the value table
 };
 
 // plain functions for the C ABI (c_api.cu)

@@ -56,6 +56,7 @@ struct ChainParams {
     CUtensorMap maps[kMaxSp][8];   // 0..5: packed weights of F1 F2 F3 G3 G2 G1; 6, 7: X hi / lo of the species' rows
     ChainSpecies sp[kMaxSp];
     int numSpecies, numTiles, M;
+    int mpu, numUnits;             // work unit = (tile, mpu consecutive ensemble members); numUnits = numTiles * (M / mpu)
     int xChunks, sChunks, ring;    // 64-column chunks of X and of the shared-memory activation buffer; weight ring depth
     float* dX;
     int ldx;
@@ -289,7 +290,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
             const int half = P.ring >> 1, s0 = g * half;
             int stage = 0;
             uint32_t phase = 0, xPhase = 0;
-            for (int t = blockIdx.x; t < P.numTiles; t += gridDim.x) {
+            for (int u = blockIdx.x; u < P.numUnits; u += gridDim.x) {
+                const int upt = P.M / P.mpu, t = u / upt, e0 = (u - t * upt) * P.mpu, e1 = e0 + P.mpu;
                 const int si = species_of(t);
                 const ChainSpecies& sp = P.sp[si];
                 if (g == 0) {
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
                         tma_load_2d(xbuf + (P.xChunks + kc) * kTile, &P.maps[si][7], xFull, kc * 64, row0);
                     }
                 }
-                for (int e = 0; e < P.M; e++) {
+                for (int e = e0; e < e1; e++) {
                     int chunkIdx = 0;
                     for (int j = 0; j < 6; j++) {
                         int N, K;
@@ -341,13 +343,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
             const uint32_t accFullBar = accFull(g), accEmptyBar = accEmpty(g);
             int stage = 0;
             uint32_t phase = 0, accPhase = 0, opBits = 0, xPhase = 0;
-            for (int t = blockIdx.x; t < P.numTiles; t += gridDim.x) {
+            for (int u = blockIdx.x; u < P.numUnits; u += gridDim.x) {
+                const int upt = P.M / P.mpu, t = u / upt, e0 = (u - t * upt) * P.mpu, e1 = e0 + P.mpu;
                 const int si = species_of(t);
                 const ChainSpecies& sp = P.sp[si];
                 mbar_wait(xFull, xPhase);
                 xPhase ^= 1u;
                 tc_fence_after();
-                for (int e = 0; e < P.M; e++) {
+                for (int e = e0; e < e1; e++) {
                     int chunkIdx = 0;
                     for (int j = 0; j < 6; j++) {
                         int N, K;
@@ -406,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
                                 needOp = false;
                                 // every slice of this layer's A operand is published, so all MMAs of the previous layer are complete: when
                                 // that layer was the last F1 of the tile, X may be replaced
-                                if (j == 1 && e == P.M - 1) mbar_arrive(xEmpty);
+                                if (j == 1 && e == e1 - 1) mbar_arrive(xEmpty);
                             }
                         }
                         if (needOp) {
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
                                 mbar_wait(opReady(kc), (opBits >> kc) & 1u);
                                 opBits ^= 1u << kc;
                             }
-                            if (j == 1 && e == P.M - 1) mbar_arrive(xEmpty);
+                            if (j == 1 && e == e1 - 1) mbar_arrive(xEmpty);
                         }
                         if (j == 5 && !chainCommitted) mbar_arrive(chainDone);   // G1 had a single chunk and it was the other issuer's
                     }
@@ -438,7 +441,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
         x.hsel = hsel;
         float* const stash = P.stash + (size_t)blockIdx.x * (kStashCols * kRows) + r;
         uint32_t fullPhase = 0, chainPhase = 0;
-        for (int t = blockIdx.x; t < P.numTiles; t += gridDim.x) {
+        for (int u = blockIdx.x; u < P.numUnits; u += gridDim.x) {
+                const int upt = P.M / P.mpu, t = u / upt, e0 = (u - t * upt) * P.mpu, e1 = e0 + P.mpu;
             const int si = species_of(t);
             const ChainSpecies& sp = P.sp[si];
             const int row0 = (t - sp.tileBegin) * kRows;
@@ -447,7 +451,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
             float esum = 0.0f;
             const unsigned char* const tab = chunkTab + si * 32;
             const int nChunks = tab[31];
-            for (int e = 0; e < P.M; e++) {
+            for (int e = e0; e < e1; e++) {
                 bool chainWaited = false;
                 for (int ci = g; ci < nChunks; ci += 2) {          // chunks alternate between the two accumulator stages / groups
                     const int j = tab[ci] >> 3, c = tab[ci] & 7;
@@ -469,7 +473,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
                                 case 2: epi_chunk<2>(P, x, sp.bias[2] + (size_t)e * N, sp.w3 + (size_t)e * N, stash, dxRow, false, accFull(g), fullPhase, accEmpty(g), lane, esum); break;
                                 case 3: epi_chunk<3>(P, x, nullptr, nullptr, stash, dxRow, false, accFull(g), fullPhase, accEmpty(g), lane, esum); break;
                                 case 4: epi_chunk<4>(P, x, nullptr, nullptr, stash, dxRow, false, accFull(g), fullPhase, accEmpty(g), lane, esum); break;
-                                default: epi_chunk<5>(P, x, nullptr, nullptr, stash, dxRow, e == 0, accFull(g), fullPhase, accEmpty(g), lane, esum); break;
+                                default: epi_chunk<5>(P, x, nullptr, nullptr, stash, dxRow, P.mpu == P.M && e == 0, accFull(g), fullPhase, accEmpty(g), lane, esum); break;
                             }
                         } else {
                             mbar_wait(accFull(g), fullPhase);
@@ -527,6 +531,7 @@ struct MlpChain::Impl {
     std::vector<__half*> dev;
     float* stash = nullptr;
     int grid = 0;
+    long long rows = 0;
     uint32_t smem = 0;
 };
 
@@ -559,6 +564,7 @@ MlpChain::MlpChain(int ensemble, int numSpecies, const SpeciesDesc* sp, const __
         c.tileBegin = tiles;
         tiles += (c.rows + kRows - 1) / kRows;
         c.tileEnd = tiles;
+        impl_->rows = std::max<long long>(impl_->rows, (long long)c.rowStart + c.rows);
         for (int l = 0; l < 3; l++) c.bias[l] = sp[s].bias[l];
         c.w3 = sp[s].w3;
         P.sChunks = std::max(P.sChunks, chunks_of(c.d2));
@@ -589,7 +595,24 @@ MlpChain::MlpChain(int ensemble, int numSpecies, const SpeciesDesc* sp, const __
     int dev = 0, sms = 0;
     NNP_CUDA_CHECK(cudaGetDevice(&dev));
     NNP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    impl_->grid = std::max(1, std::min(tiles, sms));
+    // Work unit = (tile, mpu consecutive members).  Whole tiles (mpu = M: X loaded once, dX written without atomics by the first member)
+    // leave the SMs unevenly loaded when there are only a few tiles per SM -- 392 tiles of two costs on 148 SMs: 13 % -- so the members
+    // of a tile are dealt to different CTAs until there are at least eight units per SM (each unit then reloads its 64 KB X tile from
+    // L2 and adds its dX contribution with red.global.add on a zeroed matrix).
+    int mpu = ensemble;
+    while (mpu > 1 && (long long)tiles * (ensemble / mpu) < 8LL * sms) {
+        int next = mpu - 1;
+        while (next > 1 && ensemble % next != 0) next--;
+        mpu = next;
+    }
+    if (const char* e = std::getenv("NNPOPS_CHAIN_MPU")) {   // development: force the members per unit (must divide the ensemble size)
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= ensemble && ensemble % v == 0) mpu = v;
+    }
+    P.mpu = mpu;
+    P.numUnits = tiles * (ensemble / mpu);
+    impl_->grid = std::max(1, std::min(P.numUnits, sms));
+    if (const char* e = std::getenv("NNPOPS_CHAIN_GRID")) impl_->grid = std::max(1, std::min(impl_->grid, std::atoi(e)));   // development: several units per CTA on small systems
     if (const char* e = std::getenv("NNPOPS_CHAIN_GRID")) impl_->grid = std::max(1, std::min(impl_->grid, std::atoi(e)));   // development: force several tiles per CTA
     NNP_CUDA_CHECK(cudaMalloc(&impl_->stash, sizeof(float) * (size_t)impl_->grid * kStashCols * kRows));
     P.stash = impl_->stash;
@@ -605,6 +628,7 @@ void MlpChain::launch(double* energyAcc, float* dX, float seedScale, float outSc
     ChainParams& P = impl_->P;
     if (P.numTiles == 0) return;
     P.energyAcc = energyAcc; P.dX = dX; P.seedScale = seedScale; P.outScale = outScale;
+    if (P.mpu != P.M) NNP_CUDA_CHECK(cudaMemsetAsync(dX, 0, sizeof(float) * (size_t)impl_->rows * P.ldx, stream));   // all members accumulate with red.add
     // per device, every time: the attribute is cheap to set and a process may drive several GPUs
     NNP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)impl_->smem));
     mlp_chain_kernel<<<impl_->grid, kThreads, impl_->smem, stream>>>(P);

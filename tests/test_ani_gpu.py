@@ -385,3 +385,34 @@ def test_neighbour_rows_grow_instead_of_truncating():
     torch.cuda.synchronize()
     big.energy_and_gradient(dev(pos), dev(box))
     assert big.overflowed() == 0
+
+
+@pytest.mark.parametrize("grid", [(2, 1, 1), (2, 2, 2)])
+def test_halo_decomposition_partials_sum_to_the_whole(grid):
+    """One box cut into bricks with ghost halos (SURVEY 8e variant i, nnpops_b200/halo.py), the ranks emulated one after the other
+    on one GPU: every rank's model holds only its brick + ghosts (in the real periodic box, original coordinates), the partial
+    energies and the gradient rows scattered back to the owners sum to the unsharded result, and the local systems are a fraction
+    of the box."""
+    from nnpops_b200.halo import HaloPlan
+    from nnpops_b200.OptimizedTorchANI import FusedANI
+    n = 6000
+    pos, L = lattice(n, 2.154, 0.3, 3000)
+    species = water_species(n)
+    box = cubic_box(L)
+    nets = random_networks(7, [(64, 64, 32)] * 7, 2, 1008, 3)
+    args = (7, 5.2, 3.5, ANI2X["EtaR"], ANI2X["ShfR"], ANI2X["EtaA"], ANI2X["Zeta"], ANI2X["ShfA"], ANI2X["ShfZ"])
+    e0, g0 = FusedANI(*args, species, nets).energy_and_gradient(dev(pos), dev(box))
+    e0 = float(e0.cpu()[0]); g0 = g0.cpu().numpy().astype(np.float64)
+    plan = HaloPlan(pos, [L, L, L], 5.2, grid)
+    e, g = 0.0, np.zeros_like(g0)
+    for r in range(plan.world):
+        local = plan.local_atoms(r)
+        mask = np.zeros(len(local), np.uint8); mask[:len(plan.owned[r])] = 1
+        m = FusedANI(*args, species[local], nets, owned=mask)
+        er, gr = m.energy_and_gradient(dev(pos[local]), dev(box))
+        assert m.overflowed() == 0
+        e += float(er.cpu()[0])
+        np.add.at(g, local, gr.cpu().numpy().astype(np.float64))
+        assert len(local) < n * (0.75 if plan.world == 2 else 0.45)
+    print("halo", grid, abs(e - e0) / abs(e0), rel_err(g, g0))
+    assert abs(e - e0) <= 2e-6 * abs(e0) and rel_err(g, g0) < 2e-6
