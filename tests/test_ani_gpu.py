@@ -413,6 +413,6 @@ def test_halo_decomposition_partials_sum_to_the_whole(grid):
         assert m.overflowed() == 0
         e += float(er.cpu()[0])
         np.add.at(g, local, gr.cpu().numpy().astype(np.float64))
-        assert len(local) < n * (0.75 if plan.world == 2 else 0.45)
+        assert len(local) < n * (0.8 if plan.world == 2 else 0.45)
     print("halo", grid, abs(e - e0) / abs(e0), rel_err(g, g0))
     assert abs(e - e0) <= 2e-6 * abs(e0) and rel_err(g, g0) < 2e-6
