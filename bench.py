@@ -387,9 +387,11 @@ def measure_box(args, dist, dev, nets, rank, world, local):
         pos, box = make_conformer(n, c)
         m = HaloBoxANI(7, 5.2, ANI2X["Rca"], ANI2X["EtaR"], ANI2X["ShfR"], ANI2X["EtaA"], ANI2X["Zeta"], ANI2X["ShfA"], ANI2X["ShfZ"], species,
                        nets, pos, box, mlp_impl=args.mlp, device="cuda:%d" % local)
-        models.append(m)
         pos_own.append(torch.tensor(pos[m.plan.owned[rank]], device=dev))
         boxes.append(torch.tensor(box, device=dev))
+        if not args.no_graph:
+            m.capture(boxes[-1])                             # whole step (halo exchange + local model + reverse halo + all-reduce) as one CUDA graph
+        models.append(m)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -407,6 +409,15 @@ def measure_box(args, dist, dev, nets, rank, world, local):
     t1.record()
     sync_all()
     ms_total = max_over_ranks(t0.elapsed_time(t1), dist, dev)
+    # what the exchange costs: the brick-local model alone (same local positions, no halo phases, no all-reduce), kernel by kernel
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    l0.record()
+    for i in range(args.steps):
+        models[i % pool].local.energy_and_gradient(models[i % pool].local_pos, boxes[i % pool])
+    l1.record()
+    sync_all()
+    ms_local = max_over_ranks(l0.elapsed_time(l1), dist, dev)
     counts = torch.tensor([models[0].n_owned, models[0].n_ghost, models[0].halo_bytes_forward + models[0].halo_bytes_reverse], dtype=torch.float64, device=dev)
     mx = counts.clone()
     if dist is not None:
@@ -414,7 +425,11 @@ def measure_box(args, dist, dev, nets, rank, world, local):
     return {"value": round(args.steps / (ms_total / 1e3), 4), "unit": UNIT, "ms_per_step": round(ms_total / args.steps, 4), "scaling": "strong",
             "decomposition": "bricks %s with ghost halos of Rcr = 5.2 A, one brick per GPU" % (models[0].plan.grid,),
             "atoms_owned_max": int(mx[0]), "ghost_atoms_max": int(mx[1]), "halo_bytes_per_step_per_gpu_max": int(mx[2]),
-            "collectives": "2 grouped ncclSend/ncclRecv phases (positions out, ghost gradient rows back) + 1 scalar all-reduce per step",
+            "collectives": "2 all-to-all phases of ncclSend/ncclRecv (ghost positions out, ghost gradient rows back) + 1 scalar all-reduce per step",
+            "cuda_graph": not args.no_graph,
+            "local_model_ms_per_step": round(ms_local / args.steps, 4),
+            "local_model_note": "the brick-local model alone, launched kernel by kernel without the halo phases and the all-reduce (MAX over ranks): "
+                                "the difference to ms_per_step is what the exchange and the collectives cost -- or, when negative, what the CUDA graph saves",
             "energy": float(e.cpu()[0])}
 
 
@@ -608,6 +623,7 @@ def main():
     ap.add_argument("--atoms", type=int, default=50000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sustain", type=float, default=3.0, help="seconds of the extra sustained leg (0 = skip)")
+    ap.add_argument("--no-graph", action="store_true", help="box mode: launch the step kernel by kernel instead of replaying its CUDA graph")
     ap.add_argument("--no-box", action="store_true", help="N > 1: skip the extra one-box strong-scaling measurement")
     ap.add_argument("--no-model-check", action="store_true", help="--impl reference: skip the one real full-size AEV evaluation (~80 s)")
     ap.add_argument("--mode", default="conformers", choices=["conformers", "box"],

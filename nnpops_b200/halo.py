@@ -146,8 +146,16 @@ class HaloBoxANI:
         self.local_pos = torch.empty((self.n_owned + self.n_ghost, 3), dtype=torch.float32, device=self.device)
         self.recv_pos = [torch.empty((s.stop - s.start, 3), dtype=torch.float32, device=self.device) for s in self.ghost_range]
         self.recv_grad = [torch.empty((len(ix), 3), dtype=torch.float32, device=self.device) for ix in self.plan.send_idx[r]]
+        # all-to-all form of the two halo phases (NCCL): ONE gather + ONE collective each way.  The ghosts are stored grouped by source
+        # rank, so the receive buffer of the forward phase IS the ghost block of local_pos and the send buffer of the reverse phase IS
+        # the ghost block of the local gradient.
+        self.send_all = torch.cat(self.send_idx) if self.world > 0 else None
+        self.send_splits = [len(ix) for ix in self.plan.send_idx[r]]
+        self.ghost_splits = [s.stop - s.start for s in self.ghost_range]
+        self.recv_grad_all = torch.empty((int(sum(self.send_splits)), 3), dtype=torch.float32, device=self.device)
         self.halo_bytes_forward = 12 * sum(len(ix) for ix in self.plan.send_idx[r])      # sent by this rank per evaluation
         self.halo_bytes_reverse = 12 * self.n_ghost
+        self.graph = None
 
     def _exchange(self, send, recv):
         """recv[p] <- rank p's send[self.rank], for every peer, as ONE grouped NCCL launch (ncclGroupStart ... ncclSend/ncclRecv ...)."""
@@ -186,11 +194,57 @@ class HaloBoxANI:
                 g_own.index_add_(0, self.send_idx[p], self.recv_grad[p])
         return g_own
 
-    def energy_and_gradient(self, pos_owned, cell):
-        local = self.assemble(pos_owned)
-        e, g = self.local.energy_and_gradient(local, cell)
-        g_own = self.scatter_back(g)
-        if self.world > 1 and self.dist.is_initialized():
+    def _use_all_to_all(self):
+        return (self.world > 1 and self.dist.is_initialized() and self.dist.get_backend(self.group) == "nccl")
+
+    def _step(self, pos_owned, cell):
+        dist = self.dist
+        if self._use_all_to_all():
+            self.local_pos[:self.n_owned] = pos_owned
+            send = pos_owned.index_select(0, self.send_all)
+            dist.all_to_all_single(self.local_pos[self.n_owned:], send, self.ghost_splits, self.send_splits, group=self.group)
+            e, g = self.local.energy_and_gradient(self.local_pos, cell)
+            dist.all_to_all_single(self.recv_grad_all, g[self.n_owned:].contiguous(), self.send_splits, self.ghost_splits, group=self.group)
+            g_own = g[:self.n_owned].clone()
+            g_own.index_add_(0, self.send_all, self.recv_grad_all)
+        else:
+            local = self.assemble(pos_owned)
+            e, g = self.local.energy_and_gradient(local, cell)
+            g_own = self.scatter_back(g)
+        if self.world > 1 and dist.is_initialized():
             e = e.clone()
-            self.dist.all_reduce(e, op=self.dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(e, op=dist.ReduceOp.SUM, group=self.group)
         return e, g_own
+
+    def capture(self, cell):
+        """Capture the WHOLE step -- halo exchange (NCCL), brick-local model, reverse halo, energy all-reduce -- into one CUDA graph;
+        afterwards energy_and_gradient copies the positions into the graph's input buffer and replays it (every rank must call this
+        at the same point: the collectives are captured collectively).  At eight bricks the step is a few dozen short kernels and
+        three small collectives; launched one by one the host is the bottleneck."""
+        torch = self.torch
+        self.static_pos = torch.zeros((self.n_owned, 3), dtype=torch.float32, device=self.device)
+        self.static_cell = cell.detach().clone()
+        return self
+
+    def _capture_now(self, pos_owned):
+        torch = self.torch
+        self.static_pos.copy_(pos_owned)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):                                   # warm-up: allocations, communicator set-up, one-time attributes
+                self._step(self.static_pos, self.static_cell)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_e, self.static_g = self._step(self.static_pos, self.static_cell)
+
+    def energy_and_gradient(self, pos_owned, cell):
+        if getattr(self, "static_pos", None) is not None:
+            if self.graph is None:
+                self._capture_now(pos_owned)                     # the first call after capture() records the graph with real positions
+            self.static_pos.copy_(pos_owned)
+            self.graph.replay()
+            return self.static_e, self.static_g
+        return self._step(pos_owned, cell)
