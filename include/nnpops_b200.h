@@ -108,6 +108,14 @@ NNPOPS_API int nnpops_ani_model_work(nnpops_ani_model_t h, long long* triples, l
 /* mlp_flops_forward above counts the network on the model's full AEV length (the algorithmic figure).  The fused model evaluates
  * the AEV and the first layer only on the columns whose neighbour species occur in the system (the others are identically zero):
  * aev_length = full length, active_features = columns kept, mlp_flops_forward_executed = flops actually issued per forward. */
+/* Verlet skin of the neighbour search (0 = off, the default): candidate rows within cutoff + skin are kept and reused until an atom has
+ * moved more than skin / 2 or the box has changed; the decision is taken on the device in every call (no host synchronisation, works
+ * inside CUDA graphs) and the rows the AEV kernels see are exact at every step.  The reference rebuilds its N x N neighbour table in
+ * every call (CudaANISymmetryFunctions.cu:203-209); its callers' steady state is an MD loop (BenchmarkCudaCFConv.cu:105-112).
+ * skin_stats synchronises and returns how many calls rebuilt / reused the candidate rows since set_skin. */
+NNPOPS_API int nnpops_ani_set_skin(nnpops_ani_t h, float skin);
+NNPOPS_API int nnpops_ani_model_set_skin(nnpops_ani_model_t h, float skin);
+NNPOPS_API int nnpops_ani_model_skin_stats(nnpops_ani_model_t h, unsigned long long* rebuilds, unsigned long long* reuses);
 /* *fused = 1 when the network runs as the one-kernel layer chain (csrc/mlp_chain.cu), 0 for the per-layer GEMM launches */
 NNPOPS_API int nnpops_ani_model_mlp_fused(nnpops_ani_model_t h, int* fused);
 NNPOPS_API int nnpops_ani_model_info(nnpops_ani_model_t h, int* aev_length, int* active_features, double* mlp_flops_forward_executed);

@@ -67,7 +67,7 @@ class FusedANI(torch.nn.Module):
 
     def __init__(self, num_species: int, Rcr: float, Rca: float, EtaR, ShfR, EtaA, Zeta, ShfA, ShfZ, species: Sequence[int],
                  networks, mlp_impl: str = "tcgen05", device: str = "cuda", max_radial_neighbors: int = 0,
-                 max_angular_neighbors: int = 0, shard: Tuple[int, int] = (0, 1), owned: Optional[Sequence[int]] = None):
+                 max_angular_neighbors: int = 0, shard: Tuple[int, int] = (0, 1), owned: Optional[Sequence[int]] = None, skin: float = 0.0):
         super().__init__()
         self.num_atoms = len(species)
         self.num_species = int(num_species)
@@ -95,6 +95,8 @@ class FusedANI(torch.nn.Module):
                                                           max_radial_neighbors, max_angular_neighbors, int(shard[0]), int(shard[1])))
         self.shard = (int(shard[0]), int(shard[1]))
         self._h = h
+        if skin > 0:
+            self.set_skin(skin)
         self.mlp_impl = mlp_impl
         self.aev_length = int(dims[0, 0])
 
@@ -124,6 +126,18 @@ class FusedANI(torch.nn.Module):
         with torch.cuda.device(pos.device):
             check(lib.nnpops_ani_model_energy_grad(self._h, ptr(pos), ptr(box), ptr(energy), ptr(grad), current_stream(pos.device)))
         return energy, grad
+
+    def set_skin(self, skin: float):
+        """Verlet skin of the neighbour search in the length unit of the positions (0 = rebuild every call).  For time-stepping callers:
+        the candidate rows are reused until an atom has moved more than skin / 2; the rows the kernels see stay exact."""
+        with torch.cuda.device(self.device_):
+            check(lib.nnpops_ani_model_set_skin(self._h, float(skin)))
+
+    def skin_stats(self):
+        """(calls that rebuilt the candidate rows, calls that reused them) since set_skin; synchronises."""
+        a, b = C.c_ulonglong(0), C.c_ulonglong(0)
+        check(lib.nnpops_ani_model_skin_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def _raise_if_overflowed(self):
         """Never blocks: a neighbour row that overflowed in an EARLIER evaluation is reported now (the reference has no neighbour

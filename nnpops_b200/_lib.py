@@ -35,6 +35,9 @@ _SIGS = {
     "nnpops_ani_model_work": [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_double), _vp],
     "nnpops_ani_model_info": [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(C.c_double)],
     "nnpops_ani_model_mlp_fused": [_vp, C.POINTER(_i)],
+    "nnpops_ani_set_skin": [_vp, _f],
+    "nnpops_ani_model_set_skin": [_vp, _f],
+    "nnpops_ani_model_skin_stats": [_vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)],
     "nnpops_ani_model_overflowed": [_vp, C.POINTER(_i)],
     "nnpops_ani_model_overflow_poll": [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)],
     "nnpops_ani_model_timing_begin": [_vp, _i],

@@ -104,7 +104,12 @@ __global__ void __launch_bounds__(kWPB * 32)
 ani_rows_kernel(int n, const float4* __restrict__ sorted, const int* __restrict__ sortedCell, const Geom* __restrict__ geom,
                 const int* __restrict__ cellStart, const AniTables* __restrict__ tab, int capR, int capA,
                 int* __restrict__ rowRad, int* __restrict__ rowAng, int* __restrict__ offRad, int* __restrict__ offAng,
-                int* __restrict__ flag, const int* __restrict__ sortedOrig, const unsigned char* __restrict__ owned) {
+                int* __restrict__ flag, const int* __restrict__ sortedOrig, const unsigned char* __restrict__ owned,
+                const int* __restrict__ rebuild, float skinCut2, int capC, int* __restrict__ candRow, int* __restrict__ candCnt) {
+    // Verlet skin (candRow != nullptr): on a rebuild step (*rebuild != 0) the candidates of the cell-list scan that lie within
+    // (Rcr + skin)^2 are also written to candRow; on the other steps the candidates come from candRow instead of the cells -- about
+    // 75 distance tests per centre instead of 380 -- and every one takes the minimum-image step.  Either way the rows hold exactly
+    // the atoms with r2 < Rcr^2 at the CURRENT positions.
     extern __shared__ unsigned char smemRaw[];
     __shared__ Geom g;
     if (threadIdx.x == 0) g = *geom;
@@ -112,6 +117,8 @@ ani_rows_kernel(int n, const float4* __restrict__ sorted, const int* __restrict_
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = blockIdx.x * kWPB + w;
     if (p >= n) return;
+    const bool useSkin = candRow != nullptr;
+    const bool scanCells = !useSkin || *rebuild != 0;
     if (owned != nullptr && !owned[sortedOrig[p]]) {
         // a centre of another rank (one box sharded over several GPUs): empty rows, so every downstream kernel skips it
         const int S1 = tab->nSpecies + 1;
@@ -128,30 +135,52 @@ ani_rows_kernel(int n, const float4* __restrict__ sorted, const int* __restrict_
     // the minimum-image step is skipped for runs that do not cross a periodic face (it subtracts exactly zero there, see
     // for_each_candidate_run_w): 3 FRND on the XU pipe and 9 more instructions per candidate
     const bool alwaysImage = g.periodic && (g.triclinic || g.anyOutside);
-    for_each_candidate_run_w(g, cellStart, sortedCell[p], [&](int b, int e, bool wrapped) {
-        const bool image = alwaysImage || wrapped;
-        for (int q0 = b; q0 < e; q0 += 32) {
-            const int q = q0 + lane;
-            bool ok = false;
-            uint32_t packed = 0;
-            if (q < e && q != p) {
-                const float4 cj = sorted[q];
-                float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
-                const float r2 = image ? min_image_mul(g, dx, dy, dz)
-                                       : __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                if (r2 < rcr2) {
-                    ok = true;
-                    packed = (uint32_t)q | ((uint32_t)__float_as_int(cj.w) << 24) | (r2 < rca2 ? 0x80000000u : 0u);
-                }
+    int nCand = 0;
+    auto visit = [&](int q, bool valid, bool image) {
+        bool ok = false, cand = false;
+        uint32_t packed = 0;
+        if (valid && q != p) {
+            const float4 cj = sorted[q];
+            float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
+            const float r2 = image ? min_image_mul(g, dx, dy, dz)
+                                   : __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            cand = r2 < skinCut2;
+            if (r2 < rcr2) {
+                ok = true;
+                packed = (uint32_t)q | ((uint32_t)__float_as_int(cj.w) << 24) | (r2 < rca2 ? 0x80000000u : 0u);
             }
-            const unsigned m = __ballot_sync(kFull, ok);
-            if (ok) {
-                const int idx = count + __popc(m & ((1u << lane) - 1u));
-                if (idx < capR) list[idx] = packed;
-            }
-            count += __popc(m);
         }
-    });
+        const unsigned m = __ballot_sync(kFull, ok);
+        if (ok) {
+            const int idx = count + __popc(m & ((1u << lane) - 1u));
+            if (idx < capR) list[idx] = packed;
+        }
+        count += __popc(m);
+        if (useSkin && scanCells) {   // remember every atom within the skin cutoff
+            const unsigned mc = __ballot_sync(kFull, cand);
+            if (cand) {
+                const int idx = nCand + __popc(mc & ((1u << lane) - 1u));
+                if (idx < capC) candRow[(size_t)p * capC + idx] = q;
+            }
+            nCand += __popc(mc);
+        }
+    };
+    if (scanCells) {
+        for_each_candidate_run_w(g, cellStart, sortedCell[p], [&](int b, int e, bool wrapped) {
+            const bool image = alwaysImage || wrapped;
+            for (int q0 = b; q0 < e; q0 += 32) visit(q0 + lane, q0 + lane < e, image);
+        });
+        if (useSkin) {
+            if (nCand > capC) { if (lane == 0) atomicOr(flag, 1); nCand = capC; }
+            if (lane == 0) candCnt[p] = nCand;
+        }
+    } else {
+        const int nc = candCnt[p];
+        for (int q0 = 0; q0 < nc; q0 += 32) {
+            const bool valid = q0 + lane < nc;
+            visit(valid ? candRow[(size_t)p * capC + q0 + lane] : p, valid, g.periodic != 0);
+        }
+    }
     if (count > capR) { if (lane == 0) atomicOr(flag, 1); count = capR; }
     cntR[lane] = 0; cntA[lane] = 0;
     __syncwarp();
@@ -1054,6 +1083,37 @@ __global__ void count_kernel_triples(int n, int S, const int* __restrict__ offRa
     if ((threadIdx.x & 31) == 0) { atomicAdd(&counters[0], tr); atomicAdd(&counters[1], pr); }
 }
 
+// Verlet skin, step 1: does any atom sit further than skin / 2 from where it was when the candidate rows were built (or has the
+// box changed, or is this the first call)?  The answer stays on the device: the kernels behind it read the flag.
+__global__ void skin_check_kernel(int n, const float* __restrict__ pos, const float* __restrict__ box, const float* __restrict__ refPos,
+                                  const float* __restrict__ refBox, float lim2, int force, int* __restrict__ rebuild) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && force) *rebuild = 1;
+    if (i < 9 && box != nullptr && box[i] != refBox[i]) *rebuild = 1;
+    if (i >= n) return;
+    const float dx = pos[3 * (size_t)i] - refPos[3 * (size_t)i], dy = pos[3 * (size_t)i + 1] - refPos[3 * (size_t)i + 1],
+                dz = pos[3 * (size_t)i + 2] - refPos[3 * (size_t)i + 2];
+    if (dx * dx + dy * dy + dz * dz > lim2) *rebuild = 1;   // benign race: every writer stores the same value
+}
+// step 2 (after the conditional cell-list build): a rebuild step records the reference positions / box; a reuse step refreshes the
+// coordinates of the sorted copy (the atoms keep the sorted slots of the last build) and counts itself
+__global__ void skin_refresh_kernel(int n, const float* __restrict__ pos, const float* __restrict__ box, const int* __restrict__ sortedOrig,
+                                    float4* __restrict__ sorted, float* __restrict__ refPos, float* __restrict__ refBox,
+                                    const int* __restrict__ rebuild, unsigned long long* __restrict__ stats) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool rb = *rebuild != 0;
+    if (p == 0) atomicAdd(&stats[rb ? 0 : 1], 1ull);
+    if (rb) {
+        if (p < 9 && box != nullptr) refBox[p] = box[p];
+        if (p < n) { refPos[3 * (size_t)p] = pos[3 * (size_t)p]; refPos[3 * (size_t)p + 1] = pos[3 * (size_t)p + 1]; refPos[3 * (size_t)p + 2] = pos[3 * (size_t)p + 2]; }
+    } else if (p < n) {
+        const int i = sortedOrig[p];
+        float4 v = sorted[p];
+        v.x = pos[3 * (size_t)i]; v.y = pos[3 * (size_t)i + 1]; v.z = pos[3 * (size_t)i + 2];
+        sorted[p] = v;
+    }
+}
+
 template <typename K>
 void set_smem(K kernel, size_t bytes) {
     if (bytes > 48 * 1024) NNP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -1138,7 +1198,40 @@ AniAev::AniAev(int numAtoms, int numSpecies, float rcr, float rca, const int* at
     NNP_CUDA_CHECK(cudaEventCreateWithFlags(&evJoin_, cudaEventDisableTiming));
 }
 
+void AniAev::setSkin(float skin) {
+    NNP_REQUIRE(skin >= 0.0f, "the Verlet skin must be >= 0");
+    cudaFree(candRow_); cudaFree(candCnt_); cudaFree(skinRefPos_); cudaFree(skinRefBox_); cudaFree(skinRebuild_); cudaFree(skinStats_);
+    candRow_ = candCnt_ = skinRebuild_ = nullptr; skinRefPos_ = skinRefBox_ = nullptr; skinStats_ = nullptr;
+    skin_ = skin;
+    if (skin <= 0.0f) return;
+    const size_t na = (size_t)(n_ > 0 ? n_ : 1);
+    const float rc = tabHost_.rcr > tabHost_.rca ? tabHost_.rcr : tabHost_.rca;
+    const double grow = std::pow((rc + skin) / rc, 3.0);
+    capC_ = ((int)std::ceil(capR_ * grow * 1.05) + 31) / 32 * 32;
+    NNP_CUDA_CHECK(cudaMalloc(&candRow_, sizeof(int) * na * capC_));
+    NNP_CUDA_CHECK(cudaMalloc(&candCnt_, sizeof(int) * na));
+    NNP_CUDA_CHECK(cudaMalloc(&skinRefPos_, sizeof(float) * 3 * na));
+    NNP_CUDA_CHECK(cudaMalloc(&skinRefBox_, sizeof(float) * 9));
+    NNP_CUDA_CHECK(cudaMalloc(&skinRebuild_, sizeof(int)));
+    NNP_CUDA_CHECK(cudaMalloc(&skinStats_, 2 * sizeof(unsigned long long)));
+    NNP_CUDA_CHECK(cudaMemset(skinRefPos_, 0, sizeof(float) * 3 * na));
+    NNP_CUDA_CHECK(cudaMemset(skinRefBox_, 0, sizeof(float) * 9));
+    NNP_CUDA_CHECK(cudaMemset(skinStats_, 0, 2 * sizeof(unsigned long long)));
+    skinFresh_ = true;
+}
+
+void AniAev::skinStats(unsigned long long* rebuilds, unsigned long long* reuses) {
+    unsigned long long h[2] = {0, 0};
+    if (skinStats_) {
+        NNP_CUDA_CHECK(cudaDeviceSynchronize());
+        NNP_CUDA_CHECK(cudaMemcpy(h, skinStats_, sizeof(h), cudaMemcpyDeviceToHost));
+    }
+    if (rebuilds) *rebuilds = h[0];
+    if (reuses) *reuses = h[1];
+}
+
 AniAev::~AniAev() {
+    cudaFree(candRow_); cudaFree(candCnt_); cudaFree(skinRefPos_); cudaFree(skinRefBox_); cudaFree(skinRebuild_); cudaFree(skinStats_);
     cudaFree(tab_); cudaFree(species_); cudaFree(rowRad_); cudaFree(rowAng_); cudaFree(offRad_); cudaFree(offAng_);
     cudaFree(flag_); cudaFree(counters_);
     if (flagHost_) cudaFreeHost(flagHost_);
@@ -1169,13 +1262,29 @@ void AniAev::forward(const float* positions, const float* box, float* radial, in
     // split output: one [n][radialStride] matrix pair, radial block first (radial/angular then only carry the column offsets)
     const AevOut radialOut = {radial, splitHi, splitLo};
     const AevOut angularOut = {angular, splitHi ? splitHi + radialWidth() : nullptr, splitLo ? splitLo + radialWidth() : nullptr};
-    cells_.build<float>(positions, box, species_, tabHost_.rcr > tabHost_.rca ? tabHost_.rcr : tabHost_.rca, stream);
+    const float cut = tabHost_.rcr > tabHost_.rca ? tabHost_.rcr : tabHost_.rca;
     const int grid = (n_ + kWPB - 1) / kWPB;
+    if (skin_ > 0.0f) {
+        // Verlet skin: candidate rows within cut + skin are kept while no atom has moved more than skin / 2 since they were built.
+        // Whether this step rebuilds is decided ON THE DEVICE (skinRebuild_): the cell-list kernels return at once on a reuse step,
+        // the row kernel takes its candidates from the kept rows instead of the cells.  No host round trip, CUDA-graph friendly.
+        const int tb = 256, nb = (std::max(n_, 9) + tb - 1) / tb;
+        NNP_CUDA_CHECK(cudaMemsetAsync(skinRebuild_, 0, sizeof(int), stream));
+        skin_check_kernel<<<nb, tb, 0, stream>>>(n_, positions, box, skinRefPos_, skinRefBox_, 0.25f * skin_ * skin_, skinFresh_ ? 1 : 0, skinRebuild_);
+        skinFresh_ = false;
+        cells_.build<float>(positions, box, species_, cut + skin_, stream, skinRebuild_);
+        skin_refresh_kernel<<<nb, tb, 0, stream>>>(n_, positions, box, cells_.sortedOrig, cells_.sorted, skinRefPos_, skinRefBox_, skinRebuild_, skinStats_);
+        count_launch(2);
+    } else {
+        cells_.build<float>(positions, box, species_, cut, stream);
+    }
     {
         const size_t smem = (size_t)kWPB * capR_ * sizeof(uint32_t) + (size_t)kWPB * 128 * sizeof(int);
         set_smem(ani_rows_kernel, smem);
+        const float sc = cut + skin_;
         ani_rows_kernel<<<grid, kWPB * 32, smem, stream>>>(n_, cells_.sorted, cells_.sortedCell, cells_.geom, cells_.cellStart, tab_,
-                                                           capR_, capA_, rowRad_, rowAng_, offRad_, offAng_, flag_, cells_.sortedOrig, owned_);
+                                                           capR_, capA_, rowRad_, rowAng_, offRad_, offAng_, flag_, cells_.sortedOrig, owned_,
+                                                           skinRebuild_, sc * sc, capC_, skin_ > 0.0f ? candRow_ : nullptr, candCnt_);
         count_launch();
     }
     if (ev) cudaEventRecord(ev[0], stream);

@@ -47,6 +47,13 @@ public:
     // evaluates only the centres it owns (all atoms stay neighbour candidates) and backward() switches to the centre-owned radial
     // form, so that positionGrad holds this rank's PARTIAL dE/dx over all atoms (sum over ranks = total).  nullptr = all owned.
     void setOwned(const unsigned char* deviceMask) { owned_ = deviceMask; }
+    // Verlet skin (0 = off, the default): the neighbour search keeps candidate rows within cutoff + skin and reuses them until some
+    // atom has moved more than skin / 2 (or the box has changed); the decision is taken on the device every call.  The rows handed to
+    // the AEV kernels are exact at every step.  The steady state of the reference's callers is a time-stepping loop that rebuilds its
+    // N x N table every iteration (BenchmarkCudaCFConv.cu:105-112).
+    void setSkin(float skin);
+    float skin() const { return skin_; }
+    void skinStats(unsigned long long* rebuilds, unsigned long long* reuses);   // synchronises
 
     // positions [n][3], box [3][3] or nullptr (all device, fp32).  radial/angular: device, row strides in floats.
     // ev (optional): forward records ev[0] after the neighbour rows and ev[1] after the radial kernel; backward records ev[0]
@@ -87,6 +94,15 @@ private:
     int* offAng_ = nullptr;      // [n][S+1]
     int* flag_ = nullptr;        // overflow flag
     int* flagHost_ = nullptr;    // pinned host mirror of the flag
+    float skin_ = 0.0f;
+    int capC_ = 0;
+    int* candRow_ = nullptr;     // [n][capC] sorted indices within cutoff + skin at the last rebuild
+    int* candCnt_ = nullptr;     // [n]
+    float* skinRefPos_ = nullptr;   // [n][3] positions at the last rebuild
+    float* skinRefBox_ = nullptr;   // [9]
+    int* skinRebuild_ = nullptr;    // device flag of the current call
+    unsigned long long* skinStats_ = nullptr;   // {rebuild steps, reuse steps}
+    bool skinFresh_ = true;
     unsigned long long* counters_ = nullptr;   // [2] scratch for countTriples / countRadialPairs
     const int* rowMap_ = nullptr;
     const unsigned char* owned_ = nullptr;

@@ -301,6 +301,28 @@ int nnpops_ani_model_work(nnpops_ani_model_t h, long long* triples, long long* r
     });
 }
 
+int nnpops_ani_set_skin(nnpops_ani_t h, float skin) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl, "invalid handle");
+        h->impl->setSkin(skin);
+    });
+}
+
+int nnpops_ani_model_set_skin(nnpops_ani_model_t h, float skin) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl, "invalid handle");
+        if (h->graphExec) { cudaGraphExecDestroy(h->graphExec); h->graphExec = nullptr; }   // the captured step has the old kernels
+        h->impl->aev().setSkin(skin);
+    });
+}
+
+int nnpops_ani_model_skin_stats(nnpops_ani_model_t h, unsigned long long* rebuilds, unsigned long long* reuses) {
+    return guarded([&] {
+        NNP_REQUIRE(h && h->impl, "invalid handle");
+        h->impl->aev().skinStats(rebuilds, reuses);
+    });
+}
+
 int nnpops_ani_model_mlp_fused(nnpops_ani_model_t h, int* fused) {
     return guarded([&] {
         NNP_REQUIRE(h && h->impl && fused, "invalid argument");

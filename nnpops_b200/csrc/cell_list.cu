@@ -1,5 +1,6 @@
 // Cell-list build: geometry -> histogram -> scan -> scatter -> deterministic in-cell ordering.  See cell_list.cuh.
 #include "cell_list.cuh"
+#include <algorithm>
 
 namespace nnpops {
 
@@ -10,7 +11,9 @@ namespace {
 constexpr float kCellMargin = 1.001f;   // cells are at least this many cutoffs wide: absorbs fp32 rounding of the cell index
 
 template <typename T>
-__global__ void geom_kernel(const T* __restrict__ pos, int n, const T* __restrict__ box, float cutoff, int maxCells, Geom* out) {
+__global__ void geom_kernel(const T* __restrict__ pos, int n, const T* __restrict__ box, float cutoff, int maxCells, Geom* out,
+                            const int* __restrict__ run) {
+    if (run != nullptr && *run == 0) return;   // Verlet-skin reuse step: the previous cell list stands
     __shared__ float smin[3][32], smax[3][32];
     Geom g;
     const float cw = cutoff * kCellMargin;
@@ -95,7 +98,8 @@ __device__ __forceinline__ int cell_of(const Geom& g, T px, T py, T pz, bool* ou
 
 template <typename T>
 __global__ void count_kernel(const T* __restrict__ pos, int n, Geom* __restrict__ geom, int* __restrict__ cellCount,
-                             int* __restrict__ cellOf, int* __restrict__ slot) {
+                             int* __restrict__ cellOf, int* __restrict__ slot, const int* __restrict__ run) {
+    if (run != nullptr && *run == 0) return;
     __shared__ Geom g;
     if (threadIdx.x == 0) g = *geom;
     __syncthreads();
@@ -109,7 +113,9 @@ __global__ void count_kernel(const T* __restrict__ pos, int n, Geom* __restrict_
 }
 
 // exclusive scan of cellCount[0..ncells) into cellStart[0..ncells]; entries beyond ncells are set to n so stale cells are empty
-__global__ void scan_kernel(const int* __restrict__ cellCount, int* __restrict__ cellStart, const Geom* __restrict__ geom, int maxCells) {
+__global__ void scan_kernel(const int* __restrict__ cellCount, int* __restrict__ cellStart, const Geom* __restrict__ geom, int maxCells,
+                            const int* __restrict__ run) {
+    if (run != nullptr && *run == 0) return;
     __shared__ int warpTot[32];
     __shared__ int carry;
     const int ncells = geom->ncells;
@@ -139,7 +145,8 @@ __global__ void scan_kernel(const int* __restrict__ cellCount, int* __restrict__
 }
 
 __global__ void scatter_kernel(int n, const int* __restrict__ cellOf, const int* __restrict__ slot, const int* __restrict__ cellStart,
-                               int* __restrict__ tmpIdx) {
+                               int* __restrict__ tmpIdx, const int* __restrict__ run) {
+    if (run != nullptr && *run == 0) return;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) tmpIdx[cellStart[cellOf[i]] + slot[i]] = i;
 }
@@ -147,7 +154,8 @@ __global__ void scatter_kernel(int n, const int* __restrict__ cellOf, const int*
 template <typename T>
 __global__ void order_kernel(const T* __restrict__ pos, const int* __restrict__ tags, int n, const int* __restrict__ cellOf,
                              const int* __restrict__ cellStart, const int* __restrict__ tmpIdx, float4* __restrict__ sorted,
-                             int* __restrict__ sortedOrig, int* __restrict__ sortedCell) {
+                             int* __restrict__ sortedOrig, int* __restrict__ sortedCell, const int* __restrict__ run) {
+    if (run != nullptr && *run == 0) return;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const int i = tmpIdx[p];
@@ -162,6 +170,11 @@ __global__ void order_kernel(const T* __restrict__ pos, const int* __restrict__ 
     sorted[dst] = v;
     sortedOrig[dst] = i;
     sortedCell[dst] = c;
+}
+
+__global__ void zero_counts_kernel(int* __restrict__ cellCount, int count, const int* __restrict__ run) {
+    if (run != nullptr && *run == 0) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) cellCount[i] = 0;
 }
 
 }  // namespace
@@ -191,20 +204,21 @@ void CellList::release() {
 }
 
 template <typename T>
-void CellList::build(const T* positions, const T* box, const int* tags, float cutoff, cudaStream_t stream) {
+void CellList::build(const T* positions, const T* box, const int* tags, float cutoff, cudaStream_t stream, const int* run) {
     if (n == 0) return;
     const int tb = 256, nb = (n + tb - 1) / tb;
-    geom_kernel<T><<<1, 1024, 0, stream>>>(positions, n, box, cutoff, maxCells, geom);
-    NNP_CUDA_CHECK(cudaMemsetAsync(cellCount, 0, sizeof(int) * (maxCells + 1), stream));
-    count_kernel<T><<<nb, tb, 0, stream>>>(positions, n, geom, cellCount, cellOf, slot);
-    scan_kernel<<<1, 1024, 0, stream>>>(cellCount, cellStart, geom, maxCells);
-    scatter_kernel<<<nb, tb, 0, stream>>>(n, cellOf, slot, cellStart, tmpIdx);
-    order_kernel<T><<<nb, tb, 0, stream>>>(positions, tags, n, cellOf, cellStart, tmpIdx, sorted, sortedOrig, sortedCell);
+    geom_kernel<T><<<1, 1024, 0, stream>>>(positions, n, box, cutoff, maxCells, geom, run);
+    if (run == nullptr) NNP_CUDA_CHECK(cudaMemsetAsync(cellCount, 0, sizeof(int) * (maxCells + 1), stream));
+    else zero_counts_kernel<<<std::min((maxCells + 1 + 255) / 256, 1184), 256, 0, stream>>>(cellCount, maxCells + 1, run);
+    count_kernel<T><<<nb, tb, 0, stream>>>(positions, n, geom, cellCount, cellOf, slot, run);
+    scan_kernel<<<1, 1024, 0, stream>>>(cellCount, cellStart, geom, maxCells, run);
+    scatter_kernel<<<nb, tb, 0, stream>>>(n, cellOf, slot, cellStart, tmpIdx, run);
+    order_kernel<T><<<nb, tb, 0, stream>>>(positions, tags, n, cellOf, cellStart, tmpIdx, sorted, sortedOrig, sortedCell, run);
     count_launch(5);
     NNP_CUDA_CHECK(cudaGetLastError());
 }
 
-template void CellList::build<float>(const float*, const float*, const int*, float, cudaStream_t);
-template void CellList::build<double>(const double*, const double*, const int*, float, cudaStream_t);
+template void CellList::build<float>(const float*, const float*, const int*, float, cudaStream_t, const int*);
+template void CellList::build<double>(const double*, const double*, const int*, float, cudaStream_t, const int*);
 
 }  // namespace nnpops

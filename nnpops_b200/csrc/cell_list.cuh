@@ -30,8 +30,10 @@ struct CellList {
     void release();
     // positions: device [n][3] (float or double); box: device [3][3] of the same type or nullptr (non-periodic);
     // tags: device int [n] or nullptr.  All launches go to `stream`; nothing synchronises.
+    // run (optional): device flag; when it reads 0 at execution time every kernel returns at once and the previous list stands
+    // (Verlet-skin reuse decided on the device, no host round trip).
     template <typename T>
-    void build(const T* positions, const T* box, const int* tags, float cutoff, cudaStream_t stream);
+    void build(const T* positions, const T* box, const int* tags, float cutoff, cudaStream_t stream, const int* run = nullptr);
 };
 
 // Visit the candidate ranges [begin, end) of the sorted array that can hold neighbours of an atom in cell `c`.

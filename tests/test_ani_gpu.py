@@ -416,3 +416,31 @@ def test_halo_decomposition_partials_sum_to_the_whole(grid):
         assert len(local) < n * (0.8 if plan.world == 2 else 0.45)
     print("halo", grid, abs(e - e0) / abs(e0), rel_err(g, g0))
     assert abs(e - e0) <= 2e-6 * abs(e0) and rel_err(g, g0) < 2e-6
+
+
+def test_verlet_skin_rows_are_exact_over_an_md_like_sequence():
+    """with a Verlet skin the candidate rows are reused until an atom has moved skin / 2, decided on the device.  Over a
+    sequence of small random displacements (an MD-like trajectory) energy, AEVs and forces equal those of a model that rebuilds its
+    neighbour rows from the cell list every step -- the row SETS are identical, only the summation order inside a row can differ --
+    most steps reuse the rows, and a jump of one atom forces a rebuild."""
+    n = 3000
+    pos, L = lattice(n, 2.154, 0.3, 3000)
+    species = water_species(n)
+    box = dev(cubic_box(L))
+    ref, _ = fused(pos, species, None, 5.2, "tcgen05", hidden=[(64, 64, 32)] * 7, ensemble=2)
+    sk, _ = fused(pos, species, None, 5.2, "tcgen05", hidden=[(64, 64, 32)] * 7, ensemble=2)
+    sk.set_skin(0.5)
+    rng = np.random.default_rng(8)
+    p = pos.copy()
+    for step in range(24):
+        p = p + rng.normal(0.0, 0.012, p.shape).astype(np.float32)
+        if step == 17:
+            p[5] += np.float32(0.4)                      # one atom jumps further than skin / 2: the next call must rebuild
+        e0, g0 = ref.energy_and_gradient(dev(p), box)
+        e1, g1 = sk.energy_and_gradient(dev(p), box)
+        assert abs(float(e1.cpu()[0]) - float(e0.cpu()[0])) <= 2e-6 * abs(float(e0.cpu()[0]))
+        assert rel_err(g1.cpu().numpy(), g0.cpu().numpy()) < 2e-6
+        assert rel_err(sk.features().cpu().numpy(), ref.features().cpu().numpy()) < 1e-6
+    rebuilds, reuses = sk.skin_stats()
+    print("verlet skin: %d rebuilds, %d reuses over 24 steps" % (rebuilds, reuses))
+    assert rebuilds + reuses == 24 and 2 <= rebuilds <= 6 and sk.overflowed() == 0
