@@ -100,6 +100,7 @@ __device__ __forceinline__ int pair_index(int S, int s, int t) {   // CpuANISymm
 // Neighbour rows.  One warp per centre atom (sorted order).  Candidates come from the <= 18 contiguous runs of the cell
 // list; the accept test is the reference's fp32 expression (strict r2 < Rc^2, CpuANISymmetryFunctions.cpp:129-135).
 // ------------------------------------------------------------------------------------------------------------------
+template <bool SKIN>
 __global__ void __launch_bounds__(kWPB * 32)
 ani_rows_kernel(int n, const float4* __restrict__ sorted, const int* __restrict__ sortedCell, const Geom* __restrict__ geom,
                 const int* __restrict__ cellStart, const AniTables* __restrict__ tab, int capR, int capA,
@@ -117,7 +118,7 @@ ani_rows_kernel(int n, const float4* __restrict__ sorted, const int* __restrict_
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = blockIdx.x * kWPB + w;
     if (p >= n) return;
-    const bool useSkin = candRow != nullptr;
+    constexpr bool useSkin = SKIN;
     const bool scanCells = !useSkin || *rebuild != 0;
     if (owned != nullptr && !owned[sortedOrig[p]]) {
         // a centre of another rank (one box sharded over several GPUs): empty rows, so every downstream kernel skips it
@@ -1214,10 +1215,10 @@ void AniAev::setSkin(float skin) {
     NNP_CUDA_CHECK(cudaMalloc(&skinRefBox_, sizeof(float) * 9));
     NNP_CUDA_CHECK(cudaMalloc(&skinRebuild_, sizeof(int)));
     NNP_CUDA_CHECK(cudaMalloc(&skinStats_, 2 * sizeof(unsigned long long)));
-    NNP_CUDA_CHECK(cudaMemset(skinRefPos_, 0, sizeof(float) * 3 * na));
+    // reference positions start at 3.4e38 (bytes 0x7f): the first call -- eager or a graph replay -- sees every atom "moved" and builds
+    NNP_CUDA_CHECK(cudaMemset(skinRefPos_, 0x7f, sizeof(float) * 3 * na));
     NNP_CUDA_CHECK(cudaMemset(skinRefBox_, 0, sizeof(float) * 9));
     NNP_CUDA_CHECK(cudaMemset(skinStats_, 0, 2 * sizeof(unsigned long long)));
-    skinFresh_ = true;
 }
 
 void AniAev::skinStats(unsigned long long* rebuilds, unsigned long long* reuses) {
@@ -1270,8 +1271,7 @@ void AniAev::forward(const float* positions, const float* box, float* radial, in
         // the row kernel takes its candidates from the kept rows instead of the cells.  No host round trip, CUDA-graph friendly.
         const int tb = 256, nb = (std::max(n_, 9) + tb - 1) / tb;
         NNP_CUDA_CHECK(cudaMemsetAsync(skinRebuild_, 0, sizeof(int), stream));
-        skin_check_kernel<<<nb, tb, 0, stream>>>(n_, positions, box, skinRefPos_, skinRefBox_, 0.25f * skin_ * skin_, skinFresh_ ? 1 : 0, skinRebuild_);
-        skinFresh_ = false;
+        skin_check_kernel<<<nb, tb, 0, stream>>>(n_, positions, box, skinRefPos_, skinRefBox_, 0.25f * skin_ * skin_, 0, skinRebuild_);
         cells_.build<float>(positions, box, species_, cut + skin_, stream, skinRebuild_);
         skin_refresh_kernel<<<nb, tb, 0, stream>>>(n_, positions, box, cells_.sortedOrig, cells_.sorted, skinRefPos_, skinRefBox_, skinRebuild_, skinStats_);
         count_launch(2);
@@ -1280,11 +1280,18 @@ void AniAev::forward(const float* positions, const float* box, float* radial, in
     }
     {
         const size_t smem = (size_t)kWPB * capR_ * sizeof(uint32_t) + (size_t)kWPB * 128 * sizeof(int);
-        set_smem(ani_rows_kernel, smem);
         const float sc = cut + skin_;
-        ani_rows_kernel<<<grid, kWPB * 32, smem, stream>>>(n_, cells_.sorted, cells_.sortedCell, cells_.geom, cells_.cellStart, tab_,
-                                                           capR_, capA_, rowRad_, rowAng_, offRad_, offAng_, flag_, cells_.sortedOrig, owned_,
-                                                           skinRebuild_, sc * sc, capC_, skin_ > 0.0f ? candRow_ : nullptr, candCnt_);
+        if (skin_ > 0.0f) {
+            set_smem(ani_rows_kernel<true>, smem);
+            ani_rows_kernel<true><<<grid, kWPB * 32, smem, stream>>>(n_, cells_.sorted, cells_.sortedCell, cells_.geom, cells_.cellStart, tab_,
+                                                                   capR_, capA_, rowRad_, rowAng_, offRad_, offAng_, flag_, cells_.sortedOrig, owned_,
+                                                                   skinRebuild_, sc * sc, capC_, candRow_, candCnt_);
+        } else {
+            set_smem(ani_rows_kernel<false>, smem);
+            ani_rows_kernel<false><<<grid, kWPB * 32, smem, stream>>>(n_, cells_.sorted, cells_.sortedCell, cells_.geom, cells_.cellStart, tab_,
+                                                                    capR_, capA_, rowRad_, rowAng_, offRad_, offAng_, flag_, cells_.sortedOrig, owned_,
+                                                                    nullptr, 0.0f, 0, nullptr, nullptr);
+        }
         count_launch();
     }
     if (ev) cudaEventRecord(ev[0], stream);

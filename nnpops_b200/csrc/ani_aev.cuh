@@ -102,7 +102,6 @@ private:
     float* skinRefBox_ = nullptr;   // [9]
     int* skinRebuild_ = nullptr;    // device flag of the current call
     unsigned long long* skinStats_ = nullptr;   // {rebuild steps, reuse steps}
-    bool skinFresh_ = true;
     unsigned long long* counters_ = nullptr;   // [2] scratch for countTriples / countRadialPairs
     const int* rowMap_ = nullptr;
     const unsigned char* owned_ = nullptr;
