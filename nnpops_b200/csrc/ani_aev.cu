@@ -9,6 +9,7 @@
 // and :228-353 (backward).  cos(theta - thetas) is evaluated as c*cos(thetas) + sqrt(1-c^2)*sin(thetas) instead of through
 // acosf/cosf, and a^zeta as ex2(zeta*lg2(a)).
 #include "ani_aev.cuh"
+#include "ani_angular_v2.cuh"
 #include <cuda_fp16.h>
 #include <cmath>
 #include <cstdlib>
@@ -106,7 +107,8 @@ ani_rows_kernel(int n, const float4* __restrict__ sorted, const int* __restrict_
                 const int* __restrict__ cellStart, const AniTables* __restrict__ tab, int capR, int capA,
                 int* __restrict__ rowRad, int* __restrict__ rowAng, int* __restrict__ offRad, int* __restrict__ offAng,
                 int* __restrict__ flag, const int* __restrict__ sortedOrig, const unsigned char* __restrict__ owned,
-                const int* __restrict__ rebuild, float skinCut2, int capC, int* __restrict__ candRow, int* __restrict__ candCnt) {
+                const int* __restrict__ rebuild, float skinCut2, int capC, int* __restrict__ candRow, int* __restrict__ candCnt,
+                float4* __restrict__ geoA, float4* __restrict__ geoB) {
     // Verlet skin (candRow != nullptr): on a rebuild step (*rebuild != 0) the candidates of the cell-list scan that lie within
     // (Rcr + skin)^2 are also written to candRow; on the other steps the candidates come from candRow instead of the cells -- about
     // 75 distance tests per centre instead of 380 -- and every one takes the minimum-image step.  Either way the rows hold exactly
@@ -129,6 +131,7 @@ ani_rows_kernel(int n, const float4* __restrict__ sorted, const int* __restrict_
     uint32_t* list = reinterpret_cast<uint32_t*>(smemRaw) + (size_t)w * capR;
     int* cnt = reinterpret_cast<int*>(reinterpret_cast<uint32_t*>(smemRaw) + (size_t)kWPB * capR) + w * 128;
     int* cntR = cnt, *cntA = cnt + 32, *curR = cnt + 64, *curA = cnt + 96;
+    int* sAng = reinterpret_cast<int*>(reinterpret_cast<uint32_t*>(smemRaw) + (size_t)kWPB * capR) + kWPB * 128 + w * capA;
     const int S = tab->nSpecies;
     const float rcr2 = tab->rcr2, rca2 = tab->rca2;
     const float4 ci = sorted[p];
@@ -137,14 +140,18 @@ ani_rows_kernel(int n, const float4* __restrict__ sorted, const int* __restrict_
     // for_each_candidate_run_w): 3 FRND on the XU pipe and 9 more instructions per candidate
     const bool alwaysImage = g.periodic && (g.triclinic || g.anyOutside);
     int nCand = 0;
-    auto visit = [&](int q, bool valid, bool image) {
+    // IMAGE is a compile-time tag: as a run-time flag the compiler predicates the minimum-image step, and its 14 predicated-off
+    // instructions still take issue slots in the hottest loop of the kernel
+    auto visit = [&](int q, bool valid, auto imageTag) {
+        constexpr bool image = decltype(imageTag)::value;
         bool ok = false, cand = false;
         uint32_t packed = 0;
         if (valid && q != p) {
             const float4 cj = sorted[q];
             float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
-            const float r2 = image ? min_image_mul(g, dx, dy, dz)
-                                   : __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            float r2;
+            if (image) r2 = min_image_mul(g, dx, dy, dz);
+            else r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
             cand = r2 < skinCut2;
             if (r2 < rcr2) {
                 ok = true;
@@ -168,8 +175,8 @@ ani_rows_kernel(int n, const float4* __restrict__ sorted, const int* __restrict_
     };
     if (scanCells) {
         for_each_candidate_run_w(g, cellStart, sortedCell[p], [&](int b, int e, bool wrapped) {
-            const bool image = alwaysImage || wrapped;
-            for (int q0 = b; q0 < e; q0 += 32) visit(q0 + lane, q0 + lane < e, image);
+            if (alwaysImage || wrapped) { for (int q0 = b; q0 < e; q0 += 32) visit(q0 + lane, q0 + lane < e, std::true_type{}); }
+            else { for (int q0 = b; q0 < e; q0 += 32) visit(q0 + lane, q0 + lane < e, std::false_type{}); }
         });
         if (useSkin) {
             if (nCand > capC) { if (lane == 0) atomicOr(flag, 1); nCand = capC; }
@@ -177,9 +184,16 @@ ani_rows_kernel(int n, const float4* __restrict__ sorted, const int* __restrict_
         }
     } else {
         const int nc = candCnt[p];
-        for (int q0 = 0; q0 < nc; q0 += 32) {
-            const bool valid = q0 + lane < nc;
-            visit(valid ? candRow[(size_t)p * capC + q0 + lane] : p, valid, g.periodic != 0);
+        if (g.periodic) {
+            for (int q0 = 0; q0 < nc; q0 += 32) {
+                const bool valid = q0 + lane < nc;
+                visit(valid ? candRow[(size_t)p * capC + q0 + lane] : p, valid, std::true_type{});
+            }
+        } else {
+            for (int q0 = 0; q0 < nc; q0 += 32) {
+                const bool valid = q0 + lane < nc;
+                visit(valid ? candRow[(size_t)p * capC + q0 + lane] : p, valid, std::false_type{});
+            }
         }
     }
     if (count > capR) { if (lane == 0) atomicOr(flag, 1); count = capR; }
@@ -231,7 +245,31 @@ ani_rows_kernel(int n, const float4* __restrict__ sorted, const int* __restrict_
         __syncwarp();
         const int j = (int)(e & 0x00ffffffu);
         if (valid) rowRad[(size_t)p * capR + dstR] = j;
-        if (ang && dstA < capA) rowAng[(size_t)p * capA + dstA] = j;
+        if (ang && dstA < capA) {
+            rowAng[(size_t)p * capA + dstA] = j;
+            if (geoA != nullptr) sAng[dstA] = j | (s << 24);
+        }
+    }
+    if (geoA != nullptr) {
+        // geometry of the angular neighbours, computed once for the forward and the backward kernel (ani_angular_v2.cu): unit vector
+        // scaled by sqrt(cosScale) (so that uA . uB is the damped cosine), r / 2, fc, fc', 1 / r, species and atom index.  A pass of
+        // its own over the finished angular row: every lane busy, where the placement loop above holds ~30 % angular entries.
+        __syncwarp();
+        const int cntA = min(curA[S - 1], capA);      // curA[S - 1] has advanced to the total
+        const float invRca = 1.0f / tab->rca, kf = kPi * invRca, sq = sqrtf(tab->cosScale);
+        for (int q = lane; q < cntA; q += 32) {
+            const int e = sAng[q];
+            const int j = e & 0x00ffffff;
+            const float4 cj = sorted[j];
+            float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
+            const float r = sqrtf(min_image_mul(g, dx, dy, dz));
+            const float ir = 1.0f / r;
+            float sn, cs;
+            sincospif(r * invRca, &sn, &cs);
+            const float k = ir * sq;
+            geoA[(size_t)p * capA + q] = make_float4(dx * k, dy * k, dz * k, 0.5f * r);
+            geoB[(size_t)p * capA + q] = make_float4(0.5f * cs + 0.5f, -0.5f * kf * sn, ir, __int_as_float((e & 0x7f000000) | sortedOrig[j]));
+        }
     }
 }
 
@@ -1189,6 +1227,14 @@ AniAev::AniAev(int numAtoms, int numSpecies, float rcr, float rca, const int* at
     NNP_CUDA_CHECK(cudaMalloc(&rowAng_, sizeof(int) * na * capA_));
     NNP_CUDA_CHECK(cudaMalloc(&offRad_, sizeof(int) * na * (numSpecies + 1)));
     NNP_CUDA_CHECK(cudaMalloc(&offAng_, sizeof(int) * na * (numSpecies + 1)));
+    if (angular_v2_supported(t) && 2 * capA_ <= 256 && std::getenv("NNPOPS_ANGULAR_V1") == nullptr) {
+        NNP_CUDA_CHECK(cudaMalloc(&geoA_, sizeof(float4) * na * capA_));
+        NNP_CUDA_CHECK(cudaMalloc(&geoB_, sizeof(float4) * na * capA_));
+        NNP_CUDA_CHECK(cudaMalloc(&segHist_, 2 * kSegBins * sizeof(int)));
+        NNP_CUDA_CHECK(cudaMalloc(&segs_, sizeof(int2) * na * t.nPairs));
+        NNP_CUDA_CHECK(cudaMalloc(&nSeg_, sizeof(int)));
+        NNP_CUDA_CHECK(cudaMemset(nSeg_, 0, sizeof(int)));
+    }
     NNP_CUDA_CHECK(cudaMalloc(&flag_, sizeof(int)));
     NNP_CUDA_CHECK(cudaMemset(flag_, 0, sizeof(int)));
     NNP_CUDA_CHECK(cudaMallocHost(&flagHost_, sizeof(int)));
@@ -1235,6 +1281,7 @@ AniAev::~AniAev() {
     cudaFree(candRow_); cudaFree(candCnt_); cudaFree(skinRefPos_); cudaFree(skinRefBox_); cudaFree(skinRebuild_); cudaFree(skinStats_);
     cudaFree(tab_); cudaFree(species_); cudaFree(rowRad_); cudaFree(rowAng_); cudaFree(offRad_); cudaFree(offAng_);
     cudaFree(flag_); cudaFree(counters_);
+    cudaFree(geoA_); cudaFree(geoB_); cudaFree(segHist_); cudaFree(segs_); cudaFree(nSeg_);
     if (flagHost_) cudaFreeHost(flagHost_);
     if (aux_) cudaStreamDestroy(aux_);
     if (evFork_) cudaEventDestroy(evFork_);
@@ -1257,6 +1304,14 @@ AniAev::~AniAev() {
         }                                                                                                              \
     } while (0)
 
+bool AniAev::useV2(const float* angular, int angularStride, const __half* splitHi, const __half* splitLo) const {
+    if (geoA_ == nullptr || tabHost_.nAngular == 0) return false;
+    // 16-byte stores of 8 channels: the angular block of every output row must start on a multiple of 8 elements
+    const bool aligned = ((angularStride | radialWidth()) & 7) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(angular) | reinterpret_cast<uintptr_t>(splitHi) | reinterpret_cast<uintptr_t>(splitLo)) & 15) == 0;
+    return aligned;
+}
+
 void AniAev::forward(const float* positions, const float* box, float* radial, int radialStride, float* angular, int angularStride,
                      cudaStream_t stream, cudaEvent_t* ev, __half* splitHi, __half* splitLo) {
     if (n_ == 0) return;
@@ -1278,19 +1333,25 @@ void AniAev::forward(const float* positions, const float* box, float* radial, in
     } else {
         cells_.build<float>(positions, box, species_, cut, stream);
     }
+    // second-generation angular kernels (ani_angular_v2.cu): the row kernel also writes the neighbour geometry and the size histogram
+    // of the (centre, species pair) blocks
+    const bool v2 = useV2(angular, angularStride, splitHi, splitLo);
+    lastForwardV2_ = v2;
     {
-        const size_t smem = (size_t)kWPB * capR_ * sizeof(uint32_t) + (size_t)kWPB * 128 * sizeof(int);
+        const size_t smem = (size_t)kWPB * capR_ * sizeof(uint32_t) + (size_t)kWPB * 128 * sizeof(int) + (size_t)kWPB * capA_ * sizeof(int);
         const float sc = cut + skin_;
         if (skin_ > 0.0f) {
             set_smem(ani_rows_kernel<true>, smem);
             ani_rows_kernel<true><<<grid, kWPB * 32, smem, stream>>>(n_, cells_.sorted, cells_.sortedCell, cells_.geom, cells_.cellStart, tab_,
                                                                    capR_, capA_, rowRad_, rowAng_, offRad_, offAng_, flag_, cells_.sortedOrig, owned_,
-                                                                   skinRebuild_, sc * sc, capC_, candRow_, candCnt_);
+                                                                   skinRebuild_, sc * sc, capC_, candRow_, candCnt_, v2 ? geoA_ : nullptr,
+                                                                   v2 ? geoB_ : nullptr);
         } else {
             set_smem(ani_rows_kernel<false>, smem);
             ani_rows_kernel<false><<<grid, kWPB * 32, smem, stream>>>(n_, cells_.sorted, cells_.sortedCell, cells_.geom, cells_.cellStart, tab_,
                                                                     capR_, capA_, rowRad_, rowAng_, offRad_, offAng_, flag_, cells_.sortedOrig, owned_,
-                                                                    nullptr, 0.0f, 0, nullptr, nullptr);
+                                                                    nullptr, 0.0f, 0, nullptr, nullptr, v2 ? geoA_ : nullptr,
+                                                                    v2 ? geoB_ : nullptr);
         }
         count_launch();
     }
@@ -1315,7 +1376,11 @@ void AniAev::forward(const float* positions, const float* box, float* radial, in
     }
     if (fork) NNP_CUDA_CHECK(cudaEventRecord(evJoin_, aux_));
     if (ev) cudaEventRecord(ev[1], stream);
-    if (tabHost_.nAngular > 0) {
+    if (tabHost_.nAngular > 0 && v2) {
+        const AevOutPtr o = {angularOut.f32, angularOut.hi, angularOut.lo};
+        angular_v2_build_segments(n_, tabHost_, offAng_, segHist_, segHist_ + kSegBins, segs_, nSeg_, cells_.sortedOrig, rowMap_, o, angularStride, stream);
+        angular_v2_forward(n_, tabHost_, tab_, offAng_, capA_, geoA_, geoB_, segs_, nSeg_, cells_.sortedOrig, rowMap_, o, angularStride, stream);
+    } else if (tabHost_.nAngular > 0) {
         static const int groupLanes = std::getenv("NNPOPS_ANGULAR_GROUP") ? std::atoi(std::getenv("NNPOPS_ANGULAR_GROUP")) : 8;
         const bool aligned = ((angularStride | radialWidth()) & 3) == 0 &&
                              ((reinterpret_cast<uintptr_t>(angular) | reinterpret_cast<uintptr_t>(splitHi) | reinterpret_cast<uintptr_t>(splitLo)) & 15) == 0;
@@ -1372,7 +1437,9 @@ void AniAev::backward(const float* radialGrad, int radialStride, const float* an
     }
     if (fork) NNP_CUDA_CHECK(cudaEventRecord(evJoin_, aux_));
     if (ev) cudaEventRecord(ev[0], stream);
-    if (tabHost_.nAngular > 0) {
+    if (tabHost_.nAngular > 0 && lastForwardV2_ && (angularStride & 3) == 0 && (reinterpret_cast<uintptr_t>(angularGrad) & 15) == 0) {
+        angular_v2_backward(n_, tabHost_, tab_, offAng_, capA_, geoA_, geoB_, cells_.sortedOrig, rowMap_, angularGrad, angularStride, positionGrad, stream);
+    } else if (tabHost_.nAngular > 0) {
         const int gPitch = tabHost_.nAngular + 1;
         const size_t smem = (size_t)kWPB * ((size_t)12 * capA_ + (size_t)tabHost_.nPairs * gPitch) * sizeof(float);
         NNP_REQUIRE(smem <= 200 * 1024, "angular gradient row does not fit in shared memory (numSpecies^2 * numAngular too large)");

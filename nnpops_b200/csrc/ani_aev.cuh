@@ -103,6 +103,14 @@ private:
     int* skinRebuild_ = nullptr;    // device flag of the current call
     unsigned long long* skinStats_ = nullptr;   // {rebuild steps, reuse steps}
     unsigned long long* counters_ = nullptr;   // [2] scratch for countTriples / countRadialPairs
+    // second-generation angular kernels (ani_angular_v2.cu)
+    float4* geoA_ = nullptr;     // [n][capA] {sqrt(cosScale) * unit vector, r / 2}, species-grouped like rowAng
+    float4* geoB_ = nullptr;     // [n][capA] {fc, fc', 1 / r, species << 24 | atom index}
+    int* segHist_ = nullptr;     // [2][512] size histogram of the (centre, species pair) blocks + fill cursors
+    int2* segs_ = nullptr;       // [n * nPairs] non-empty blocks, largest first
+    int* nSeg_ = nullptr;
+    bool lastForwardV2_ = false;
+    bool useV2(const float* angular, int angularStride, const __half* splitHi, const __half* splitLo) const;
     const int* rowMap_ = nullptr;
     const unsigned char* owned_ = nullptr;
     bool haveForward_ = false;

@@ -1,0 +1,513 @@
+// Angular AEV kernels, second generation (sm_100a).  Behaviour matched: CpuANISymmetryFunctions.cpp:139-194 (forward) and
+// :265-353 (backward); reference CUDA counterparts CudaANISymmetryFunctions.cu:242-290 and :473-596.
+//
+// What changed against the first generation (ani_aev.cu: ani_angular_fwd_grouped_kernel / ani_angular_bwd_fast_kernel):
+//
+//  * Neighbour geometry is computed ONCE, by the row kernel, and stored next to the index rows (species-grouped order):
+//      geoA[p][q] = { sqrt(cs) * delta / r  (3 floats),  r / 2 }          cs = 0.95 (TorchANI) so that  uA . uB = cs * cos(theta)
+//      geoB[p][q] = { fc(r), fc'(r), 1 / r, (species << 24) | atom index }
+//    The compute kernels pull a centre's rows into shared memory with cp.async.bulk (TMA, mbarrier completion) instead of
+//    gathering coordinates and redoing min-image / sqrt / cos per kernel.
+//
+//  * Forward: the unit of work is a SEGMENT = one (centre, species pair) block of triples.  All non-empty segments of the system are
+//    binned by size and laid out largest first (angular_v2_build_segments); a warp takes 8 consecutive segments -- practically equal
+//    sizes -- and gives each 4 lanes, so every lane slot of every iteration holds a real triple (the per-centre kernels padded each
+//    block to the largest of the centres sharing a warp: 70 % lane fill on liquid water, 51 % on a protein).  lane <-> triple, 32
+//    channel accumulators in registers, a 2-level butterfly leaves lane gl with channels [8 gl, 8 gl + 8): one 16-byte store per
+//    hi / lo half.  Triples of a same-species segment are enumerated in rotation order (a, a + d mod n), those of a mixed segment
+//    as (a, d): both advance by "a += 4, wrap", no division in the loop.
+//
+//  * Backward: warp per centre, lane <-> triple in flat rotation order, step = min(32, 2 n - 2) triples per iteration.  With that
+//    step the lanes of one iteration that share the parity of d hold pairwise different a and pairwise different b (checked
+//    exhaustively for n <= 64 in tests/test_abi_and_host.py), so the forces on the two neighbours are accumulated with plain
+//    16-byte read-modify-writes into [parity][slot] arrays -- the first generation used 6 shared-memory float atomics per triple,
+//    which sm_100 executes as compare-and-swap loops.  The channel contraction runs as G[z] = sum_a g[a][z] E_a first (the radial
+//    factor is shared by the 4 angular channels), and the centre's force is minus the sum of its neighbours' at the end.
+#include "ani_angular_v2.cuh"
+#include <cmath>
+
+namespace nnpops {
+
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kFwdBudget = 256;    // neighbour entries of shared memory per warp in the forward kernel (>= 2 * capA required)
+constexpr int kBwdPitch = 36;      // floats per species-pair block of the staged gradient row (32 + 4: conflict-free float4 reads)
+
+__device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2a(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rsqrta(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// 1-D bulk copy global -> shared (TMA): 16-byte aligned addresses, size a multiple of 16
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ int pair_index(int S, int s, int t) {   // CpuANISymmetryFunctions.cpp:39-43, s <= t
+    return s * S - (s * (s - 1)) / 2 + (t - s);
+}
+
+__device__ __forceinline__ void zero_block32(const AevOutPtr& o, size_t idx) {
+    if (o.hi) {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { reinterpret_cast<uint4*>(o.hi + idx)[i] = z; reinterpret_cast<uint4*>(o.lo + idx)[i] = z; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) reinterpret_cast<float4*>(o.f32 + idx)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Segment list: counting sort of the non-empty (centre, species pair) blocks by size, largest first.  Two small kernels, one thread
+// per centre, 512 centres per CTA.  All counting goes through shared-memory histograms, so a CTA touches each global bin once
+// (atomics of many threads on the few populated bins of a global histogram serialise: 44 us for 150 000 segments).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int seg_bin(int ntrip) { return min((ntrip + kSegGroup - 1) / kSegGroup, kSegBins - 1); }
+
+__global__ void __launch_bounds__(kSegBins)
+ani_seg_hist_kernel(int n, int S, const int* __restrict__ offAng, int* __restrict__ hist) {
+    __shared__ int local[kSegBins];
+    const int tid = threadIdx.x;
+    local[tid] = 0;
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + tid;
+    if (p < n) {
+        const int* off = offAng + (size_t)p * (S + 1);
+        for (int s = 0; s < S; s++) {
+            const int ns = off[s + 1] - off[s];
+            if (ns == 0) continue;
+            for (int t = s; t < S; t++) {
+                const int ntrip = (s == t) ? (ns * (ns - 1)) / 2 : ns * (off[t + 1] - off[t]);
+                if (ntrip > 0) atomicAdd(&local[seg_bin(ntrip)], 1);
+            }
+        }
+    }
+    __syncthreads();
+    if (local[tid] > 0) atomicAdd(&hist[tid], local[tid]);
+}
+
+__global__ void __launch_bounds__(kSegBins)
+ani_seg_scatter_kernel(int n, int S, const int* __restrict__ offAng, const int* __restrict__ hist, int* __restrict__ cursor,
+                       int2* __restrict__ segs, int* __restrict__ nSeg, const int* __restrict__ sortedOrig, const int* __restrict__ rowMap,
+                       AevOutPtr out, int stride) {
+    __shared__ int base[kSegBins];       // first slot of this CTA's entries of a bin
+    __shared__ int local[kSegBins];      // entries of this CTA per bin, then the running cursor
+    __shared__ int warpTot[kSegBins / 32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    local[tid] = 0;
+    {   // thread t owns bin (kSegBins - 1 - t): inclusive scan in descending bin order
+        const int v = hist[kSegBins - 1 - tid];
+        int x = v;
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(kFull, x, o); if (lane >= o) x += y; }
+        if (lane == 31) warpTot[w] = x;
+        __syncthreads();
+        int add = 0;
+        for (int i = 0; i < w; i++) add += warpTot[i];
+        base[kSegBins - 1 - tid] = add + x - v;
+        if (blockIdx.x == 0 && tid == kSegBins - 1) *nSeg = add + x;
+    }
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + tid;
+    const int* off = offAng + (size_t)min(p, n - 1) * (S + 1);
+    if (p < n) {
+        for (int s = 0; s < S; s++) {
+            const int ns = off[s + 1] - off[s];
+            if (ns == 0) continue;
+            for (int t = s; t < S; t++) {
+                const int ntrip = (s == t) ? (ns * (ns - 1)) / 2 : ns * (off[t + 1] - off[t]);
+                if (ntrip > 0) atomicAdd(&local[seg_bin(ntrip)], 1);
+            }
+        }
+    }
+    __syncthreads();
+    {   // reserve this CTA's range of every populated bin with ONE global atomic
+        const int c = local[tid];
+        if (c > 0) base[tid] += atomicAdd(&cursor[tid], c);
+        local[tid] = 0;
+    }
+    __syncthreads();
+    if (p >= n) return;
+    const int orig = sortedOrig[p];
+    const size_t orow = (size_t)(rowMap ? rowMap[orig] : orig) * stride;
+    int pIdx = 0;
+    for (int s = 0; s < S; s++) {
+        const int ns = off[s + 1] - off[s];
+        for (int t = s; t < S; t++, pIdx++) {
+            const int nt = off[t + 1] - off[t];
+            const int ntrip = (s == t) ? (ns * (ns - 1)) / 2 : ns * nt;
+            if (ntrip <= 0) { zero_block32(out, orow + (size_t)pIdx * 32); continue; }
+            const int bin = seg_bin(ntrip);
+            segs[base[bin] + atomicAdd(&local[bin], 1)] = make_int2(p, (s << 16) | t);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Forward
+// ------------------------------------------------------------------------------------------------------------------
+template <int NSA, int NSZ>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 3)
+ani_angular_fwd_seg_kernel(const AniTables* __restrict__ tab, const int* __restrict__ offAng, int capA, const float4* __restrict__ geoA,
+                           const float4* __restrict__ geoB, const int2* __restrict__ segs, const int* __restrict__ nSegPtr,
+                           const int* __restrict__ sortedOrig, const int* __restrict__ rowMap, AevOutPtr out, int stride) {
+    static_assert(NSA * NSZ == 32, "32 angular channels");
+    constexpr int G = kSegGroup, GPW = 32 / G;
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    __shared__ __align__(8) unsigned long long bars[kWarpsPerCta];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane / G, gl = lane % G;
+    if (lane == 0) mbar_init(smem_u32(&bars[w]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const uint32_t bar = smem_u32(&bars[w]);
+    float4* sA = reinterpret_cast<float4*>(smemRaw + (size_t)w * kFwdBudget * 20);
+    float* sFc = reinterpret_cast<float*>(sA + kFwdBudget);
+    const uint32_t sAu = smem_u32(sA);
+    const int S = tab->nSpecies;
+    const float fZeta = tab->fZeta, nEtaL2 = -tab->fEtaL2, fScale = tab->fScale;
+    float shf[NSA], cz[NSZ], sz[NSZ];
+#pragma unroll
+    for (int a = 0; a < NSA; a++) shf[a] = tab->fShfA[a];
+#pragma unroll
+    for (int z = 0; z < NSZ; z++) { cz[z] = tab->fCos[z]; sz[z] = tab->fSin[z]; }
+    const int nSeg = *nSegPtr;
+    const int nChunks = (nSeg + GPW - 1) / GPW;
+    uint32_t phase = 0;
+    for (int chunk = blockIdx.x * kWarpsPerCta + w; chunk < nChunks; chunk += gridDim.x * kWarpsPerCta) {
+        const int segIdx = chunk * GPW + sub;
+        const bool valid = segIdx < nSeg;
+        int p = 0, bs = 0, ns = 0, bt = 0, nt = 0, ntrip = 0, e = 0, pIdx = 0;
+        bool same = true;
+        if (valid) {
+            const int2 sg = segs[segIdx];
+            p = sg.x;
+            const int s = sg.y >> 16, t = sg.y & 0xffff;
+            const int* off = offAng + (size_t)p * (S + 1);
+            bs = off[s]; ns = off[s + 1] - bs; bt = off[t]; nt = off[t + 1] - bt;
+            same = s == t;
+            ntrip = same ? (ns * (ns - 1)) / 2 : ns * nt;
+            e = same ? ns : ns + nt;
+            pIdx = pair_index(S, s, t);
+        }
+        int first = 0;
+        while (first < GPW) {   // normally ONE pass; more only when the 8 segments need more than kFwdBudget entries
+            int run = 0, lim = GPW, myBase = 0;
+            for (int g = first; g < GPW; g++) {
+                const int eg = __shfl_sync(kFull, e, g * G);
+                if (run + eg > kFwdBudget) { lim = g; break; }
+                if (g == sub) myBase = run;
+                run += eg;
+            }
+            if (run == 0) break;                      // only invalid segments left
+            const bool act = valid && sub >= first && sub < lim;
+            if (lane == 0) mbar_expect_tx(bar, (uint32_t)run * 16u);
+            __syncwarp();
+            if (act) {
+                const size_t rowBase = (size_t)p * capA;
+                if (gl == 0) {
+                    bulk_g2s(sAu + (uint32_t)myBase * 16u, geoA + rowBase + bs, (uint32_t)ns * 16u, bar);
+                    if (!same) bulk_g2s(sAu + (uint32_t)(myBase + ns) * 16u, geoA + rowBase + bt, (uint32_t)nt * 16u, bar);
+                }
+                for (int i = gl; i < e; i += G) sFc[myBase + i] = geoB[rowBase + (i < ns ? bs + i : bt + i - ns)].x;
+            }
+            __syncwarp();
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            const int trip = act ? ntrip : 0;
+            const int maxTrip = __reduce_max_sync(kFull, trip);
+            // lane gl starts at triple q = gl and advances by G.  Same species: q = d * ns + a  <->  pair (a, a + d + 1 mod ns);
+            // mixed: q = d * ns + a  <->  (a of species s, d of species t).
+            const int nsl = act ? ns : (1 << 28);
+            int a = gl, d = 0;
+            while (a >= nsl) { a -= nsl; d++; }
+            const int mb = act ? myBase : 0;
+            const int tOff = same ? 0 : ns;
+            float acc[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) acc[i] = 0.0f;
+            for (int q = gl; q < maxTrip; q += G) {
+                const bool v = q < trip;
+                int x = a + d + 1;
+                x -= (x >= nsl) ? nsl : 0;
+                const int ja = v ? mb + a : 0, jb = v ? mb + (same ? x : tOff + d) : 0;
+                const float4 va = sA[ja], vb = sA[jb];
+                const float fa = sFc[ja], fb = sFc[jb];
+                const float c = fmaf(va.z, vb.z, fmaf(va.y, vb.y, va.x * vb.x));
+                const float xx = fmaxf(fmaf(-c, c, 1.0f), 1e-30f);
+                const float sn = xx * rsqrta(xx);
+                const float rm = va.w + vb.w;
+                const float F = v ? fa * fb : 0.0f;
+                float P[NSZ];
+#pragma unroll
+                for (int z = 0; z < NSZ; z++) {
+                    const float base = fabsf(fmaf(sn, sz[z], fmaf(c, cz[z], 1.0f)));
+                    P[z] = F * ex2a(fZeta * lg2a(base));
+                }
+#pragma unroll
+                for (int k = 0; k < NSA; k++) {
+                    const float tt = rm - shf[k];
+                    const float E = ex2a(tt * (nEtaL2 * tt));
+#pragma unroll
+                    for (int z = 0; z < NSZ; z++) acc[k * NSZ + z] = fmaf(P[z], E, acc[k * NSZ + z]);
+                }
+                a += G;
+                while (a >= nsl) { a -= nsl; d++; }
+            }
+            // in-group transpose-reduce: lane gl ends with channels [8 gl, 8 gl + 8)
+#pragma unroll
+            for (int o = G / 2, c2 = 16; o >= 1; o >>= 1, c2 >>= 1) {
+                const bool up = (gl & o) != 0;
+#pragma unroll
+                for (int i = 0; i < c2; i++) {
+                    const float send = up ? acc[i] : acc[i + c2];
+                    const float keep = up ? acc[i + c2] : acc[i];
+                    acc[i] = keep + __shfl_xor_sync(kFull, send, o);
+                }
+            }
+            if (act) {
+                const int orig = sortedOrig[p];
+                const size_t dst = (size_t)(rowMap ? rowMap[orig] : orig) * stride + (size_t)pIdx * 32 + gl * 8;
+                if (out.hi) {
+                    uint32_t wh[4], wl[4];
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2) {
+                        const float v0 = acc[i] * fScale, v1 = acc[i + 1] * fScale;
+                        const __half2 h2 = __floats2half2_rn(v0, v1);
+                        const float2 f2 = __half22float2(h2);
+                        const __half2 l2 = __floats2half2_rn((v0 - f2.x) * 2048.0f, (v1 - f2.y) * 2048.0f);
+                        wh[i / 2] = *reinterpret_cast<const uint32_t*>(&h2);
+                        wl[i / 2] = *reinterpret_cast<const uint32_t*>(&l2);
+                    }
+                    *reinterpret_cast<uint4*>(out.hi + dst) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+                    *reinterpret_cast<uint4*>(out.lo + dst) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+                } else {
+                    reinterpret_cast<float4*>(out.f32 + dst)[0] = make_float4(acc[0] * fScale, acc[1] * fScale, acc[2] * fScale, acc[3] * fScale);
+                    reinterpret_cast<float4*>(out.f32 + dst)[1] = make_float4(acc[4] * fScale, acc[5] * fScale, acc[6] * fScale, acc[7] * fScale);
+                }
+            }
+            __syncwarp();      // every lane is done with the staged rows before the next bulk copy lands on them
+            first = lim;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Backward
+// ------------------------------------------------------------------------------------------------------------------
+template <int NSA, int NSZ>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 4)
+ani_angular_bwd_v2_kernel(int n, const AniTables* __restrict__ tab, const int* __restrict__ offAng, int capA,
+                          const float4* __restrict__ geoA, const float4* __restrict__ geoB, const int* __restrict__ sortedOrig,
+                          const int* __restrict__ rowMap, const float* __restrict__ grad, int stride, float* __restrict__ posGrad) {
+    static_assert(NSZ == 4 && NSA * NSZ == 32, "8 x 4 channels");
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    __shared__ __align__(8) unsigned long long bars[kWarpsPerCta];
+    __shared__ unsigned char pairTab[kAniMaxSpecies * kAniMaxSpecies];
+    const int S = tab->nSpecies, nPairs = tab->nPairs;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) mbar_init(smem_u32(&bars[w]), 1);
+    for (int i = threadIdx.x; i < S * S; i += blockDim.x) {
+        const int s = i / S, t = i % S;
+        pairTab[i] = (unsigned char)pair_index(S, min(s, t), max(s, t));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const int p = blockIdx.x * kWarpsPerCta + w;
+    if (p >= n) return;
+    const int cnt = offAng[(size_t)p * (S + 1) + S];
+    if (cnt < 2) return;
+    // per warp: float4 sA[capA], sB[capA], acc[4][capA] (force accumulators X0, X1 for the first, Y0, Y1 for the second neighbour of a
+    // triple, indexed by the parity of d), float sG[nPairs][36]
+    const size_t perWarp = (size_t)capA * 96 + (size_t)nPairs * kBwdPitch * 4;
+    unsigned char* wbase = smemRaw + (size_t)w * perWarp;
+    float4* sA = reinterpret_cast<float4*>(wbase);
+    float4* sB = sA + capA;
+    float4* sAcc = sB + capA;
+    float* sG = reinterpret_cast<float*>(sAcc + 4 * capA);
+    const uint32_t bar = smem_u32(&bars[w]);
+    const int orig = sortedOrig[p];
+    const float* gi = grad + (size_t)(rowMap ? rowMap[orig] : orig) * stride;
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)cnt * 32u + (uint32_t)nPairs * 128u);
+    __syncwarp();
+    if (lane == 0) {
+        bulk_g2s(smem_u32(sA), geoA + (size_t)p * capA, (uint32_t)cnt * 16u, bar);
+        bulk_g2s(smem_u32(sB), geoB + (size_t)p * capA, (uint32_t)cnt * 16u, bar);
+    }
+    for (int i = lane; i < nPairs; i += 32) bulk_g2s(smem_u32(sG + i * kBwdPitch), gi + i * 32, 128u, bar);
+    for (int i = lane; i < cnt; i += 32) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        sAcc[i] = z; sAcc[capA + i] = z; sAcc[2 * capA + i] = z; sAcc[3 * capA + i] = z;
+    }
+    const float cs = tab->cosScale;
+    const float rcs = 1.0f / cs, sqcs = sqrtf(cs), k1 = 1.0f / sqcs;
+    const float fZeta = tab->fZeta, nEtaL2 = -tab->fEtaL2, zm1 = tab->fZeta - 1.0f;
+    const float kA = k1 * tab->fScale, kB = -k1 * tab->fEta * tab->fScale, kC = sqcs * tab->fZeta * tab->fScale;
+    float shf[NSA], cz[NSZ], sz[NSZ];
+#pragma unroll
+    for (int a = 0; a < NSA; a++) shf[a] = tab->fShfA[a];
+#pragma unroll
+    for (int z = 0; z < NSZ; z++) { cz[z] = tab->fCos[z]; sz[z] = tab->fSin[z]; }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    const int total = (cnt * (cnt - 1)) >> 1;
+    const int step = min(32, 2 * cnt - 2);
+    int a = lane, d1 = 0;
+    if (a >= cnt) { a -= cnt; d1 = 1; }
+    const bool laneOn = lane < step;
+    for (int q0 = 0; q0 < total; q0 += step) {
+        if (laneOn && q0 + lane < total) {
+            int b = a + d1 + 1;
+            b -= (b >= cnt) ? cnt : 0;
+            const float4 va = sA[a], vb = sA[b], wa = sB[a], wb = sB[b];
+            const int spa = __float_as_int(wa.w) >> 24, spb = __float_as_int(wb.w) >> 24;
+            const float* gp = sG + pairTab[spa * S + spb] * kBwdPitch;
+            const float c = fmaf(va.z, vb.z, fmaf(va.y, vb.y, va.x * vb.x));
+            const float xx = fmaxf(fmaf(-c, c, 1.0f), 1e-30f);
+            const float isn = rsqrta(xx), sn = xx * isn;
+            const float rm = va.w + vb.w;
+            float P[NSZ], Q[NSZ];
+#pragma unroll
+            for (int z = 0; z < NSZ; z++) {
+                const float base = fabsf(fmaf(sn, sz[z], fmaf(c, cz[z], 1.0f)));
+                const float pm1 = ex2a(zm1 * lg2a(base));
+                P[z] = pm1 * base;
+                Q[z] = pm1 * fmaf(c, sz[z], -sn * cz[z]);
+            }
+            float GE[NSZ] = {0.f, 0.f, 0.f, 0.f}, GT[NSZ] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < NSA; k++) {
+                const float tt = rm - shf[k];
+                const float E = ex2a(tt * (nEtaL2 * tt));
+                const float Et = E * tt;
+                const float4 g4 = *reinterpret_cast<const float4*>(gp + k * NSZ);
+                GE[0] = fmaf(g4.x, E, GE[0]); GE[1] = fmaf(g4.y, E, GE[1]); GE[2] = fmaf(g4.z, E, GE[2]); GE[3] = fmaf(g4.w, E, GE[3]);
+                GT[0] = fmaf(g4.x, Et, GT[0]); GT[1] = fmaf(g4.y, Et, GT[1]); GT[2] = fmaf(g4.z, Et, GT[2]); GT[3] = fmaf(g4.w, Et, GT[3]);
+            }
+            float A = 0.0f, Bp = 0.0f, C = 0.0f;
+#pragma unroll
+            for (int z = 0; z < NSZ; z++) { A = fmaf(P[z], GE[z], A); Bp = fmaf(P[z], GT[z], Bp); C = fmaf(Q[z], GE[z], C); }
+            // W_a = k1 (fc'_a fc_b A + F B),  Kc = sqrt(cs) / sin(theta') * F * C  (see the derivation in DESIGN.md section 3)
+            const float F = wa.x * wb.x;
+            const float FB = F * (kB * Bp);
+            const float Ak = kA * A;
+            const float Wa = fmaf(wa.y * wb.x, Ak, FB), Wb = fmaf(wa.x * wb.y, Ak, FB);
+            const float Kc = (kC * isn) * (F * C);
+            const float ga = Kc * wa.z, gb = Kc * wb.z;
+            const float cth = c * rcs;
+            const float al = fmaf(ga, cth, Wa), be = fmaf(gb, cth, Wb);
+            const float fax = fmaf(al, va.x, -ga * vb.x), fay = fmaf(al, va.y, -ga * vb.y), faz = fmaf(al, va.z, -ga * vb.z);
+            const float fbx = fmaf(be, vb.x, -gb * va.x), fby = fmaf(be, vb.y, -gb * va.y), fbz = fmaf(be, vb.z, -gb * va.z);
+            float4* xa = sAcc + (d1 & 1) * capA + a;
+            float4* yb = sAcc + (2 + (d1 & 1)) * capA + b;
+            float4 ax = *xa, by = *yb;
+            ax.x += fax; ax.y += fay; ax.z += faz;
+            by.x += fbx; by.y += fby; by.z += fbz;
+            *xa = ax; *yb = by;
+        }
+        __syncwarp();
+        a += step;
+        if (a >= cnt) { a -= cnt; d1++; }
+        if (a >= cnt) { a -= cnt; d1++; }
+    }
+    float cx = 0.0f, cy = 0.0f, cz2 = 0.0f;
+    for (int q = lane; q < cnt; q += 32) {
+        const float4 x0 = sAcc[q], x1 = sAcc[capA + q], y0 = sAcc[2 * capA + q], y1 = sAcc[3 * capA + q];
+        const float fx = (x0.x + x1.x) + (y0.x + y1.x), fy = (x0.y + x1.y) + (y0.y + y1.y), fz = (x0.z + x1.z) + (y0.z + y1.z);
+        float* dst = posGrad + 3 * (size_t)(__float_as_int(sB[q].w) & 0x00ffffff);
+        atomicAdd(dst, fx); atomicAdd(dst + 1, fy); atomicAdd(dst + 2, fz);
+        cx -= fx; cy -= fy; cz2 -= fz;
+    }
+    cx = warp_sum(cx); cy = warp_sum(cy); cz2 = warp_sum(cz2);
+    if (lane == 0) {
+        float* dst = posGrad + 3 * (size_t)orig;
+        atomicAdd(dst, cx); atomicAdd(dst + 1, cy); atomicAdd(dst + 2, cz2);
+    }
+}
+
+template <typename K>
+void set_smem_v2(K kernel, size_t bytes) {
+    // the attribute is per device and per kernel; K differs per kernel signature, so each kernel gets its own table
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static size_t have[64] = {0};
+    if (dev >= 0 && dev < 64 && have[dev] >= bytes) return;
+    NNP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    NNP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (dev >= 0 && dev < 64) have[dev] = bytes;
+}
+
+int sm_count_v2() {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    static int cache[64] = {0};
+    if (dev >= 0 && dev < 64 && cache[dev]) return cache[dev];
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (dev >= 0 && dev < 64) cache[dev] = sms;
+    return sms;
+}
+
+}  // namespace
+
+bool angular_v2_supported(const AniTables& t) {
+    return t.fast && t.nShfA == 8 && t.nShfZ == 4 && t.torchani && t.nAngular == 32 && t.nSpecies <= 15;
+}
+
+void angular_v2_build_segments(int n, const AniTables& tabHost, const int* offAng, const int* hist, int* cursor, int2* segs, int* nSeg,
+                               const int* sortedOrig, const int* rowMap, AevOutPtr out, int stride, cudaStream_t stream) {
+    NNP_CUDA_CHECK(cudaMemsetAsync(const_cast<int*>(hist), 0, 2 * kSegBins * sizeof(int), stream));   // hist and cursor are adjacent
+    const int grid = (n + kSegBins - 1) / kSegBins;
+    ani_seg_hist_kernel<<<grid, kSegBins, 0, stream>>>(n, tabHost.nSpecies, offAng, const_cast<int*>(hist));
+    ani_seg_scatter_kernel<<<grid, kSegBins, 0, stream>>>(n, tabHost.nSpecies, offAng, hist, cursor, segs, nSeg, sortedOrig, rowMap, out, stride);
+    count_launch(2);
+}
+
+void angular_v2_forward(int n, const AniTables& tabHost, const AniTables* tab, const int* offAng, int capA, const float4* geoA,
+                        const float4* geoB, const int2* segs, const int* nSeg, const int* sortedOrig, const int* rowMap, AevOutPtr out,
+                        int stride, cudaStream_t stream) {
+    NNP_REQUIRE(2 * capA <= kFwdBudget, "angular neighbour capacity above 128 is not supported by the segment kernel");
+    const size_t smem = (size_t)kWarpsPerCta * kFwdBudget * 20;
+    auto k = ani_angular_fwd_seg_kernel<8, 4>;
+    set_smem_v2(k, smem);
+    // persistent: at most 3 CTAs per SM, never more CTAs than chunks of 8 segments could exist
+    const long long maxChunks = ((long long)n * tabHost.nPairs + 7) / 8;
+    const int grid = (int)std::min<long long>((long long)sm_count_v2() * 3, (maxChunks + kWarpsPerCta - 1) / kWarpsPerCta);
+    if (grid <= 0) return;
+    k<<<grid, kWarpsPerCta * 32, smem, stream>>>(tab, offAng, capA, geoA, geoB, segs, nSeg, sortedOrig, rowMap, out, stride);
+    count_launch();
+}
+
+void angular_v2_backward(int n, const AniTables& tabHost, const AniTables* tab, const int* offAng, int capA, const float4* geoA,
+                         const float4* geoB, const int* sortedOrig, const int* rowMap, const float* grad, int stride, float* posGrad,
+                         cudaStream_t stream) {
+    const size_t smem = (size_t)kWarpsPerCta * ((size_t)capA * 96 + (size_t)tabHost.nPairs * kBwdPitch * 4);
+    NNP_REQUIRE(smem <= 200 * 1024, "angular gradient row does not fit in shared memory (numSpecies^2 * numAngular too large)");
+    auto k = ani_angular_bwd_v2_kernel<8, 4>;
+    set_smem_v2(k, smem);
+    const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+    k<<<grid, kWarpsPerCta * 32, smem, stream>>>(n, tab, offAng, capA, geoA, geoB, sortedOrig, rowMap, grad, stride, posGrad);
+    count_launch();
+}
+
+}  // namespace nnpops

@@ -1,0 +1,34 @@
+// Angular AEV kernels, second generation (factorised TorchANI tables: 8 radial shifts x 4 angular shifts, ANI-2x; 4 x 8, ANI-1x).
+// Replaces the inner loops of CudaANISymmetryFunctions.cu:242-290 (forward) and :473-596 (backward); the mathematics is
+// CpuANISymmetryFunctions.cpp:139-194 / :265-353.  See ani_angular_v2.cu for the design.
+#pragma once
+#include "ani_aev.cuh"
+
+namespace nnpops {
+
+struct AevOutPtr {      // one AEV element is written as fp32, or as the fp16 hi/lo pair of the tensor-core MLP
+    float* f32;
+    __half* hi;
+    __half* lo;
+};
+
+constexpr int kSegBins = 512;      // segments are binned by their number of G-lane chunks (descending order in the list)
+constexpr int kSegGroup = 4;       // lanes per segment in the forward kernel
+
+// true when the tables / layout are the ones the v2 kernels are compiled for
+bool angular_v2_supported(const AniTables& t);
+
+// Segment list of one forward: every non-empty (centre, species pair) block, sorted by size (largest first).  Empty blocks are
+// zero-filled here.  hist [kSegBins] and cursor [kSegBins] are scratch, adjacent in memory (hist first).
+void angular_v2_build_segments(int n, const AniTables& tabHost, const int* offAng, const int* hist, int* cursor, int2* segs, int* nSeg,
+                               const int* sortedOrig, const int* rowMap, AevOutPtr out, int stride, cudaStream_t stream);
+
+void angular_v2_forward(int n, const AniTables& tabHost, const AniTables* tab, const int* offAng, int capA, const float4* geoA,
+                        const float4* geoB, const int2* segs, const int* nSeg, const int* sortedOrig, const int* rowMap, AevOutPtr out,
+                        int stride, cudaStream_t stream);
+
+void angular_v2_backward(int n, const AniTables& tabHost, const AniTables* tab, const int* offAng, int capA, const float4* geoA,
+                         const float4* geoB, const int* sortedOrig, const int* rowMap, const float* grad, int stride, float* posGrad,
+                         cudaStream_t stream);
+
+}  // namespace nnpops
