@@ -101,14 +101,16 @@ __device__ __forceinline__ int pair_index(int S, int s, int t) {   // CpuANISymm
 // Neighbour rows.  One warp per centre atom (sorted order).  Candidates come from the <= 18 contiguous runs of the cell
 // list; the accept test is the reference's fp32 expression (strict r2 < Rc^2, CpuANISymmetryFunctions.cpp:129-135).
 // ------------------------------------------------------------------------------------------------------------------
+#ifndef NNP_ROWS_MINB
+#define NNP_ROWS_MINB 5
+#endif
 template <bool SKIN>
-__global__ void __launch_bounds__(kWPB * 32)
+__global__ void __launch_bounds__(kWPB * 32, NNP_ROWS_MINB)
 ani_rows_kernel(int n, const float4* __restrict__ sorted, const int* __restrict__ sortedCell, const Geom* __restrict__ geom,
                 const int* __restrict__ cellStart, const AniTables* __restrict__ tab, int capR, int capA,
                 int* __restrict__ rowRad, int* __restrict__ rowAng, int* __restrict__ offRad, int* __restrict__ offAng,
                 int* __restrict__ flag, const int* __restrict__ sortedOrig, const unsigned char* __restrict__ owned,
-                const int* __restrict__ rebuild, float skinCut2, int capC, int* __restrict__ candRow, int* __restrict__ candCnt,
-                float4* __restrict__ geoA, float4* __restrict__ geoB) {
+                const int* __restrict__ rebuild, float skinCut2, int capC, int* __restrict__ candRow, int* __restrict__ candCnt) {
     // Verlet skin (candRow != nullptr): on a rebuild step (*rebuild != 0) the candidates of the cell-list scan that lie within
     // (Rcr + skin)^2 are also written to candRow; on the other steps the candidates come from candRow instead of the cells -- about
     // 75 distance tests per centre instead of 380 -- and every one takes the minimum-image step.  Either way the rows hold exactly
@@ -131,7 +133,6 @@ ani_rows_kernel(int n, const float4* __restrict__ sorted, const int* __restrict_
     uint32_t* list = reinterpret_cast<uint32_t*>(smemRaw) + (size_t)w * capR;
     int* cnt = reinterpret_cast<int*>(reinterpret_cast<uint32_t*>(smemRaw) + (size_t)kWPB * capR) + w * 128;
     int* cntR = cnt, *cntA = cnt + 32, *curR = cnt + 64, *curA = cnt + 96;
-    int* sAng = reinterpret_cast<int*>(reinterpret_cast<uint32_t*>(smemRaw) + (size_t)kWPB * capR) + kWPB * 128 + w * capA;
     const int S = tab->nSpecies;
     const float rcr2 = tab->rcr2, rca2 = tab->rca2;
     const float4 ci = sorted[p];
@@ -155,7 +156,7 @@ ani_rows_kernel(int n, const float4* __restrict__ sorted, const int* __restrict_
             cand = r2 < skinCut2;
             if (r2 < rcr2) {
                 ok = true;
-                packed = (uint32_t)q | ((uint32_t)__float_as_int(cj.w) << 24) | (r2 < rca2 ? 0x80000000u : 0u);
+                packed = (uint32_t)q | ((uint32_t)__float_as_int(cj.w) & 0x7f000000u) | (r2 < rca2 ? 0x80000000u : 0u);
             }
         }
         const unsigned m = __ballot_sync(kFull, ok);
@@ -245,31 +246,7 @@ ani_rows_kernel(int n, const float4* __restrict__ sorted, const int* __restrict_
         __syncwarp();
         const int j = (int)(e & 0x00ffffffu);
         if (valid) rowRad[(size_t)p * capR + dstR] = j;
-        if (ang && dstA < capA) {
-            rowAng[(size_t)p * capA + dstA] = j;
-            if (geoA != nullptr) sAng[dstA] = j | (s << 24);
-        }
-    }
-    if (geoA != nullptr) {
-        // geometry of the angular neighbours, computed once for the forward and the backward kernel (ani_angular_v2.cu): unit vector
-        // scaled by sqrt(cosScale) (so that uA . uB is the damped cosine), r / 2, fc, fc', 1 / r, species and atom index.  A pass of
-        // its own over the finished angular row: every lane busy, where the placement loop above holds ~30 % angular entries.
-        __syncwarp();
-        const int cntA = min(curA[S - 1], capA);      // curA[S - 1] has advanced to the total
-        const float invRca = 1.0f / tab->rca, kf = kPi * invRca, sq = sqrtf(tab->cosScale);
-        for (int q = lane; q < cntA; q += 32) {
-            const int e = sAng[q];
-            const int j = e & 0x00ffffff;
-            const float4 cj = sorted[j];
-            float dx = __fsub_rn(cj.x, ci.x), dy = __fsub_rn(cj.y, ci.y), dz = __fsub_rn(cj.z, ci.z);
-            const float r = sqrtf(min_image_mul(g, dx, dy, dz));
-            const float ir = 1.0f / r;
-            float sn, cs;
-            sincospif(r * invRca, &sn, &cs);
-            const float k = ir * sq;
-            geoA[(size_t)p * capA + q] = make_float4(dx * k, dy * k, dz * k, 0.5f * r);
-            geoB[(size_t)p * capA + q] = make_float4(0.5f * cs + 0.5f, -0.5f * kf * sn, ir, __int_as_float((e & 0x7f000000) | sortedOrig[j]));
-        }
+        if (ang && dstA < capA) rowAng[(size_t)p * capA + dstA] = j;
     }
 }
 
@@ -686,7 +663,7 @@ ani_radial_bwd_kernel(int n, const float4* __restrict__ sorted, const int* __res
     float* sGi = reinterpret_cast<float*>(smemRaw) + (size_t)w * S * nR;
     const int cnt = min(offRad[(size_t)p * (S + 1) + S], capR);
     const float4 ci = sorted[p];
-    const int sp = __float_as_int(ci.w);
+    const int sp = __float_as_int(ci.w) >> 24;
     const int orig = sortedOrig[p];
     {
         const float* gi = grad + (size_t)(rowMap ? rowMap[orig] : orig) * stride;
@@ -707,7 +684,7 @@ ani_radial_bwd_kernel(int n, const float4* __restrict__ sorted, const int* __res
         float sn, cs;
         sincosf(r * kf, &sn, &cs);
         const float fc = 0.5f * cs + 0.5f, dfc = -0.5f * kf * sn;
-        const float* gi = sGi + __float_as_int(cj.w) * nR;
+        const float* gi = sGi + (__float_as_int(cj.w) >> 24) * nR;
         float wsum = 0.0f;
         if (vec) {
             for (int k0 = 0; k0 < nR; k0 += 16) {
@@ -865,7 +842,7 @@ ani_radial_bwd_scatter_kernel(int n, const float4* __restrict__ sorted, const in
         float sn, cs;
         sincosf(r * kf, &sn, &cs);
         const float fc = 0.5f * cs + 0.5f, dfc = -0.5f * kf * sn;
-        const float* gi = sGi + __float_as_int(cj.w) * nR;
+        const float* gi = sGi + (__float_as_int(cj.w) >> 24) * nR;
         float wsum = 0.0f;
         for (int k = 0; k < nR; k++) {
             const float t = r - sShf[k];
@@ -933,7 +910,7 @@ ani_angular_bwd_fast_kernel(int n, const float4* __restrict__ sorted, const int*
         float sn, cs;
         sincosf(r * kf, &sn, &cs);
         sv[q] = make_float4(dx, dy, dz, r);
-        sw[q] = make_float4(1.0f / r, 0.5f * cs + 0.5f, -0.5f * kf * sn, cj.w);
+        sw[q] = make_float4(1.0f / r, 0.5f * cs + 0.5f, -0.5f * kf * sn, __int_as_float(__float_as_int(cj.w) >> 24));
         sorig[q] = sortedOrig[j];
         sfx[q] = 0.0f; sfy[q] = 0.0f; sfz[q] = 0.0f;
     }
@@ -1055,7 +1032,7 @@ ani_angular_bwd_kernel(int n, const float4* __restrict__ sorted, const int* __re
         sincosf(r * kf, &sn, &cs);
         sdx[q] = dx; sdy[q] = dy; sdz[q] = dz; sr[q] = r; sir[q] = 1.0f / r;
         sfc[q] = 0.5f * cs + 0.5f; sdfc[q] = -0.5f * kf * sn;
-        ssp[q] = __float_as_int(cj.w);
+        ssp[q] = __float_as_int(cj.w) >> 24;
         sorig[q] = sortedOrig[j];
         sfx[q] = 0.0f; sfy[q] = 0.0f; sfz[q] = 0.0f;
     }
@@ -1221,7 +1198,13 @@ AniAev::AniAev(int numAtoms, int numSpecies, float rcr, float rca, const int* at
     NNP_CUDA_CHECK(cudaMalloc(&tab_, sizeof(AniTables)));
     NNP_CUDA_CHECK(cudaMemcpy(tab_, &t, sizeof(AniTables), cudaMemcpyHostToDevice));
     NNP_CUDA_CHECK(cudaMalloc(&species_, sizeof(int) * na));
-    if (n_ > 0) NNP_CUDA_CHECK(cudaMemcpy(species_, atomSpecies, sizeof(int) * n_, cudaMemcpyHostToDevice));
+    if (n_ > 0) {
+        // the tag every atom carries through the cell list (float4.w of the sorted copy): species << 24 | atom index, so that one
+        // gather of a neighbour's coordinates also brings its species and its index (numAtoms < 2^24, numSpecies <= 32)
+        std::vector<int> tagged(n_);
+        for (int i = 0; i < n_; i++) tagged[i] = (atomSpecies[i] << 24) | i;
+        NNP_CUDA_CHECK(cudaMemcpy(species_, tagged.data(), sizeof(int) * n_, cudaMemcpyHostToDevice));
+    }
     cells_.init(n_);
     NNP_CUDA_CHECK(cudaMalloc(&rowRad_, sizeof(int) * na * capR_));
     NNP_CUDA_CHECK(cudaMalloc(&rowAng_, sizeof(int) * na * capA_));
@@ -1234,6 +1217,11 @@ AniAev::AniAev(int numAtoms, int numSpecies, float rcr, float rca, const int* at
         NNP_CUDA_CHECK(cudaMalloc(&segs_, sizeof(int2) * na * t.nPairs));
         NNP_CUDA_CHECK(cudaMalloc(&nSeg_, sizeof(int)));
         NNP_CUDA_CHECK(cudaMemset(nSeg_, 0, sizeof(int)));
+    }
+    NNP_CUDA_CHECK(cudaMalloc(&gradAcc_, sizeof(float4) * na));
+    if (radial_v2_supported(t) && std::getenv("NNPOPS_RADIAL_V1") == nullptr) {
+        NNP_CUDA_CHECK(cudaMalloc(&radGeoA_, sizeof(float4) * na * capR_));
+        NNP_CUDA_CHECK(cudaMalloc(&radGeoB_, sizeof(float4) * na * capR_));
     }
     NNP_CUDA_CHECK(cudaMalloc(&flag_, sizeof(int)));
     NNP_CUDA_CHECK(cudaMemset(flag_, 0, sizeof(int)));
@@ -1281,6 +1269,7 @@ AniAev::~AniAev() {
     cudaFree(candRow_); cudaFree(candCnt_); cudaFree(skinRefPos_); cudaFree(skinRefBox_); cudaFree(skinRebuild_); cudaFree(skinStats_);
     cudaFree(tab_); cudaFree(species_); cudaFree(rowRad_); cudaFree(rowAng_); cudaFree(offRad_); cudaFree(offAng_);
     cudaFree(flag_); cudaFree(counters_);
+    cudaFree(radGeoA_); cudaFree(radGeoB_); cudaFree(gradAcc_);
     cudaFree(geoA_); cudaFree(geoB_); cudaFree(segHist_); cudaFree(segs_); cudaFree(nSeg_);
     if (flagHost_) cudaFreeHost(flagHost_);
     if (aux_) cudaStreamDestroy(aux_);
@@ -1333,25 +1322,27 @@ void AniAev::forward(const float* positions, const float* box, float* radial, in
     } else {
         cells_.build<float>(positions, box, species_, cut, stream);
     }
-    // second-generation angular kernels (ani_angular_v2.cu): the row kernel also writes the neighbour geometry and the size histogram
-    // of the (centre, species pair) blocks
+    // second-generation angular kernels (ani_angular_v2.cu): geometry rows of the angular neighbours, size-sorted (centre, species
+    // pair) segments, TMA-staged forward and backward kernels
     const bool v2 = useV2(angular, angularStride, splitHi, splitLo);
     lastForwardV2_ = v2;
+    // radial path, second generation: pair geometry (kept for the backward kernel) and the radial AEV in one kernel
+    const bool rv2 = radGeoA_ != nullptr && (radialStride & 1) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(radial) | reinterpret_cast<uintptr_t>(splitHi) | reinterpret_cast<uintptr_t>(splitLo)) & 7) == 0;
+    lastForwardRadV2_ = rv2;
     {
-        const size_t smem = (size_t)kWPB * capR_ * sizeof(uint32_t) + (size_t)kWPB * 128 * sizeof(int) + (size_t)kWPB * capA_ * sizeof(int);
+        const size_t smem = (size_t)kWPB * capR_ * sizeof(uint32_t) + (size_t)kWPB * 128 * sizeof(int);
         const float sc = cut + skin_;
         if (skin_ > 0.0f) {
             set_smem(ani_rows_kernel<true>, smem);
             ani_rows_kernel<true><<<grid, kWPB * 32, smem, stream>>>(n_, cells_.sorted, cells_.sortedCell, cells_.geom, cells_.cellStart, tab_,
                                                                    capR_, capA_, rowRad_, rowAng_, offRad_, offAng_, flag_, cells_.sortedOrig, owned_,
-                                                                   skinRebuild_, sc * sc, capC_, candRow_, candCnt_, v2 ? geoA_ : nullptr,
-                                                                   v2 ? geoB_ : nullptr);
+                                                                   skinRebuild_, sc * sc, capC_, candRow_, candCnt_);
         } else {
             set_smem(ani_rows_kernel<false>, smem);
             ani_rows_kernel<false><<<grid, kWPB * 32, smem, stream>>>(n_, cells_.sorted, cells_.sortedCell, cells_.geom, cells_.cellStart, tab_,
                                                                     capR_, capA_, rowRad_, rowAng_, offRad_, offAng_, flag_, cells_.sortedOrig, owned_,
-                                                                    nullptr, 0.0f, 0, nullptr, nullptr, v2 ? geoA_ : nullptr,
-                                                                    v2 ? geoB_ : nullptr);
+                                                                    nullptr, 0.0f, 0, nullptr, nullptr);
         }
         count_launch();
     }
@@ -1367,7 +1358,11 @@ void AniAev::forward(const float* positions, const float* box, float* radial, in
     // 4 bytes to pinned memory behind the row kernel (on the side stream when there is one, off the critical path): overflowPoll()
     // then sees a truncated row without anybody blocking
     NNP_CUDA_CHECK(cudaMemcpyAsync(flagHost_, flag_, sizeof(int), cudaMemcpyDeviceToHost, rs));
-    if (tabHost_.nRadial > 0) {
+    if (tabHost_.nRadial > 0 && rv2) {
+        const AevOutPtr o = {radialOut.f32, radialOut.hi, radialOut.lo};
+        radial_v2_forward(n_, tabHost_, tab_, cells_.sorted, cells_.sortedOrig, cells_.geom, rowRad_, offRad_, capR_, radGeoA_, radGeoB_, rowMap_, o,
+                          radialStride, rs);
+    } else if (tabHost_.nRadial > 0) {
         const size_t smem = (size_t)kWPB * 2 * capR_ * sizeof(float);
         set_smem(ani_radial_fwd_kernel, smem);
         ani_radial_fwd_kernel<<<grid, kWPB * 32, smem, rs>>>(n_, cells_.sorted, cells_.sortedOrig, cells_.geom, tab_, rowRad_, offRad_,
@@ -1378,6 +1373,7 @@ void AniAev::forward(const float* positions, const float* box, float* radial, in
     if (ev) cudaEventRecord(ev[1], stream);
     if (tabHost_.nAngular > 0 && v2) {
         const AevOutPtr o = {angularOut.f32, angularOut.hi, angularOut.lo};
+        angular_v2_geometry(n_, tabHost_, tab_, cells_.sorted, cells_.sortedOrig, cells_.geom, rowAng_, offAng_, capA_, geoA_, geoB_, stream);
         angular_v2_build_segments(n_, tabHost_, offAng_, segHist_, segHist_ + kSegBins, segs_, nSeg_, cells_.sortedOrig, rowMap_, o, angularStride, stream);
         angular_v2_forward(n_, tabHost_, tab_, offAng_, capA_, geoA_, geoB_, segs_, nSeg_, cells_.sortedOrig, rowMap_, o, angularStride, stream);
     } else if (tabHost_.nAngular > 0) {
@@ -1417,14 +1413,21 @@ void AniAev::backward(const float* radialGrad, int radialStride, const float* an
     if (n_ == 0) return;
     NNP_REQUIRE(haveForward_, "backward() called before forward()");
     const int grid = (n_ + kWPB - 1) / kWPB;
-    NNP_CUDA_CHECK(cudaMemsetAsync(positionGrad, 0, sizeof(float) * 3 * n_, stream));
+    const bool angV2 = tabHost_.nAngular > 0 && lastForwardV2_ && (angularStride & 3) == 0 && (reinterpret_cast<uintptr_t>(angularGrad) & 15) == 0;
+    const bool radV2 = tabHost_.nRadial > 0 && lastForwardRadV2_ && (radialStride & 3) == 0 && (reinterpret_cast<uintptr_t>(radialGrad) & 15) == 0;
+    // both second-generation kernels: forces go into a padded [n][4] buffer by 16-byte vector reductions, copied out at the end
+    const bool padded = (angV2 || tabHost_.nAngular == 0) && (radV2 || tabHost_.nRadial == 0) && gradAcc_ != nullptr;
+    float* acc = padded ? reinterpret_cast<float*>(gradAcc_) : positionGrad;
+    NNP_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(float) * (padded ? 4 : 3) * n_, stream));
     const bool fork = tabHost_.nRadial > 0 && tabHost_.nAngular > 0;
     cudaStream_t rs = fork ? aux_ : stream;
     if (fork) {
         NNP_CUDA_CHECK(cudaEventRecord(evFork_, stream));
         NNP_CUDA_CHECK(cudaStreamWaitEvent(aux_, evFork_, 0));
     }
-    if (tabHost_.nRadial > 0) {
+    if (radV2) {
+        radial_v2_backward(n_, tabHost_, tab_, offRad_, capR_, radGeoA_, radGeoB_, cells_.sortedOrig, rowMap_, radialGrad, radialStride, acc, padded, rs);
+    } else if (tabHost_.nRadial > 0) {
         const size_t smem = (size_t)kWPB * tabHost_.nSpecies * tabHost_.nRadial * sizeof(float);
         // the centre-owned (scatter) form is required when the box is sharded and is also the faster one on a single GPU (no
         // gathers of neighbour gradient rows: 0.224 vs 0.255 ms for the backward stage); NNPOPS_RADIAL_GATHER selects the gather form
@@ -1437,8 +1440,8 @@ void AniAev::backward(const float* radialGrad, int radialStride, const float* an
     }
     if (fork) NNP_CUDA_CHECK(cudaEventRecord(evJoin_, aux_));
     if (ev) cudaEventRecord(ev[0], stream);
-    if (tabHost_.nAngular > 0 && lastForwardV2_ && (angularStride & 3) == 0 && (reinterpret_cast<uintptr_t>(angularGrad) & 15) == 0) {
-        angular_v2_backward(n_, tabHost_, tab_, offAng_, capA_, geoA_, geoB_, cells_.sortedOrig, rowMap_, angularGrad, angularStride, positionGrad, stream);
+    if (angV2) {
+        angular_v2_backward(n_, tabHost_, tab_, offAng_, capA_, geoA_, geoB_, cells_.sortedOrig, rowMap_, angularGrad, angularStride, acc, padded, stream);
     } else if (tabHost_.nAngular > 0) {
         const int gPitch = tabHost_.nAngular + 1;
         const size_t smem = (size_t)kWPB * ((size_t)12 * capA_ + (size_t)tabHost_.nPairs * gPitch) * sizeof(float);
@@ -1459,6 +1462,7 @@ void AniAev::backward(const float* radialGrad, int radialStride, const float* an
         count_launch();
     }
     if (fork) NNP_CUDA_CHECK(cudaStreamWaitEvent(stream, evJoin_, 0));
+    if (padded) grad_compact(n_, gradAcc_, positionGrad, stream);
     NNP_CUDA_CHECK(cudaGetLastError());
 }
 

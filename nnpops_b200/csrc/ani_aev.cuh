@@ -110,6 +110,10 @@ private:
     int2* segs_ = nullptr;       // [n * nPairs] non-empty blocks, largest first
     int* nSeg_ = nullptr;
     bool lastForwardV2_ = false;
+    float4* radGeoA_ = nullptr;  // [n][capR] {unit vector, r} of every radial pair, species-grouped like rowRad
+    float4* radGeoB_ = nullptr;  // [n][capR] {fc, fc', species << 24 | atom index, -}
+    bool lastForwardRadV2_ = false;
+    float4* gradAcc_ = nullptr;  // [n] padded force accumulator of the second-generation backward kernels
     bool useV2(const float* angular, int angularStride, const __half* splitHi, const __half* splitLo) const;
     const int* rowMap_ = nullptr;
     const unsigned char* owned_ = nullptr;

@@ -38,6 +38,13 @@ __device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f3
 __device__ __forceinline__ float lg2a(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rsqrta(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+typedef unsigned long long u64;   // packed fp32x2 (FADD2 / FMUL2 / FFMA2: one issue slot for two lanes of work)
+__device__ __forceinline__ u64 pk2(float x, float y) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ void unpk2(u64 v, float& x, float& y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -63,6 +70,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// accumulate a force on an atom: one 16-byte vector reduction into a padded [n][4] buffer (VEC), or three scalar ones into [n][3]
+template <bool VEC>
+__device__ __forceinline__ void grad_add(float* __restrict__ dst, size_t atom, float x, float y, float z) {
+    if (VEC) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * atom), "f"(x), "f"(y), "f"(z), "f"(0.0f) : "memory");
+    } else {
+        atomicAdd(dst + 3 * atom, x); atomicAdd(dst + 3 * atom + 1, y); atomicAdd(dst + 3 * atom + 2, z);
+    }
 }
 
 __device__ __forceinline__ int pair_index(int S, int s, int t) {   // CpuANISymmetryFunctions.cpp:39-43, s <= t
@@ -168,8 +185,11 @@ ani_seg_scatter_kernel(int n, int S, const int* __restrict__ offAng, const int* 
 // ------------------------------------------------------------------------------------------------------------------
 // Forward
 // ------------------------------------------------------------------------------------------------------------------
+#ifndef NNP_FWD_MINB
+#define NNP_FWD_MINB 3
+#endif
 template <int NSA, int NSZ>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 3)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, NNP_FWD_MINB)
 ani_angular_fwd_seg_kernel(const AniTables* __restrict__ tab, const int* __restrict__ offAng, int capA, const float4* __restrict__ geoA,
                            const float4* __restrict__ geoB, const int2* __restrict__ segs, const int* __restrict__ nSegPtr,
                            const int* __restrict__ sortedOrig, const int* __restrict__ rowMap, AevOutPtr out, int stride) {
@@ -316,7 +336,7 @@ ani_angular_fwd_seg_kernel(const AniTables* __restrict__ tab, const int* __restr
 // ------------------------------------------------------------------------------------------------------------------
 // Backward
 // ------------------------------------------------------------------------------------------------------------------
-template <int NSA, int NSZ>
+template <int NSA, int NSZ, bool VEC>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 4)
 ani_angular_bwd_v2_kernel(int n, const AniTables* __restrict__ tab, const int* __restrict__ offAng, int capA,
                           const float4* __restrict__ geoA, const float4* __restrict__ geoB, const int* __restrict__ sortedOrig,
@@ -435,15 +455,223 @@ ani_angular_bwd_v2_kernel(int n, const AniTables* __restrict__ tab, const int* _
     for (int q = lane; q < cnt; q += 32) {
         const float4 x0 = sAcc[q], x1 = sAcc[capA + q], y0 = sAcc[2 * capA + q], y1 = sAcc[3 * capA + q];
         const float fx = (x0.x + x1.x) + (y0.x + y1.x), fy = (x0.y + x1.y) + (y0.y + y1.y), fz = (x0.z + x1.z) + (y0.z + y1.z);
-        float* dst = posGrad + 3 * (size_t)(__float_as_int(sB[q].w) & 0x00ffffff);
-        atomicAdd(dst, fx); atomicAdd(dst + 1, fy); atomicAdd(dst + 2, fz);
+        grad_add<VEC>(posGrad, (size_t)(__float_as_int(sB[q].w) & 0x00ffffff), fx, fy, fz);
         cx -= fx; cy -= fy; cz2 -= fz;
     }
     cx = warp_sum(cx); cy = warp_sum(cy); cz2 = warp_sum(cz2);
-    if (lane == 0) {
-        float* dst = posGrad + 3 * (size_t)orig;
-        atomicAdd(dst, cx); atomicAdd(dst + 1, cy); atomicAdd(dst + 2, cz2);
+    if (lane == 0) grad_add<VEC>(posGrad, (size_t)orig, cx, cy, cz2);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Geometry of the angular neighbours (geoA / geoB, see the top of the file): 8 lanes per centre, 4 centres per warp.
+// delta and r2 are the reference's fp32 expressions (min_image_mul), as in the row kernel that accepted the pair.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ani_angular_geo_kernel(int n, const AniTables* __restrict__ tab, const float4* __restrict__ sorted, const int* __restrict__ sortedOrig,
+                       const Geom* __restrict__ geom, const int* __restrict__ rowAng, const int* __restrict__ offAng, int capA,
+                       float4* __restrict__ geoA, float4* __restrict__ geoB) {
+    __shared__ Geom g;
+    if (threadIdx.x == 0) g = *geom;
+    __syncthreads();
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, gl = threadIdx.x & 7;
+    if (p >= n) return;
+    const int S = tab->nSpecies;
+    const int cnt = offAng[(size_t)p * (S + 1) + S];
+    const float4 ci = sorted[p];
+    const float invRca = 1.0f / tab->rca, sq = sqrtf(tab->cosScale);
+    for (int q0 = 0; q0 < cnt; q0 += 32) {       // 4 entries per lane per trip: all index loads, then all coordinate gathers, in flight together
+        int j[4];
+        float4 cj[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int q = q0 + gl + 8 * u; j[u] = q < cnt ? rowAng[(size_t)p * capA + q] : -1; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) cj[u] = j[u] >= 0 ? sorted[j[u]] : ci;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (j[u] < 0) continue;
+            const int q = q0 + gl + 8 * u;
+            float dx = __fsub_rn(cj[u].x, ci.x), dy = __fsub_rn(cj[u].y, ci.y), dz = __fsub_rn(cj[u].z, ci.z);
+            const float r = sqrtf(min_image_mul(g, dx, dy, dz));
+            const float ir = 1.0f / r;
+            float sn, cs;
+            sincospif(r * invRca, &sn, &cs);
+            const float k = ir * sq;
+            geoA[(size_t)p * capA + q] = make_float4(dx * k, dy * k, dz * k, 0.5f * r);
+            geoB[(size_t)p * capA + q] = make_float4(0.5f * cs + 0.5f, -0.5f * kPi * invRca * sn, ir, cj[u].w);   // .w: species << 24 | atom index
+        }
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Radial forward (CpuANISymmetryFunctions.cpp:139-160), warp per centre.  Pass 1, lane <-> neighbour: pair geometry, written to
+// radGeoA = {unit vector, r} / radGeoB = {fc, fc', species << 24 | atom index} for the backward kernel and staged as (r, fc) in
+// shared memory.  Pass 2, lane = (h, kq): kq owns the channel pair (2 kq, 2 kq + 1) -- packed fp32x2 arithmetic -- and h is one
+// of 32 / KQ neighbour sub-streams; one shuffle reduction over h per species block.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+ani_radial_fwd_v2_kernel(int n, const AniTables* __restrict__ tab, const float4* __restrict__ sorted, const int* __restrict__ sortedOrig,
+                         const Geom* __restrict__ geom, const int* __restrict__ rowRad, const int* __restrict__ offRad, int capR,
+                         float4* __restrict__ radGeoA, float4* __restrict__ radGeoB, const int* __restrict__ rowMap, AevOutPtr out,
+                         int stride) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    __shared__ Geom g;
+    if (threadIdx.x == 0) g = *geom;
+    __syncthreads();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * kWarpsPerCta + w;
+    if (p >= n) return;
+    float2* sRF = reinterpret_cast<float2*>(smemRaw) + (size_t)w * capR;
+    const int S = tab->nSpecies, nR = tab->nRadial;
+    const int* off = offRad + (size_t)p * (S + 1);
+    const int cnt = min(off[S], capR);
+    const float4 ci = sorted[p];
+    const float invRcr = 1.0f / tab->rcr;
+    for (int q0 = 0; q0 < cnt; q0 += 64) {       // two entries per lane per trip, both gathers in flight together
+        int j[2];
+        float4 cj[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) { const int q = q0 + lane + 32 * u; j[u] = q < cnt ? rowRad[(size_t)p * capR + q] : -1; }
+#pragma unroll
+        for (int u = 0; u < 2; u++) cj[u] = j[u] >= 0 ? sorted[j[u]] : ci;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            if (j[u] < 0) continue;
+            const int q = q0 + lane + 32 * u;
+            float dx = __fsub_rn(cj[u].x, ci.x), dy = __fsub_rn(cj[u].y, ci.y), dz = __fsub_rn(cj[u].z, ci.z);
+            const float r = sqrtf(min_image_mul(g, dx, dy, dz));
+            const float ir = 1.0f / r;
+            float sn, cs;
+            sincospif(r * invRcr, &sn, &cs);
+            const float fc = 0.5f * cs + 0.5f;
+            radGeoA[(size_t)p * capR + q] = make_float4(dx * ir, dy * ir, dz * ir, r);
+            radGeoB[(size_t)p * capR + q] = make_float4(fc, -0.5f * kPi * invRcr * sn, cj[u].w, 0.0f);   // .z: species << 24 | atom index
+            sRF[q] = make_float2(r, fc);
+        }
+    }
+    __syncwarp();
+    int KQ = 1;
+    while (2 * KQ < nR) KQ <<= 1;
+    const int H = 32 / KQ, kq = lane % KQ, h = lane / KQ;
+    const bool kval = 2 * kq < nR;             // nR is even on this path
+    const float nEta = -tab->rEtaL2[0], scale = tab->radialScale;
+    const u64 nEta2 = pk2(nEta, nEta);
+    const u64 nShf2 = kval ? pk2(-tab->rShf[2 * kq], -tab->rShf[2 * kq + 1]) : pk2(0.f, 0.f);
+    const int orig = sortedOrig[p];
+    const size_t orow = (size_t)(rowMap ? rowMap[orig] : orig) * stride;
+    for (int sp = 0; sp < S; sp++) {
+        const int b = min(off[sp], cnt), e2 = min(off[sp + 1], cnt);
+        u64 acc = pk2(0.f, 0.f);
+        for (int q = b + h; q < e2; q += H) {
+            const float2 rf = sRF[q];
+            const u64 t2 = fadd2(pk2(rf.x, rf.x), nShf2);
+            const u64 a2 = fmul2(fmul2(t2, nEta2), t2);
+            float a0, a1;
+            unpk2(a2, a0, a1);
+            acc = ffma2(pk2(rf.y, rf.y), pk2(ex2a(a0), ex2a(a1)), acc);
+        }
+        float v0, v1;
+        unpk2(acc, v0, v1);
+        for (int o = KQ; o < 32; o <<= 1) { v0 += __shfl_xor_sync(kFull, v0, o); v1 += __shfl_xor_sync(kFull, v1, o); }
+        if (h == 0 && kval) {
+            const size_t idx = orow + (size_t)sp * nR + 2 * kq;
+            v0 *= scale; v1 *= scale;
+            if (out.hi) {
+                const __half2 h2 = __floats2half2_rn(v0, v1);
+                const float2 f2 = __half22float2(h2);
+                *reinterpret_cast<__half2*>(out.hi + idx) = h2;
+                *reinterpret_cast<__half2*>(out.lo + idx) = __floats2half2_rn((v0 - f2.x) * 2048.0f, (v1 - f2.y) * 2048.0f);
+            } else {
+                *reinterpret_cast<float2*>(out.f32 + idx) = make_float2(v0, v1);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Radial backward, centre-owned (CpuANISymmetryFunctions.cpp:228-263 restricted to the centre's own AEV row; summed over all
+// centres -- or ranks -- it equals the reference's gather form).  Warp per centre, lane <-> neighbour; the pair geometry comes from
+// the rows the row kernel wrote (coalesced 16-byte loads, nothing is re-derived), the centre's gradient row is staged by one bulk copy:
+//   w_ij = scale * sum_k G[i][s_j][k] e_k (fc' - 2 eta (r - Rs_k) fc) = scale * (fc' S0 - 2 eta fc S1),
+//   S0 = sum_k g_k e_k,  S1 = sum_k g_k e_k (r - Rs_k)
+// evaluated two channels at a time in packed fp32x2.
+// ------------------------------------------------------------------------------------------------------------------
+template <int NR, bool VEC>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+ani_radial_bwd_v2_kernel(int n, const AniTables* __restrict__ tab, const int* __restrict__ offRad, int capR,
+                         const float4* __restrict__ radGeoA, const float4* __restrict__ radGeoB, const int* __restrict__ sortedOrig,
+                         const int* __restrict__ rowMap, const float* __restrict__ grad, int stride, float* __restrict__ posGrad) {
+    static_assert(NR % 4 == 0, "channel quads");
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    __shared__ __align__(8) unsigned long long bars[kWarpsPerCta];
+    const int S = tab->nSpecies;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) mbar_init(smem_u32(&bars[w]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const int p = blockIdx.x * kWarpsPerCta + w;
+    if (p >= n) return;
+    const int cnt = min(offRad[(size_t)p * (S + 1) + S], capR);
+    if (cnt == 0) return;                      // also every centre owned by another rank
+    float* sG = reinterpret_cast<float*>(smemRaw) + (size_t)w * S * NR;
+    const uint32_t bar = smem_u32(&bars[w]);
+    const int orig = sortedOrig[p];
+    const float* gi = grad + (size_t)(rowMap ? rowMap[orig] : orig) * stride;
+    if (lane == 0) {
+        mbar_expect_tx(bar, (uint32_t)(S * NR * 4));
+        bulk_g2s(smem_u32(sG), gi, (uint32_t)(S * NR * 4), bar);
+    }
+    const float nEta = -tab->rEtaL2[0];
+    const u64 nEta2 = pk2(nEta, nEta);
+    u64 nShf2[NR / 2];
+#pragma unroll
+    for (int k = 0; k < NR / 2; k++) nShf2[k] = pk2(-tab->rShf[2 * k], -tab->rShf[2 * k + 1]);
+    const float sc = tab->radialScale, m2eta = -2.0f * tab->rEta[0];
+    mbar_wait(bar, 0);
+    float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+    for (int q0 = 0; q0 < cnt; q0 += 64) {       // two pairs per lane per trip: the four 16-byte loads are in flight together
+        float4 gaa[2], gbb[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int q = q0 + lane + 32 * u;
+            if (q < cnt) { gaa[u] = radGeoA[(size_t)p * capR + q]; gbb[u] = radGeoB[(size_t)p * capR + q]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            if (q0 + lane + 32 * u >= cnt) continue;
+            const float4 ga = gaa[u], gb = gbb[u];
+            const int tagged = __float_as_int(gb.z);
+            const float* gp = sG + (tagged >> 24) * NR;
+            const u64 r2 = pk2(ga.w, ga.w);
+            u64 S0 = pk2(0.f, 0.f), S1 = pk2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < NR / 2; k += 2) {
+                const float4 g4 = *reinterpret_cast<const float4*>(gp + 2 * k);
+                const u64 t0 = fadd2(r2, nShf2[k]), t1 = fadd2(r2, nShf2[k + 1]);
+                const u64 a0 = fmul2(fmul2(t0, nEta2), t0), a1 = fmul2(fmul2(t1, nEta2), t1);
+                float x0, x1, x2, x3;
+                unpk2(a0, x0, x1); unpk2(a1, x2, x3);
+                const u64 e0 = pk2(ex2a(x0), ex2a(x1)), e1 = pk2(ex2a(x2), ex2a(x3));
+                const u64 g0 = pk2(g4.x, g4.y), g1 = pk2(g4.z, g4.w);
+                S0 = ffma2(g0, e0, S0); S0 = ffma2(g1, e1, S0);
+                S1 = ffma2(g0, fmul2(e0, t0), S1); S1 = ffma2(g1, fmul2(e1, t1), S1);
+            }
+            float s00, s01, s10, s11;
+            unpk2(S0, s00, s01); unpk2(S1, s10, s11);
+            const float wr = sc * fmaf(gb.y, s00 + s01, m2eta * gb.x * (s10 + s11));
+            const float gx = wr * ga.x, gy = wr * ga.y, gz = wr * ga.z;
+            fx -= gx; fy -= gy; fz -= gz;
+            grad_add<VEC>(posGrad, (size_t)(tagged & 0x00ffffff), gx, gy, gz);
+        }
+    }
+    fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
+    if (lane == 0) grad_add<VEC>(posGrad, (size_t)orig, fx, fy, fz);
+}
+
+__global__ void grad_compact_kernel(int n, const float4* __restrict__ acc, float* __restrict__ posGrad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 v = acc[i];
+    posGrad[3 * (size_t)i] = v.x; posGrad[3 * (size_t)i + 1] = v.y; posGrad[3 * (size_t)i + 2] = v.z;
 }
 
 template <typename K>
@@ -470,6 +698,53 @@ int sm_count_v2() {
 
 }  // namespace
 
+bool radial_v2_supported(const AniTables& t) {
+    if (t.nRadial != 16 || !t.torchani) return false;
+    for (int k = 1; k < t.nRadial; k++)
+        if (t.rEta[k] != t.rEta[0]) return false;
+    return true;
+}
+
+void radial_v2_forward(int n, const AniTables& tabHost, const AniTables* tab, const float4* sorted, const int* sortedOrig, const Geom* geom,
+                       const int* rowRad, const int* offRad, int capR, float4* radGeoA, float4* radGeoB, const int* rowMap, AevOutPtr out,
+                       int stride, cudaStream_t stream) {
+    const size_t smem = (size_t)kWarpsPerCta * capR * sizeof(float2);
+    auto k = ani_radial_fwd_v2_kernel;
+    set_smem_v2(k, smem);
+    const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+    k<<<grid, kWarpsPerCta * 32, smem, stream>>>(n, tab, sorted, sortedOrig, geom, rowRad, offRad, capR, radGeoA, radGeoB, rowMap, out, stride);
+    count_launch();
+}
+
+void angular_v2_geometry(int n, const AniTables& tabHost, const AniTables* tab, const float4* sorted, const int* sortedOrig, const Geom* geom,
+                         const int* rowAng, const int* offAng, int capA, float4* geoA, float4* geoB, cudaStream_t stream) {
+    const long long threads = (long long)n * 8;
+    ani_angular_geo_kernel<<<(int)((threads + 255) / 256), 256, 0, stream>>>(n, tab, sorted, sortedOrig, geom, rowAng, offAng, capA, geoA, geoB);
+    count_launch();
+}
+
+void radial_v2_backward(int n, const AniTables& tabHost, const AniTables* tab, const int* offRad, int capR, const float4* radGeoA,
+                        const float4* radGeoB, const int* sortedOrig, const int* rowMap, const float* grad, int stride, float* posGrad,
+                        bool padded, cudaStream_t stream) {
+    const size_t smem = (size_t)kWarpsPerCta * tabHost.nSpecies * 16 * sizeof(float);
+    const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (padded) {
+        auto k = ani_radial_bwd_v2_kernel<16, true>;
+        set_smem_v2(k, smem);
+        k<<<grid, kWarpsPerCta * 32, smem, stream>>>(n, tab, offRad, capR, radGeoA, radGeoB, sortedOrig, rowMap, grad, stride, posGrad);
+    } else {
+        auto k = ani_radial_bwd_v2_kernel<16, false>;
+        set_smem_v2(k, smem);
+        k<<<grid, kWarpsPerCta * 32, smem, stream>>>(n, tab, offRad, capR, radGeoA, radGeoB, sortedOrig, rowMap, grad, stride, posGrad);
+    }
+    count_launch();
+}
+
+void grad_compact(int n, const float4* acc, float* posGrad, cudaStream_t stream) {
+    grad_compact_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, acc, posGrad);
+    count_launch();
+}
+
 bool angular_v2_supported(const AniTables& t) {
     return t.fast && t.nShfA == 8 && t.nShfZ == 4 && t.torchani && t.nAngular == 32 && t.nSpecies <= 15;
 }
@@ -492,7 +767,7 @@ void angular_v2_forward(int n, const AniTables& tabHost, const AniTables* tab, c
     set_smem_v2(k, smem);
     // persistent: at most 3 CTAs per SM, never more CTAs than chunks of 8 segments could exist
     const long long maxChunks = ((long long)n * tabHost.nPairs + 7) / 8;
-    const int grid = (int)std::min<long long>((long long)sm_count_v2() * 3, (maxChunks + kWarpsPerCta - 1) / kWarpsPerCta);
+    const int grid = (int)std::min<long long>((long long)sm_count_v2() * NNP_FWD_MINB, (maxChunks + kWarpsPerCta - 1) / kWarpsPerCta);
     if (grid <= 0) return;
     k<<<grid, kWarpsPerCta * 32, smem, stream>>>(tab, offAng, capA, geoA, geoB, segs, nSeg, sortedOrig, rowMap, out, stride);
     count_launch();
@@ -500,13 +775,19 @@ void angular_v2_forward(int n, const AniTables& tabHost, const AniTables* tab, c
 
 void angular_v2_backward(int n, const AniTables& tabHost, const AniTables* tab, const int* offAng, int capA, const float4* geoA,
                          const float4* geoB, const int* sortedOrig, const int* rowMap, const float* grad, int stride, float* posGrad,
-                         cudaStream_t stream) {
+                         bool padded, cudaStream_t stream) {
     const size_t smem = (size_t)kWarpsPerCta * ((size_t)capA * 96 + (size_t)tabHost.nPairs * kBwdPitch * 4);
     NNP_REQUIRE(smem <= 200 * 1024, "angular gradient row does not fit in shared memory (numSpecies^2 * numAngular too large)");
-    auto k = ani_angular_bwd_v2_kernel<8, 4>;
-    set_smem_v2(k, smem);
     const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
-    k<<<grid, kWarpsPerCta * 32, smem, stream>>>(n, tab, offAng, capA, geoA, geoB, sortedOrig, rowMap, grad, stride, posGrad);
+    if (padded) {
+        auto k = ani_angular_bwd_v2_kernel<8, 4, true>;
+        set_smem_v2(k, smem);
+        k<<<grid, kWarpsPerCta * 32, smem, stream>>>(n, tab, offAng, capA, geoA, geoB, sortedOrig, rowMap, grad, stride, posGrad);
+    } else {
+        auto k = ani_angular_bwd_v2_kernel<8, 4, false>;
+        set_smem_v2(k, smem);
+        k<<<grid, kWarpsPerCta * 32, smem, stream>>>(n, tab, offAng, capA, geoA, geoB, sortedOrig, rowMap, grad, stride, posGrad);
+    }
     count_launch();
 }
 

@@ -29,6 +29,23 @@ void angular_v2_forward(int n, const AniTables& tabHost, const AniTables* tab, c
 
 void angular_v2_backward(int n, const AniTables& tabHost, const AniTables* tab, const int* offAng, int capA, const float4* geoA,
                          const float4* geoB, const int* sortedOrig, const int* rowMap, const float* grad, int stride, float* posGrad,
-                         cudaStream_t stream);
+                         bool padded, cudaStream_t stream);
+
+// Radial path, second generation: the forward kernel evaluates the pair geometry once and the radial AEV with it; the backward
+// kernel reads the geometry rows  radGeoA = {unit vector, r},  radGeoB = {fc, fc', species << 24 | atom index, -}.
+// Supported for 16 radial functions with one EtaR (ANI-1x / ANI-2x).
+bool radial_v2_supported(const AniTables& t);
+void radial_v2_forward(int n, const AniTables& tabHost, const AniTables* tab, const float4* sorted, const int* sortedOrig, const Geom* geom,
+                       const int* rowRad, const int* offRad, int capR, float4* radGeoA, float4* radGeoB, const int* rowMap, AevOutPtr out,
+                       int stride, cudaStream_t stream);
+// geometry rows of the angular neighbours (geoA / geoB) from the index rows of the row kernel
+void angular_v2_geometry(int n, const AniTables& tabHost, const AniTables* tab, const float4* sorted, const int* sortedOrig, const Geom* geom,
+                         const int* rowAng, const int* offAng, int capA, float4* geoA, float4* geoB, cudaStream_t stream);
+void radial_v2_backward(int n, const AniTables& tabHost, const AniTables* tab, const int* offRad, int capR, const float4* radGeoA,
+                        const float4* radGeoB, const int* sortedOrig, const int* rowMap, const float* grad, int stride, float* posGrad,
+                        bool padded, cudaStream_t stream);
+// posGrad of the backward kernels: [n][3] accumulated with scalar reductions, or (padded) a zeroed [n][4] buffer accumulated with one
+// 16-byte vector reduction per force (red.global.add.v4.f32: a third of the L2 atomic operations) and copied out by grad_compact
+void grad_compact(int n, const float4* acc, float* posGrad, cudaStream_t stream);
 
 }  // namespace nnpops

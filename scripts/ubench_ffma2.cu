@@ -42,7 +42,60 @@ void run(const char* name) {
            ms * 1e-3 * 1.965e9 / (iters * 16.0));   // 16 warps per SMSP share the slot
     cudaFree(out);
 }
+// a loop shaped like the angular kernels: NF independent FFMA (or NF / 2 FFMA2), NA integer adds, NM independent MUFU.EX2
+template <int NF, int NA, int NM, bool PACKED>
+__global__ void mix(float* out, int iters, float seed) {
+    float2 a[16];
+    float m[NM > 0 ? NM : 1];
+    int c[8];
+    for (int i = 0; i < 16; i++) a[i] = make_float2(threadIdx.x * 1e-3f + i, i * 0.25f);
+    for (int i = 0; i < NM; i++) m[i] = seed * (i + 1) * 1e-3f;
+    for (int i = 0; i < 8; i++) c[i] = threadIdx.x + i;
+    const float2 b = make_float2(seed, seed * 0.5f);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < NF / 32; r++)
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                if (PACKED) a[i] = ffma2(a[i], b, b);
+                else { a[i].x = fmaf(a[i].x, b.x, b.y); a[i].y = fmaf(a[i].y, b.x, b.y); }
+            }
+#pragma unroll
+        for (int i = 0; i < NM; i++) m[i] = ex2a(m[i]);
+#pragma unroll
+        for (int i = 0; i < NA; i++) c[i & 7] += c[(i + 1) & 7] ^ it;
+    }
+    float s = 0;
+    for (int i = 0; i < 16; i++) s += a[i].x + a[i].y;
+    for (int i = 0; i < NM; i++) s += m[i];
+    for (int i = 0; i < 8; i++) s += c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+template <int NF, int NA, int NM, bool PACKED>
+void runmix(const char* name, int cpsm) {
+    float* out; cudaMalloc(&out, 148 * 8 * 256 * 4);
+    const int iters = 4000;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    mix<NF, NA, NM, PACKED><<<148 * cpsm, 256>>>(out, 100, 1.0001f);
+    cudaEventRecord(e0);
+    mix<NF, NA, NM, PACKED><<<148 * cpsm, 256>>>(out, iters, 1.0001f);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    // warps per SMSP = cpsm * 8 / 4; clocks per warp-iteration per SMSP slot
+    printf("%-44s %d CTA/SM: %.3f ms  %.1f clk per warp-iteration per SMSP\n", name, cpsm, ms, ms * 1e-3 * 1.965e9 / (iters * (cpsm * 2.0)));
+    cudaFree(out);
+}
 int main() {
+    for (int cpsm : {3, 8}) {
+        runmix<96, 0, 0, false>("96 FFMA", cpsm);
+        runmix<96, 0, 17, false>("96 FFMA + 17 MUFU", cpsm);
+        runmix<96, 0, 17, true>("48 FFMA2 + 17 MUFU", cpsm);
+        runmix<64, 32, 17, false>("64 FFMA + 32 IADD/LOP + 17 MUFU", cpsm);
+        runmix<64, 32, 0, false>("64 FFMA + 32 IADD/LOP", cpsm);
+        runmix<32, 0, 17, false>("32 FFMA + 17 MUFU", cpsm);
+        runmix<32, 0, 8, false>("32 FFMA + 8 MUFU", cpsm);
+        runmix<0, 0, 17, false>("17 MUFU", cpsm);
+    }
     run<0>("16 FFMA"); run<1>("8 FFMA2"); run<2>("16 FFMA + 2 MUFU"); run<3>("8 FFMA2 + 2 MUFU");
     return 0;
 }
