@@ -1159,6 +1159,7 @@ AniAev::AniAev(int numAtoms, int numSpecies, float rcr, float rca, const int* at
     t.torchani = torchani ? 1 : 0;
     t.radialScale = torchani ? 0.25f : 1.0f;
     t.cosScale = torchani ? 0.95f : 1.0f;
+    t.invRcr = 1.0f / rcr; t.invRca = 1.0f / rca; t.sqrtCosScale = std::sqrt(t.cosScale);
     const double log2e = 1.4426950408889634;
     for (int k = 0; k < nRadial; k++) {
         t.rEta[k] = radialFn[2 * k]; t.rShf[k] = radialFn[2 * k + 1];

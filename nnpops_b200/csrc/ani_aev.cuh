@@ -28,6 +28,7 @@ struct AniTables {
     int fast, nShfA, nShfZ;
     float fEta, fEtaL2, fZeta, fScale;
     float fShfA[kAniMaxShf], fCos[kAniMaxShf], fSin[kAniMaxShf];
+    float invRcr, invRca, sqrtCosScale;   // 1 / rcr, 1 / rca, sqrt(cosScale): host-computed for the geometry kernels
 };
 
 class AniAev {

@@ -24,7 +24,10 @@
 //    which sm_100 executes as compare-and-swap loops.  The channel contraction runs as G[z] = sum_a g[a][z] E_a first (the radial
 //    factor is shared by the 4 angular channels), and the centre's force is minus the sum of its neighbours' at the end.
 #include "ani_angular_v2.cuh"
+#include <algorithm>
 #include <cmath>
+#include <map>
+#include <mutex>
 
 namespace nnpops {
 
@@ -207,11 +210,12 @@ ani_angular_fwd_seg_kernel(const AniTables* __restrict__ tab, const int* __restr
     const uint32_t sAu = smem_u32(sA);
     const int S = tab->nSpecies;
     const float fZeta = tab->fZeta, nEtaL2 = -tab->fEtaL2, fScale = tab->fScale;
-    float shf[NSA], cz[NSZ], sz[NSZ];
+    u64 nShf2[NSA / 2], cz2[NSZ / 2], sz2[NSZ / 2];   // packed fp32x2 constants: two radial / angular shifts per register pair
 #pragma unroll
-    for (int a = 0; a < NSA; a++) shf[a] = tab->fShfA[a];
+    for (int a = 0; a < NSA / 2; a++) nShf2[a] = pk2(-tab->fShfA[2 * a], -tab->fShfA[2 * a + 1]);
 #pragma unroll
-    for (int z = 0; z < NSZ; z++) { cz[z] = tab->fCos[z]; sz[z] = tab->fSin[z]; }
+    for (int z = 0; z < NSZ / 2; z++) { cz2[z] = pk2(tab->fCos[2 * z], tab->fCos[2 * z + 1]); sz2[z] = pk2(tab->fSin[2 * z], tab->fSin[2 * z + 1]); }
+    const u64 nEta2 = pk2(nEtaL2, nEtaL2), one2 = pk2(1.0f, 1.0f);
     const int nSeg = *nSegPtr;
     const int nChunks = (nSeg + GPW - 1) / GPW;
     uint32_t phase = 0;
@@ -264,9 +268,11 @@ ani_angular_fwd_seg_kernel(const AniTables* __restrict__ tab, const int* __restr
             while (a >= nsl) { a -= nsl; d++; }
             const int mb = act ? myBase : 0;
             const int tOff = same ? 0 : ns;
-            float acc[32];
+            u64 acc2[NSA / 2][NSZ];                 // acc2[k][z] = channels ((2 k) * NSZ + z, (2 k + 1) * NSZ + z)
 #pragma unroll
-            for (int i = 0; i < 32; i++) acc[i] = 0.0f;
+            for (int k = 0; k < NSA / 2; k++)
+#pragma unroll
+                for (int z = 0; z < NSZ; z++) acc2[k][z] = pk2(0.f, 0.f);
             for (int q = gl; q < maxTrip; q += G) {
                 const bool v = q < trip;
                 int x = a + d + 1;
@@ -279,22 +285,35 @@ ani_angular_fwd_seg_kernel(const AniTables* __restrict__ tab, const int* __restr
                 const float sn = xx * rsqrta(xx);
                 const float rm = va.w + vb.w;
                 const float F = v ? fa * fb : 0.0f;
-                float P[NSZ];
+                const u64 c2 = pk2(c, c), sn2 = pk2(sn, sn);
+                u64 Pd[NSZ];                            // (P_z, P_z)
 #pragma unroll
-                for (int z = 0; z < NSZ; z++) {
-                    const float base = fabsf(fmaf(sn, sz[z], fmaf(c, cz[z], 1.0f)));
-                    P[z] = F * ex2a(fZeta * lg2a(base));
+                for (int z = 0; z < NSZ / 2; z++) {
+                    const u64 base2 = ffma2(sn2, sz2[z], ffma2(c2, cz2[z], one2));
+                    float b0, b1;
+                    unpk2(base2, b0, b1);
+                    const float p0 = F * ex2a(fZeta * lg2a(fabsf(b0))), p1 = F * ex2a(fZeta * lg2a(fabsf(b1)));
+                    Pd[2 * z] = pk2(p0, p0); Pd[2 * z + 1] = pk2(p1, p1);
                 }
+                const u64 rm2 = pk2(rm, rm);
 #pragma unroll
-                for (int k = 0; k < NSA; k++) {
-                    const float tt = rm - shf[k];
-                    const float E = ex2a(tt * (nEtaL2 * tt));
+                for (int k = 0; k < NSA / 2; k++) {
+                    const u64 tt2 = fadd2(rm2, nShf2[k]);
+                    const u64 ar2 = fmul2(fmul2(tt2, nEta2), tt2);
+                    float a0, a1;
+                    unpk2(ar2, a0, a1);
+                    const u64 E2 = pk2(ex2a(a0), ex2a(a1));
 #pragma unroll
-                    for (int z = 0; z < NSZ; z++) acc[k * NSZ + z] = fmaf(P[z], E, acc[k * NSZ + z]);
+                    for (int z = 0; z < NSZ; z++) acc2[k][z] = ffma2(Pd[z], E2, acc2[k][z]);
                 }
                 a += G;
                 while (a >= nsl) { a -= nsl; d++; }
             }
+            float acc[32];
+#pragma unroll
+            for (int k = 0; k < NSA / 2; k++)
+#pragma unroll
+                for (int z = 0; z < NSZ; z++) unpk2(acc2[k][z], acc[(2 * k) * NSZ + z], acc[(2 * k + 1) * NSZ + z]);
             // in-group transpose-reduce: lane gl ends with channels [8 gl, 8 gl + 8)
 #pragma unroll
             for (int o = G / 2, c2 = 16; o >= 1; o >>= 1, c2 >>= 1) {
@@ -354,10 +373,6 @@ ani_angular_bwd_v2_kernel(int n, const AniTables* __restrict__ tab, const int* _
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    const int p = blockIdx.x * kWarpsPerCta + w;
-    if (p >= n) return;
-    const int cnt = offAng[(size_t)p * (S + 1) + S];
-    if (cnt < 2) return;
     // per warp: float4 sA[capA], sB[capA], acc[4][capA] (force accumulators X0, X1 for the first, Y0, Y1 for the second neighbour of a
     // triple, indexed by the parity of d), float sG[nPairs][36]
     const size_t perWarp = (size_t)capA * 96 + (size_t)nPairs * kBwdPitch * 4;
@@ -367,6 +382,21 @@ ani_angular_bwd_v2_kernel(int n, const AniTables* __restrict__ tab, const int* _
     float4* sAcc = sB + capA;
     float* sG = reinterpret_cast<float*>(sAcc + 4 * capA);
     const uint32_t bar = smem_u32(&bars[w]);
+    const float cs = tab->cosScale;
+    const float rcs = 1.0f / cs, sqcs = sqrtf(cs), k1 = 1.0f / sqcs;
+    const float nEtaL2 = -tab->fEtaL2, zm1 = tab->fZeta - 1.0f;
+    const float kA = k1 * tab->fScale, kB = -k1 * tab->fEta * tab->fScale, kC = sqcs * tab->fZeta * tab->fScale;
+    u64 nShf2[NSA / 2], cz2[NSZ / 2], sz2[NSZ / 2];
+#pragma unroll
+    for (int a = 0; a < NSA / 2; a++) nShf2[a] = pk2(-tab->fShfA[2 * a], -tab->fShfA[2 * a + 1]);
+#pragma unroll
+    for (int z = 0; z < NSZ / 2; z++) { cz2[z] = pk2(tab->fCos[2 * z], tab->fCos[2 * z + 1]); sz2[z] = pk2(tab->fSin[2 * z], tab->fSin[2 * z + 1]); }
+    const u64 nEta2 = pk2(nEtaL2, nEtaL2), one2 = pk2(1.0f, 1.0f);
+    uint32_t phase = 0;
+    // persistent: a warp walks over centres, so the table set-up above and the CTA launch are paid once per warp
+    for (int p = blockIdx.x * kWarpsPerCta + w; p < n; p += gridDim.x * kWarpsPerCta) {
+    const int cnt = offAng[(size_t)p * (S + 1) + S];
+    if (cnt < 2) continue;
     const int orig = sortedOrig[p];
     const float* gi = grad + (size_t)(rowMap ? rowMap[orig] : orig) * stride;
     if (lane == 0) mbar_expect_tx(bar, (uint32_t)cnt * 32u + (uint32_t)nPairs * 128u);
@@ -380,17 +410,19 @@ ani_angular_bwd_v2_kernel(int n, const AniTables* __restrict__ tab, const int* _
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         sAcc[i] = z; sAcc[capA + i] = z; sAcc[2 * capA + i] = z; sAcc[3 * capA + i] = z;
     }
-    const float cs = tab->cosScale;
-    const float rcs = 1.0f / cs, sqcs = sqrtf(cs), k1 = 1.0f / sqcs;
-    const float fZeta = tab->fZeta, nEtaL2 = -tab->fEtaL2, zm1 = tab->fZeta - 1.0f;
-    const float kA = k1 * tab->fScale, kB = -k1 * tab->fEta * tab->fScale, kC = sqcs * tab->fZeta * tab->fScale;
-    float shf[NSA], cz[NSZ], sz[NSZ];
-#pragma unroll
-    for (int a = 0; a < NSA; a++) shf[a] = tab->fShfA[a];
-#pragma unroll
-    for (int z = 0; z < NSZ; z++) { cz[z] = tab->fCos[z]; sz[z] = tab->fSin[z]; }
     __syncwarp();
-    mbar_wait(bar, 0);
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    // re-lay every 32-float gradient block from [a][z] to [a / 2][z][a % 2] (in place; lane <-> destination element)
+    {
+        const int src = (2 * (lane >> 3) + (lane & 1)) * 4 + ((lane >> 1) & 3);
+        for (int blk = 0; blk < nPairs; blk++) {
+            const float v = sG[blk * kBwdPitch + src];
+            __syncwarp();
+            sG[blk * kBwdPitch + lane] = v;
+        }
+        __syncwarp();
+    }
     const int total = (cnt * (cnt - 1)) >> 1;
     const int step = min(32, 2 * cnt - 2);
     int a = lane, d1 = 0;
@@ -407,23 +439,45 @@ ani_angular_bwd_v2_kernel(int n, const AniTables* __restrict__ tab, const int* _
             const float xx = fmaxf(fmaf(-c, c, 1.0f), 1e-30f);
             const float isn = rsqrta(xx), sn = xx * isn;
             const float rm = va.w + vb.w;
-            float P[NSZ], Q[NSZ];
+            // angular factors, two shifts at a time (packed fp32x2): P_z = base^zeta, Q_z = base^(zeta - 1) (c sin_z - sn cos_z)
+            const u64 c2 = pk2(c, c), sn2 = pk2(sn, sn), nsn2 = pk2(-sn, -sn);
+            u64 P2[NSZ / 2], Q2[NSZ / 2];
+#pragma unroll
+            for (int z = 0; z < NSZ / 2; z++) {
+                const u64 base2 = ffma2(sn2, sz2[z], ffma2(c2, cz2[z], one2));
+                float b0, b1;
+                unpk2(base2, b0, b1);
+                const u64 pm2 = pk2(ex2a(zm1 * lg2a(fabsf(b0))), ex2a(zm1 * lg2a(fabsf(b1))));
+                P2[z] = fmul2(pm2, base2);
+                Q2[z] = fmul2(pm2, ffma2(c2, sz2[z], fmul2(nsn2, cz2[z])));
+            }
+            // radial factors two shifts at a time; the staged gradient block is laid out [a / 2][z][a % 2], so that one 16-byte load
+            // brings the (a, a + 1) pairs of two angular channels:  GE_z = sum_a g[a][z] E_a,  GT_z = sum_a g[a][z] E_a (rm - Rs_a)
+            const u64 rm2 = pk2(rm, rm);
+            u64 GE2[NSZ], GT2[NSZ];
+#pragma unroll
+            for (int z = 0; z < NSZ; z++) { GE2[z] = pk2(0.f, 0.f); GT2[z] = pk2(0.f, 0.f); }
+#pragma unroll
+            for (int k = 0; k < NSA / 2; k++) {
+                const u64 tt2 = fadd2(rm2, nShf2[k]);
+                const u64 ar2 = fmul2(fmul2(tt2, nEta2), tt2);
+                float a0, a1;
+                unpk2(ar2, a0, a1);
+                const u64 E2 = pk2(ex2a(a0), ex2a(a1));
+                const u64 Et2 = fmul2(E2, tt2);
+                const float4 ga = *reinterpret_cast<const float4*>(gp + k * 8), gb = *reinterpret_cast<const float4*>(gp + k * 8 + 4);
+                const u64 g0 = pk2(ga.x, ga.y), g1 = pk2(ga.z, ga.w), g2 = pk2(gb.x, gb.y), g3 = pk2(gb.z, gb.w);
+                GE2[0] = ffma2(g0, E2, GE2[0]); GE2[1] = ffma2(g1, E2, GE2[1]); GE2[2] = ffma2(g2, E2, GE2[2]); GE2[3] = ffma2(g3, E2, GE2[3]);
+                GT2[0] = ffma2(g0, Et2, GT2[0]); GT2[1] = ffma2(g1, Et2, GT2[1]); GT2[2] = ffma2(g2, Et2, GT2[2]); GT2[3] = ffma2(g3, Et2, GT2[3]);
+            }
+            float P[NSZ], Q[NSZ], GE[NSZ], GT[NSZ];
+#pragma unroll
+            for (int z = 0; z < NSZ / 2; z++) { unpk2(P2[z], P[2 * z], P[2 * z + 1]); unpk2(Q2[z], Q[2 * z], Q[2 * z + 1]); }
 #pragma unroll
             for (int z = 0; z < NSZ; z++) {
-                const float base = fabsf(fmaf(sn, sz[z], fmaf(c, cz[z], 1.0f)));
-                const float pm1 = ex2a(zm1 * lg2a(base));
-                P[z] = pm1 * base;
-                Q[z] = pm1 * fmaf(c, sz[z], -sn * cz[z]);
-            }
-            float GE[NSZ] = {0.f, 0.f, 0.f, 0.f}, GT[NSZ] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int k = 0; k < NSA; k++) {
-                const float tt = rm - shf[k];
-                const float E = ex2a(tt * (nEtaL2 * tt));
-                const float Et = E * tt;
-                const float4 g4 = *reinterpret_cast<const float4*>(gp + k * NSZ);
-                GE[0] = fmaf(g4.x, E, GE[0]); GE[1] = fmaf(g4.y, E, GE[1]); GE[2] = fmaf(g4.z, E, GE[2]); GE[3] = fmaf(g4.w, E, GE[3]);
-                GT[0] = fmaf(g4.x, Et, GT[0]); GT[1] = fmaf(g4.y, Et, GT[1]); GT[2] = fmaf(g4.z, Et, GT[2]); GT[3] = fmaf(g4.w, Et, GT[3]);
+                float lo, hi;
+                unpk2(GE2[z], lo, hi); GE[z] = lo + hi;
+                unpk2(GT2[z], lo, hi); GT[z] = lo + hi;
             }
             float A = 0.0f, Bp = 0.0f, C = 0.0f;
 #pragma unroll
@@ -451,15 +505,17 @@ ani_angular_bwd_v2_kernel(int n, const AniTables* __restrict__ tab, const int* _
         if (a >= cnt) { a -= cnt; d1++; }
         if (a >= cnt) { a -= cnt; d1++; }
     }
-    float cx = 0.0f, cy = 0.0f, cz2 = 0.0f;
+    float cx = 0.0f, cy = 0.0f, czc = 0.0f;
     for (int q = lane; q < cnt; q += 32) {
         const float4 x0 = sAcc[q], x1 = sAcc[capA + q], y0 = sAcc[2 * capA + q], y1 = sAcc[3 * capA + q];
         const float fx = (x0.x + x1.x) + (y0.x + y1.x), fy = (x0.y + x1.y) + (y0.y + y1.y), fz = (x0.z + x1.z) + (y0.z + y1.z);
         grad_add<VEC>(posGrad, (size_t)(__float_as_int(sB[q].w) & 0x00ffffff), fx, fy, fz);
-        cx -= fx; cy -= fy; cz2 -= fz;
+        cx -= fx; cy -= fy; czc -= fz;
     }
-    cx = warp_sum(cx); cy = warp_sum(cy); cz2 = warp_sum(cz2);
-    if (lane == 0) grad_add<VEC>(posGrad, (size_t)orig, cx, cy, cz2);
+    cx = warp_sum(cx); cy = warp_sum(cy); czc = warp_sum(czc);
+    if (lane == 0) grad_add<VEC>(posGrad, (size_t)orig, cx, cy, czc);
+    __syncwarp();                              // every lane is done with the staged rows before the next bulk copies land on them
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -478,7 +534,7 @@ ani_angular_geo_kernel(int n, const AniTables* __restrict__ tab, const float4* _
     const int S = tab->nSpecies;
     const int cnt = offAng[(size_t)p * (S + 1) + S];
     const float4 ci = sorted[p];
-    const float invRca = 1.0f / tab->rca, sq = sqrtf(tab->cosScale);
+    const float invRca = tab->invRca, sq = tab->sqrtCosScale;
     for (int q0 = 0; q0 < cnt; q0 += 32) {       // 4 entries per lane per trip: all index loads, then all coordinate gathers, in flight together
         int j[4];
         float4 cj[4];
@@ -508,6 +564,7 @@ ani_angular_geo_kernel(int n, const AniTables* __restrict__ tab, const float4* _
 // shared memory.  Pass 2, lane = (h, kq): kq owns the channel pair (2 kq, 2 kq + 1) -- packed fp32x2 arithmetic -- and h is one
 // of 32 / KQ neighbour sub-streams; one shuffle reduction over h per species block.
 // ------------------------------------------------------------------------------------------------------------------
+template <int NR>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 ani_radial_fwd_v2_kernel(int n, const AniTables* __restrict__ tab, const float4* __restrict__ sorted, const int* __restrict__ sortedOrig,
                          const Geom* __restrict__ geom, const int* __restrict__ rowRad, const int* __restrict__ offRad, int capR,
@@ -518,14 +575,21 @@ ani_radial_fwd_v2_kernel(int n, const AniTables* __restrict__ tab, const float4*
     if (threadIdx.x == 0) g = *geom;
     __syncthreads();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p = blockIdx.x * kWarpsPerCta + w;
-    if (p >= n) return;
     float2* sRF = reinterpret_cast<float2*>(smemRaw) + (size_t)w * capR;
-    const int S = tab->nSpecies, nR = tab->nRadial;
+    constexpr int nR = NR;
+    const int S = tab->nSpecies;
+    const float invRcr = tab->invRcr;
+    static_assert(NR == 4 || NR == 8 || NR == 16 || NR == 32 || NR == 64, "channel pairs must tile a warp");
+    constexpr int KQ = NR / 2, H = 32 / KQ;
+    const int kq = lane % KQ, h = lane / KQ;
+    const float nEta = -tab->rEtaL2[0], scale = tab->radialScale;
+    const u64 nEta2 = pk2(nEta, nEta);
+    const u64 nShf2 = pk2(-tab->rShf[2 * kq], -tab->rShf[2 * kq + 1]);
+    // persistent: a warp walks over centres (a centre is a few hundred warp instructions)
+    for (int p = blockIdx.x * kWarpsPerCta + w; p < n; p += gridDim.x * kWarpsPerCta) {
     const int* off = offRad + (size_t)p * (S + 1);
     const int cnt = min(off[S], capR);
     const float4 ci = sorted[p];
-    const float invRcr = 1.0f / tab->rcr;
     for (int q0 = 0; q0 < cnt; q0 += 64) {       // two entries per lane per trip, both gathers in flight together
         int j[2];
         float4 cj[2];
@@ -549,13 +613,6 @@ ani_radial_fwd_v2_kernel(int n, const AniTables* __restrict__ tab, const float4*
         }
     }
     __syncwarp();
-    int KQ = 1;
-    while (2 * KQ < nR) KQ <<= 1;
-    const int H = 32 / KQ, kq = lane % KQ, h = lane / KQ;
-    const bool kval = 2 * kq < nR;             // nR is even on this path
-    const float nEta = -tab->rEtaL2[0], scale = tab->radialScale;
-    const u64 nEta2 = pk2(nEta, nEta);
-    const u64 nShf2 = kval ? pk2(-tab->rShf[2 * kq], -tab->rShf[2 * kq + 1]) : pk2(0.f, 0.f);
     const int orig = sortedOrig[p];
     const size_t orow = (size_t)(rowMap ? rowMap[orig] : orig) * stride;
     for (int sp = 0; sp < S; sp++) {
@@ -572,7 +629,7 @@ ani_radial_fwd_v2_kernel(int n, const AniTables* __restrict__ tab, const float4*
         float v0, v1;
         unpk2(acc, v0, v1);
         for (int o = KQ; o < 32; o <<= 1) { v0 += __shfl_xor_sync(kFull, v0, o); v1 += __shfl_xor_sync(kFull, v1, o); }
-        if (h == 0 && kval) {
+        if (h == 0) {
             const size_t idx = orow + (size_t)sp * nR + 2 * kq;
             v0 *= scale; v1 *= scale;
             if (out.hi) {
@@ -584,6 +641,8 @@ ani_radial_fwd_v2_kernel(int n, const AniTables* __restrict__ tab, const float4*
                 *reinterpret_cast<float2*>(out.f32 + idx) = make_float2(v0, v1);
             }
         }
+    }
+    __syncwarp();                              // the staged (r, fc) pairs are re-used by the next centre
     }
 }
 
@@ -608,25 +667,27 @@ ani_radial_bwd_v2_kernel(int n, const AniTables* __restrict__ tab, const int* __
     if (lane == 0) mbar_init(smem_u32(&bars[w]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    const int p = blockIdx.x * kWarpsPerCta + w;
-    if (p >= n) return;
-    const int cnt = min(offRad[(size_t)p * (S + 1) + S], capR);
-    if (cnt == 0) return;                      // also every centre owned by another rank
     float* sG = reinterpret_cast<float*>(smemRaw) + (size_t)w * S * NR;
     const uint32_t bar = smem_u32(&bars[w]);
-    const int orig = sortedOrig[p];
-    const float* gi = grad + (size_t)(rowMap ? rowMap[orig] : orig) * stride;
-    if (lane == 0) {
-        mbar_expect_tx(bar, (uint32_t)(S * NR * 4));
-        bulk_g2s(smem_u32(sG), gi, (uint32_t)(S * NR * 4), bar);
-    }
     const float nEta = -tab->rEtaL2[0];
     const u64 nEta2 = pk2(nEta, nEta);
     u64 nShf2[NR / 2];
 #pragma unroll
     for (int k = 0; k < NR / 2; k++) nShf2[k] = pk2(-tab->rShf[2 * k], -tab->rShf[2 * k + 1]);
     const float sc = tab->radialScale, m2eta = -2.0f * tab->rEta[0];
-    mbar_wait(bar, 0);
+    uint32_t phase = 0;
+    // persistent: a warp walks over centres (a centre is ~400 warp instructions -- one CTA per 8 centres spent as long being launched)
+    for (int p = blockIdx.x * kWarpsPerCta + w; p < n; p += gridDim.x * kWarpsPerCta) {
+    const int cnt = min(offRad[(size_t)p * (S + 1) + S], capR);
+    if (cnt == 0) continue;                    // also every centre owned by another rank
+    const int orig = sortedOrig[p];
+    const float* gi = grad + (size_t)(rowMap ? rowMap[orig] : orig) * stride;
+    if (lane == 0) {
+        mbar_expect_tx(bar, (uint32_t)(S * NR * 4));
+        bulk_g2s(smem_u32(sG), gi, (uint32_t)(S * NR * 4), bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
     float fx = 0.0f, fy = 0.0f, fz = 0.0f;
     for (int q0 = 0; q0 < cnt; q0 += 64) {       // two pairs per lane per trip: the four 16-byte loads are in flight together
         float4 gaa[2], gbb[2];
@@ -665,6 +726,8 @@ ani_radial_bwd_v2_kernel(int n, const AniTables* __restrict__ tab, const int* __
     }
     fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
     if (lane == 0) grad_add<VEC>(posGrad, (size_t)orig, fx, fy, fz);
+    __syncwarp();                              // every lane is done with the staged gradient row before the next bulk copy
+    }
 }
 
 __global__ void grad_compact_kernel(int n, const float4* __restrict__ acc, float* __restrict__ posGrad) {
@@ -676,14 +739,17 @@ __global__ void grad_compact_kernel(int n, const float4* __restrict__ acc, float
 
 template <typename K>
 void set_smem_v2(K kernel, size_t bytes) {
-    // the attribute is per device and per kernel; K differs per kernel signature, so each kernel gets its own table
+    // the attribute is per device and per kernel instantiation
     int dev = 0;
     cudaGetDevice(&dev);
-    static size_t have[64] = {0};
-    if (dev >= 0 && dev < 64 && have[dev] >= bytes) return;
-    NNP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    static std::mutex mtx;
+    static std::map<std::pair<const void*, int>, size_t> have;
+    std::lock_guard<std::mutex> lock(mtx);
+    size_t& h = have[{reinterpret_cast<const void*>(kernel), dev}];
+    if (h >= bytes && h != 0) return;
+    NNP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bytes, 1)));
     NNP_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    if (dev >= 0 && dev < 64) have[dev] = bytes;
+    h = std::max<size_t>(bytes, 1);
 }
 
 int sm_count_v2() {
@@ -709,9 +775,9 @@ void radial_v2_forward(int n, const AniTables& tabHost, const AniTables* tab, co
                        const int* rowRad, const int* offRad, int capR, float4* radGeoA, float4* radGeoB, const int* rowMap, AevOutPtr out,
                        int stride, cudaStream_t stream) {
     const size_t smem = (size_t)kWarpsPerCta * capR * sizeof(float2);
-    auto k = ani_radial_fwd_v2_kernel;
+    auto k = ani_radial_fwd_v2_kernel<16>;
     set_smem_v2(k, smem);
-    const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;   // latency-bound (gathers): one centre per warp keeps the most warps in flight
     k<<<grid, kWarpsPerCta * 32, smem, stream>>>(n, tab, sorted, sortedOrig, geom, rowRad, offRad, capR, radGeoA, radGeoB, rowMap, out, stride);
     count_launch();
 }
@@ -727,7 +793,7 @@ void radial_v2_backward(int n, const AniTables& tabHost, const AniTables* tab, c
                         const float4* radGeoB, const int* sortedOrig, const int* rowMap, const float* grad, int stride, float* posGrad,
                         bool padded, cudaStream_t stream) {
     const size_t smem = (size_t)kWarpsPerCta * tabHost.nSpecies * 16 * sizeof(float);
-    const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;   // latency-bound: one centre per warp keeps the most warps in flight
     if (padded) {
         auto k = ani_radial_bwd_v2_kernel<16, true>;
         set_smem_v2(k, smem);
@@ -778,7 +844,8 @@ void angular_v2_backward(int n, const AniTables& tabHost, const AniTables* tab, 
                          bool padded, cudaStream_t stream) {
     const size_t smem = (size_t)kWarpsPerCta * ((size_t)capA * 96 + (size_t)tabHost.nPairs * kBwdPitch * 4);
     NNP_REQUIRE(smem <= 200 * 1024, "angular gradient row does not fit in shared memory (numSpecies^2 * numAngular too large)");
-    const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int perSm = std::max(1, std::min(4, (int)((220 * 1024) / (smem + 1024))));
+    const int grid = std::min((n + kWarpsPerCta - 1) / kWarpsPerCta, sm_count_v2() * perSm);
     if (padded) {
         auto k = ani_angular_bwd_v2_kernel<8, 4, true>;
         set_smem_v2(k, smem);

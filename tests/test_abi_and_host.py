@@ -80,3 +80,33 @@ def test_pme_moduli_match_reference_construction():
         ref = o.pme_moduli(order, (14, 15, 16))
         for g, r in zip(got, ref):
             assert np.allclose(g.numpy(), r, rtol=2e-5, atol=1e-7)
+
+
+def test_angular_backward_enumeration_is_collision_free():
+    """The angular backward kernel (csrc/ani_angular_v2.cu) walks the n (n - 1) / 2 neighbour pairs of a centre in flat rotation order,
+    step = min(32, 2 n - 2) pairs per warp iteration, and accumulates the two forces of a pair with plain (non-atomic) read-modify-writes
+    into arrays indexed by (parity of d, slot).  That is only correct if, within one iteration, no two lanes share (parity, first slot)
+    or (parity, second slot) -- and the enumeration must visit every unordered pair exactly once.  Exhaustive check for n <= 128."""
+    for n in range(2, 129):
+        total = n * (n - 1) // 2
+        step = min(32, 2 * n - 2)
+        seen = set()
+        for q0 in range(0, total, step):
+            first, second = set(), set()
+            for lane in range(32):
+                q = q0 + lane
+                if lane >= step or q >= total:
+                    continue
+                d, a = divmod(q, n)
+                b = a + d + 1
+                if b >= n:
+                    b -= n
+                assert 0 <= b < n and a != b
+                pair = frozenset((a, b))
+                assert pair not in seen
+                seen.add(pair)
+                ka, kb = (d & 1, a), (d & 1, b)
+                assert ka not in first and kb not in second, (n, q0, lane)
+                first.add(ka)
+                second.add(kb)
+        assert len(seen) == total
