@@ -22,6 +22,8 @@ def build(force=False):
         subprocess.check_call(["make", "-s", "-C", ODIR, "oracle"])
     if os.path.isdir("/root/reference/src/ani") and (force or not os.path.exists(os.path.join(ODIR, "_ref", "libnnpops_ref.so"))):
         subprocess.check_call(["make", "-s", "-C", ODIR, "ref"])
+    if os.path.isdir("/root/reference/src/ani") and (force or not os.path.exists(os.path.join(ODIR, "_ref", "libnnpops_ref_cuda.so"))):
+        subprocess.check_call(["make", "-s", "-C", ODIR, "refcuda"])   # the reference's own CUDA kernels for sm_100a (GPU comparator)
 
 
 _libs = {}
@@ -41,6 +43,57 @@ def ref_lib():
         p = os.path.join(ODIR, "_ref", "libnnpops_ref.so")
         _libs["ref"] = C.CDLL(p) if os.path.exists(p) else None
     return _libs["ref"]
+
+
+def ref_cuda_lib():
+    """The reference's CUDA classes compiled for sm_100a (None when never built).  GPU comparator only."""
+    if "refcuda" not in _libs:
+        build()
+        p = os.path.join(ODIR, "_ref", "libnnpops_ref_cuda.so")
+        l = C.CDLL(p) if os.path.exists(p) else None
+        if l is not None:
+            l.refcuda_ani_create.restype = C.c_void_p
+            l.refcuda_ani_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+            l.refcuda_ani_destroy.argtypes = [C.c_void_p]
+            l.refcuda_ani_forward.argtypes = [C.c_void_p] * 5
+            l.refcuda_ani_backward.argtypes = [C.c_void_p] * 4
+        _libs["refcuda"] = l
+    return _libs["refcuda"]
+
+
+class RefCudaANI:
+    """The reference's CudaANISymmetryFunctions on torch CUDA tensors (device pointers; src/ani/CudaANISymmetryFunctions.h:62-99)."""
+
+    def __init__(self, species, n_species, rcr, rca, radial_fn, angular_fn, periodic, torchani=True):
+        self.l = ref_cuda_lib()
+        species = np.ascontiguousarray(species, np.int32)
+        rf = np.ascontiguousarray(radial_fn, np.float32).reshape(-1, 2)
+        af = np.ascontiguousarray(angular_fn, np.float32).reshape(-1, 4)
+        self.n, self.ns, self.nr, self.na = len(species), n_species, len(rf), len(af)
+        self.h = self.l.refcuda_ani_create(self.n, n_species, rcr, rca, int(periodic), species.ctypes.data, self.nr, rf.ctypes.data, self.na,
+                                           af.ctypes.data, int(torchani))
+        if not self.h:
+            raise RuntimeError("reference CudaANISymmetryFunctions could not be constructed")
+
+    def forward(self, pos, box):
+        import torch
+        radial = torch.empty((self.n, self.ns * self.nr), dtype=torch.float32, device=pos.device)
+        angular = torch.empty((self.n, self.ns * (self.ns + 1) // 2 * self.na), dtype=torch.float32, device=pos.device)
+        rc = self.l.refcuda_ani_forward(self.h, pos.data_ptr(), box.data_ptr() if box is not None else None, radial.data_ptr(), angular.data_ptr())
+        assert rc == 0
+        return radial, angular
+
+    def backward(self, radial_grad, angular_grad):
+        import torch
+        out = torch.empty((self.n, 3), dtype=torch.float32, device=radial_grad.device)
+        rc = self.l.refcuda_ani_backward(self.h, radial_grad.data_ptr(), angular_grad.data_ptr(), out.data_ptr())
+        assert rc == 0
+        return out
+
+    def close(self):
+        if self.h:
+            self.l.refcuda_ani_destroy(self.h)
+            self.h = None
 
 
 def _opt(a, dtype):
