@@ -112,36 +112,32 @@ __global__ void count_kernel(const T* __restrict__ pos, int n, Geom* __restrict_
     slot[i] = atomicAdd(&cellCount[c], 1);
 }
 
-// exclusive scan of cellCount[0..ncells) into cellStart[0..ncells]; entries beyond ncells are set to n so stale cells are empty
+// exclusive scan of cellCount[0..ncells) into cellStart[0..ncells] by ONE CTA: every thread owns a contiguous chunk of cells (serial
+// sum, then serial write-back), the chunk totals are scanned across the CTA.  One pass over the array whatever the number of cells --
+// the ANI path uses cells of half the cutoff, 27 000 of them for the 50 000-atom box.
 __global__ void scan_kernel(const int* __restrict__ cellCount, int* __restrict__ cellStart, const Geom* __restrict__ geom, int maxCells,
                             const int* __restrict__ run) {
     if (run != nullptr && *run == 0) return;
     __shared__ int warpTot[32];
-    __shared__ int carry;
     const int ncells = geom->ncells;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    if (threadIdx.x == 0) carry = 0;
+    const int chunk = (ncells + blockDim.x - 1) / blockDim.x;
+    const int b = min(threadIdx.x * chunk, ncells), e = min(b + chunk, ncells);
+    int sum = 0;
+    for (int i = b; i < e; i++) sum += cellCount[i];
+    int x = sum;
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(kFull, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warpTot[w] = x;
     __syncthreads();
-    for (int base = 0; base < ncells; base += blockDim.x) {
-        int i = base + threadIdx.x;
-        int v = i < ncells ? cellCount[i] : 0;
-        int x = v;
-        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(kFull, x, o); if (lane >= o) x += y; }
-        if (lane == 31) warpTot[w] = x;
-        __syncthreads();
-        if (w == 0) {
-            int t = lane < nw ? warpTot[lane] : 0;
-            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(kFull, t, o); if (lane >= o) t += y; }
-            warpTot[lane] = t;   // inclusive
-        }
-        __syncthreads();
-        int excl = carry + (w > 0 ? warpTot[w - 1] : 0) + x - v;
-        if (i < ncells) cellStart[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
-        __syncthreads();
+    if (w == 0) {
+        int t = lane < nw ? warpTot[lane] : 0;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(kFull, t, o); if (lane >= o) t += y; }
+        warpTot[lane] = t;   // inclusive
     }
-    if (threadIdx.x == 0) cellStart[ncells] = carry;
+    __syncthreads();
+    int run0 = (w > 0 ? warpTot[w - 1] : 0) + x - sum;
+    for (int i = b; i < e; i++) { cellStart[i] = run0; run0 += cellCount[i]; }
+    if (threadIdx.x == blockDim.x - 1) cellStart[ncells] = warpTot[nw - 1];
 }
 
 __global__ void scatter_kernel(int n, const int* __restrict__ cellOf, const int* __restrict__ slot, const int* __restrict__ cellStart,
