@@ -1280,7 +1280,7 @@ AniAev::AniAev(int numAtoms, int numSpecies, float rcr, float rca, const int* at
         NNP_CUDA_CHECK(cudaMalloc(&geoA_, sizeof(float4) * na * capA_));
         NNP_CUDA_CHECK(cudaMalloc(&geoB_, sizeof(float4) * na * capA_));
         NNP_CUDA_CHECK(cudaMalloc(&segHist_, 2 * kSegBins * sizeof(int)));
-        NNP_CUDA_CHECK(cudaMalloc(&segs_, sizeof(int2) * na * t.nPairs));
+        NNP_CUDA_CHECK(cudaMalloc(&segs_, sizeof(int4) * na * t.nPairs));
         NNP_CUDA_CHECK(cudaMalloc(&nSeg_, sizeof(int)));
         NNP_CUDA_CHECK(cudaMemset(nSeg_, 0, sizeof(int)));
     }

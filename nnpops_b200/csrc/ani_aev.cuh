@@ -108,7 +108,7 @@ private:
     float4* geoA_ = nullptr;     // [n][capA] {sqrt(cosScale) * unit vector, r / 2}, species-grouped like rowAng
     float4* geoB_ = nullptr;     // [n][capA] {fc, fc', 1 / r, species << 24 | atom index}
     int* segHist_ = nullptr;     // [2][512] size histogram of the (centre, species pair) blocks + fill cursors
-    int2* segs_ = nullptr;       // [n * nPairs] non-empty blocks, largest first
+    int4* segs_ = nullptr;       // [n * nPairs] non-empty blocks, largest first
     int* nSeg_ = nullptr;
     bool lastForwardV2_ = false;
     float4* radGeoA_ = nullptr;  // [n][capR] {unit vector, r} of every radial pair, species-grouped like rowRad

@@ -131,7 +131,7 @@ ani_seg_hist_kernel(int n, int S, const int* __restrict__ offAng, int* __restric
 
 __global__ void __launch_bounds__(kSegBins)
 ani_seg_scatter_kernel(int n, int S, const int* __restrict__ offAng, const int* __restrict__ hist, int* __restrict__ cursor,
-                       int2* __restrict__ segs, int* __restrict__ nSeg, const int* __restrict__ sortedOrig, const int* __restrict__ rowMap,
+                       int4* __restrict__ segs, int* __restrict__ nSeg, const int* __restrict__ sortedOrig, const int* __restrict__ rowMap,
                        AevOutPtr out, int stride) {
     __shared__ int base[kSegBins];       // first slot of this CTA's entries of a bin
     __shared__ int local[kSegBins];      // entries of this CTA per bin, then the running cursor
@@ -171,7 +171,8 @@ ani_seg_scatter_kernel(int n, int S, const int* __restrict__ offAng, const int* 
     __syncthreads();
     if (p >= n) return;
     const int orig = sortedOrig[p];
-    const size_t orow = (size_t)(rowMap ? rowMap[orig] : orig) * stride;
+    const int outRow = rowMap ? rowMap[orig] : orig;
+    const size_t orow = (size_t)outRow * stride;
     int pIdx = 0;
     for (int s = 0; s < S; s++) {
         const int ns = off[s + 1] - off[s];
@@ -180,7 +181,10 @@ ani_seg_scatter_kernel(int n, int S, const int* __restrict__ offAng, const int* 
             const int ntrip = (s == t) ? (ns * (ns - 1)) / 2 : ns * nt;
             if (ntrip <= 0) { zero_block32(out, orow + (size_t)pIdx * 32); continue; }
             const int bin = seg_bin(ntrip);
-            segs[base[bin] + atomicAdd(&local[bin], 1)] = make_int2(p, (s << 16) | t);
+            // everything the forward kernel needs to know about the segment: centre, species pair block, the two sub-ranges of the
+            // centre's angular row (start and length, 8 bits each: capA <= 128), output row
+            segs[base[bin] + atomicAdd(&local[bin], 1)] =
+                make_int4(p, (pIdx << 1) | (s == t ? 1 : 0), off[s] | (ns << 8) | (off[t] << 16) | (nt << 24), outRow);
         }
     }
 }
@@ -191,11 +195,14 @@ ani_seg_scatter_kernel(int n, int S, const int* __restrict__ offAng, const int* 
 #ifndef NNP_FWD_MINB
 #define NNP_FWD_MINB 3
 #endif
+#ifndef NNP_FWD_UNROLL
+#define NNP_FWD_UNROLL 1
+#endif
 template <int NSA, int NSZ>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, NNP_FWD_MINB)
 ani_angular_fwd_seg_kernel(const AniTables* __restrict__ tab, const int* __restrict__ offAng, int capA, const float4* __restrict__ geoA,
-                           const float4* __restrict__ geoB, const int2* __restrict__ segs, const int* __restrict__ nSegPtr,
-                           const int* __restrict__ sortedOrig, const int* __restrict__ rowMap, AevOutPtr out, int stride) {
+                           const float4* __restrict__ geoB, const int4* __restrict__ segs, const int* __restrict__ nSegPtr,
+                           AevOutPtr out, int stride) {
     static_assert(NSA * NSZ == 32, "32 angular channels");
     constexpr int G = kSegGroup, GPW = 32 / G;
     extern __shared__ __align__(128) unsigned char smemRaw[];
@@ -222,27 +229,31 @@ ani_angular_fwd_seg_kernel(const AniTables* __restrict__ tab, const int* __restr
     for (int chunk = blockIdx.x * kWarpsPerCta + w; chunk < nChunks; chunk += gridDim.x * kWarpsPerCta) {
         const int segIdx = chunk * GPW + sub;
         const bool valid = segIdx < nSeg;
-        int p = 0, bs = 0, ns = 0, bt = 0, nt = 0, ntrip = 0, e = 0, pIdx = 0;
+        int p = 0, bs = 0, ns = 0, bt = 0, nt = 0, ntrip = 0, e = 0, pIdx = 0, outRow = 0;
         bool same = true;
         if (valid) {
-            const int2 sg = segs[segIdx];
-            p = sg.x;
-            const int s = sg.y >> 16, t = sg.y & 0xffff;
-            const int* off = offAng + (size_t)p * (S + 1);
-            bs = off[s]; ns = off[s + 1] - bs; bt = off[t]; nt = off[t + 1] - bt;
-            same = s == t;
+            const int4 sg = segs[segIdx];              // one 16-byte load: no dependent look-ups in the offset tables
+            p = sg.x; pIdx = sg.y >> 1; same = (sg.y & 1) != 0; outRow = sg.w;
+            bs = sg.z & 0xff; ns = (sg.z >> 8) & 0xff; bt = (sg.z >> 16) & 0xff; nt = (sg.z >> 24) & 0xff;
             ntrip = same ? (ns * (ns - 1)) / 2 : ns * nt;
             e = same ? ns : ns + nt;
-            pIdx = pair_index(S, s, t);
         }
+        // shared-memory offsets of the 8 segments: a scan over the groups (every lane of a group holds the same e)
+        int incl = e;
+#pragma unroll
+        for (int o = G; o < 32; o <<= 1) { const int y = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += y; }
+        const int allEntries = __shfl_sync(kFull, incl, 31);
         int first = 0;
-        while (first < GPW) {   // normally ONE pass; more only when the 8 segments need more than kFwdBudget entries
-            int run = 0, lim = GPW, myBase = 0;
-            for (int g = first; g < GPW; g++) {
-                const int eg = __shfl_sync(kFull, e, g * G);
-                if (run + eg > kFwdBudget) { lim = g; break; }
-                if (g == sub) myBase = run;
-                run += eg;
+        while (first < GPW) {   // ONE pass unless the 8 segments need more than kFwdBudget entries (then as many groups as fit per pass)
+            int run = allEntries, lim = GPW, myBase = incl - e;
+            if (allEntries > kFwdBudget) {
+                run = 0; myBase = 0;
+                for (int g = first; g < GPW; g++) {
+                    const int eg = __shfl_sync(kFull, e, g * G);
+                    if (run + eg > kFwdBudget) { lim = g; break; }
+                    if (g == sub) myBase = run;
+                    run += eg;
+                }
             }
             if (run == 0) break;                      // only invalid segments left
             const bool act = valid && sub >= first && sub < lim;
@@ -273,11 +284,11 @@ ani_angular_fwd_seg_kernel(const AniTables* __restrict__ tab, const int* __restr
             for (int k = 0; k < NSA / 2; k++)
 #pragma unroll
                 for (int z = 0; z < NSZ; z++) acc2[k][z] = pk2(0.f, 0.f);
-            for (int q = gl; q < maxTrip; q += G) {
-                const bool v = q < trip;
-                int x = a + d + 1;
+            // one triple: lane-local state (a, d) -> neighbour slots, angular and radial factors, 32 channel updates
+            auto triple = [&](int ta, int td, bool v) {
+                int x = ta + td + 1;
                 x -= (x >= nsl) ? nsl : 0;
-                const int ja = v ? mb + a : 0, jb = v ? mb + (same ? x : tOff + d) : 0;
+                const int ja = v ? mb + ta : 0, jb = v ? mb + (same ? x : tOff + td) : 0;
                 const float4 va = sA[ja], vb = sA[jb];
                 const float fa = sFc[ja], fb = sFc[jb];
                 const float c = fmaf(va.z, vb.z, fmaf(va.y, vb.y, va.x * vb.x));
@@ -306,9 +317,24 @@ ani_angular_fwd_seg_kernel(const AniTables* __restrict__ tab, const int* __restr
 #pragma unroll
                     for (int z = 0; z < NSZ; z++) acc2[k][z] = ffma2(Pd[z], E2, acc2[k][z]);
                 }
+            };
+#if NNP_FWD_UNROLL == 2
+            // two triples per lane and trip: two independent MUFU / FMA chains in flight per warp
+            for (int q = gl; q < maxTrip; q += 2 * G) {
+                int a1 = a + G, d1 = d;
+                while (a1 >= nsl) { a1 -= nsl; d1++; }
+                triple(a, d, q < trip);
+                triple(a1, d1, q + G < trip);
+                a = a1 + G; d = d1;
+                while (a >= nsl) { a -= nsl; d++; }
+            }
+#else
+            for (int q = gl; q < maxTrip; q += G) {
+                triple(a, d, q < trip);
                 a += G;
                 while (a >= nsl) { a -= nsl; d++; }
             }
+#endif
             float acc[32];
 #pragma unroll
             for (int k = 0; k < NSA / 2; k++)
@@ -326,8 +352,7 @@ ani_angular_fwd_seg_kernel(const AniTables* __restrict__ tab, const int* __restr
                 }
             }
             if (act) {
-                const int orig = sortedOrig[p];
-                const size_t dst = (size_t)(rowMap ? rowMap[orig] : orig) * stride + (size_t)pIdx * 32 + gl * 8;
+                const size_t dst = (size_t)outRow * stride + (size_t)pIdx * 32 + gl * 8;
                 if (out.hi) {
                     uint32_t wh[4], wl[4];
 #pragma unroll
@@ -815,7 +840,7 @@ bool angular_v2_supported(const AniTables& t) {
     return t.fast && t.nShfA == 8 && t.nShfZ == 4 && t.torchani && t.nAngular == 32 && t.nSpecies <= 15;
 }
 
-void angular_v2_build_segments(int n, const AniTables& tabHost, const int* offAng, const int* hist, int* cursor, int2* segs, int* nSeg,
+void angular_v2_build_segments(int n, const AniTables& tabHost, const int* offAng, const int* hist, int* cursor, int4* segs, int* nSeg,
                                const int* sortedOrig, const int* rowMap, AevOutPtr out, int stride, cudaStream_t stream) {
     NNP_CUDA_CHECK(cudaMemsetAsync(const_cast<int*>(hist), 0, 2 * kSegBins * sizeof(int), stream));   // hist and cursor are adjacent
     const int grid = (n + kSegBins - 1) / kSegBins;
@@ -825,7 +850,7 @@ void angular_v2_build_segments(int n, const AniTables& tabHost, const int* offAn
 }
 
 void angular_v2_forward(int n, const AniTables& tabHost, const AniTables* tab, const int* offAng, int capA, const float4* geoA,
-                        const float4* geoB, const int2* segs, const int* nSeg, const int* sortedOrig, const int* rowMap, AevOutPtr out,
+                        const float4* geoB, const int4* segs, const int* nSeg, const int* sortedOrig, const int* rowMap, AevOutPtr out,
                         int stride, cudaStream_t stream) {
     NNP_REQUIRE(2 * capA <= kFwdBudget, "angular neighbour capacity above 128 is not supported by the segment kernel");
     const size_t smem = (size_t)kWarpsPerCta * kFwdBudget * 20;
@@ -835,7 +860,7 @@ void angular_v2_forward(int n, const AniTables& tabHost, const AniTables* tab, c
     const long long maxChunks = ((long long)n * tabHost.nPairs + 7) / 8;
     const int grid = (int)std::min<long long>((long long)sm_count_v2() * NNP_FWD_MINB, (maxChunks + kWarpsPerCta - 1) / kWarpsPerCta);
     if (grid <= 0) return;
-    k<<<grid, kWarpsPerCta * 32, smem, stream>>>(tab, offAng, capA, geoA, geoB, segs, nSeg, sortedOrig, rowMap, out, stride);
+    k<<<grid, kWarpsPerCta * 32, smem, stream>>>(tab, offAng, capA, geoA, geoB, segs, nSeg, out, stride);
     count_launch();
 }
 

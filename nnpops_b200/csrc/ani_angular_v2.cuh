@@ -20,11 +20,11 @@ bool angular_v2_supported(const AniTables& t);
 
 // Segment list of one forward: every non-empty (centre, species pair) block, sorted by size (largest first).  Empty blocks are
 // zero-filled here.  hist [kSegBins] and cursor [kSegBins] are scratch, adjacent in memory (hist first).
-void angular_v2_build_segments(int n, const AniTables& tabHost, const int* offAng, const int* hist, int* cursor, int2* segs, int* nSeg,
+void angular_v2_build_segments(int n, const AniTables& tabHost, const int* offAng, const int* hist, int* cursor, int4* segs, int* nSeg,
                                const int* sortedOrig, const int* rowMap, AevOutPtr out, int stride, cudaStream_t stream);
 
 void angular_v2_forward(int n, const AniTables& tabHost, const AniTables* tab, const int* offAng, int capA, const float4* geoA,
-                        const float4* geoB, const int2* segs, const int* nSeg, const int* sortedOrig, const int* rowMap, AevOutPtr out,
+                        const float4* geoB, const int4* segs, const int* nSeg, const int* sortedOrig, const int* rowMap, AevOutPtr out,
                         int stride, cudaStream_t stream);
 
 void angular_v2_backward(int n, const AniTables& tabHost, const AniTables* tab, const int* offAng, int capA, const float4* geoA,

@@ -115,7 +115,7 @@ __global__ void count_kernel(const T* __restrict__ pos, int n, Geom* __restrict_
 // exclusive scan of cellCount[0..ncells) into cellStart[0..ncells] by ONE CTA: every thread owns a contiguous chunk of cells (serial
 // sum, then serial write-back), the chunk totals are scanned across the CTA.  One pass over the array whatever the number of cells --
 // the ANI path uses cells of half the cutoff, 27 000 of them for the 50 000-atom box.
-__global__ void scan_kernel(const int* __restrict__ cellCount, int* __restrict__ cellStart, const Geom* __restrict__ geom, int maxCells,
+__global__ void scan_kernel(int* __restrict__ cellCount, int* __restrict__ cellStart, const Geom* __restrict__ geom, int maxCells,
                             const int* __restrict__ run) {
     if (run != nullptr && *run == 0) return;
     __shared__ int warpTot[32];
@@ -136,7 +136,8 @@ __global__ void scan_kernel(const int* __restrict__ cellCount, int* __restrict__
     }
     __syncthreads();
     int run0 = (w > 0 ? warpTot[w - 1] : 0) + x - sum;
-    for (int i = b; i < e; i++) { cellStart[i] = run0; run0 += cellCount[i]; }
+    // the counts are consumed here: zero them for the next build (no per-build memset launch; CellList::init zeroes them once)
+    for (int i = b; i < e; i++) { cellStart[i] = run0; run0 += cellCount[i]; cellCount[i] = 0; }
     if (threadIdx.x == blockDim.x - 1) cellStart[ncells] = warpTot[nw - 1];
 }
 
@@ -168,11 +169,6 @@ __global__ void order_kernel(const T* __restrict__ pos, const int* __restrict__ 
     sortedCell[dst] = c;
 }
 
-__global__ void zero_counts_kernel(int* __restrict__ cellCount, int count, const int* __restrict__ run) {
-    if (run != nullptr && *run == 0) return;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) cellCount[i] = 0;
-}
-
 }  // namespace
 
 void CellList::init(int numAtoms) {
@@ -183,6 +179,7 @@ void CellList::init(int numAtoms) {
     size_t na = (size_t)(n > 0 ? n : 1);
     NNP_CUDA_CHECK(cudaMalloc(&geom, sizeof(Geom)));
     NNP_CUDA_CHECK(cudaMalloc(&cellCount, sizeof(int) * (maxCells + 1)));
+    NNP_CUDA_CHECK(cudaMemset(cellCount, 0, sizeof(int) * (maxCells + 1)));   // kept zero between builds by scan_kernel
     NNP_CUDA_CHECK(cudaMalloc(&cellStart, sizeof(int) * (maxCells + 1)));
     NNP_CUDA_CHECK(cudaMalloc(&cellOf, sizeof(int) * na));
     NNP_CUDA_CHECK(cudaMalloc(&slot, sizeof(int) * na));
@@ -204,8 +201,6 @@ void CellList::build(const T* positions, const T* box, const int* tags, float cu
     if (n == 0) return;
     const int tb = 256, nb = (n + tb - 1) / tb;
     geom_kernel<T><<<1, 1024, 0, stream>>>(positions, n, box, cutoff, maxCells, geom, run);
-    if (run == nullptr) NNP_CUDA_CHECK(cudaMemsetAsync(cellCount, 0, sizeof(int) * (maxCells + 1), stream));
-    else zero_counts_kernel<<<std::min((maxCells + 1 + 255) / 256, 1184), 256, 0, stream>>>(cellCount, maxCells + 1, run);
     count_kernel<T><<<nb, tb, 0, stream>>>(positions, n, geom, cellCount, cellOf, slot, run);
     scan_kernel<<<1, 1024, 0, stream>>>(cellCount, cellStart, geom, maxCells, run);
     scatter_kernel<<<nb, tb, 0, stream>>>(n, cellOf, slot, cellStart, tmpIdx, run);
