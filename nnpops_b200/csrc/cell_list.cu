@@ -112,33 +112,48 @@ __global__ void count_kernel(const T* __restrict__ pos, int n, Geom* __restrict_
     slot[i] = atomicAdd(&cellCount[c], 1);
 }
 
-// exclusive scan of cellCount[0..ncells) into cellStart[0..ncells] by ONE CTA: every thread owns a contiguous chunk of cells (serial
-// sum, then serial write-back), the chunk totals are scanned across the CTA.  One pass over the array whatever the number of cells --
-// the ANI path uses cells of half the cutoff, 27 000 of them for the 50 000-atom box.
-__global__ void scan_kernel(int* __restrict__ cellCount, int* __restrict__ cellStart, const Geom* __restrict__ geom, int maxCells,
-                            const int* __restrict__ run) {
+// exclusive scan of cellCount[0..ncells) into cellStart[0..ncells] by ONE CTA, through shared memory: a tile of counts is loaded with
+// coalesced accesses, every thread scans its own contiguous chunk of the tile in shared memory (odd chunk length: no bank
+// conflicts), the chunk totals are scanned across the CTA, and the result goes back coalesced.  The counts are zeroed on the way
+// (no per-build memset).  The ANI path uses cells of half the cutoff: 27 000 cells for the 50 000-atom box, one tile.
+constexpr int kScanTile = 47 * 1024;   // ints of shared memory per tile (188 KB)
+
+__global__ void __launch_bounds__(1024)
+scan_kernel(int* __restrict__ cellCount, int* __restrict__ cellStart, const Geom* __restrict__ geom, int maxCells, const int* __restrict__ run) {
     if (run != nullptr && *run == 0) return;
+    extern __shared__ int tile[];
     __shared__ int warpTot[32];
+    __shared__ int carry;
     const int ncells = geom->ncells;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int chunk = (ncells + blockDim.x - 1) / blockDim.x;
-    const int b = min(threadIdx.x * chunk, ncells), e = min(b + chunk, ncells);
-    int sum = 0;
-    for (int i = b; i < e; i++) sum += cellCount[i];
-    int x = sum;
-    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(kFull, x, o); if (lane >= o) x += y; }
-    if (lane == 31) warpTot[w] = x;
-    __syncthreads();
-    if (w == 0) {
-        int t = lane < nw ? warpTot[lane] : 0;
-        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(kFull, t, o); if (lane >= o) t += y; }
-        warpTot[lane] = t;   // inclusive
+    if (threadIdx.x == 0) carry = 0;
+    for (int base = 0; base < ncells; base += kScanTile) {
+        const int cnt = min(kScanTile, ncells - base);
+        int chunk = (cnt + blockDim.x - 1) / blockDim.x;
+        chunk |= 1;                                           // odd stride between threads: conflict-free shared-memory walks
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) { tile[i] = cellCount[base + i]; cellCount[base + i] = 0; }
+        __syncthreads();
+        const int b = min(threadIdx.x * chunk, cnt), e = min(b + chunk, cnt);
+        int sum = 0;
+        for (int i = b; i < e; i++) sum += tile[i];
+        int x = sum;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(kFull, x, o); if (lane >= o) x += y; }
+        if (lane == 31) warpTot[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            int t = lane < nw ? warpTot[lane] : 0;
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(kFull, t, o); if (lane >= o) t += y; }
+            warpTot[lane] = t;   // inclusive
+        }
+        __syncthreads();
+        int run0 = carry + (w > 0 ? warpTot[w - 1] : 0) + x - sum;
+        for (int i = b; i < e; i++) { const int v = tile[i]; tile[i] = run0; run0 += v; }
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) cellStart[base + i] = tile[i];
+        if (threadIdx.x == 0) carry += warpTot[nw - 1];
+        __syncthreads();
     }
-    __syncthreads();
-    int run0 = (w > 0 ? warpTot[w - 1] : 0) + x - sum;
-    // the counts are consumed here: zero them for the next build (no per-build memset launch; CellList::init zeroes them once)
-    for (int i = b; i < e; i++) { cellStart[i] = run0; run0 += cellCount[i]; cellCount[i] = 0; }
-    if (threadIdx.x == blockDim.x - 1) cellStart[ncells] = warpTot[nw - 1];
+    if (threadIdx.x == 0) cellStart[ncells] = carry;
 }
 
 __global__ void scatter_kernel(int n, const int* __restrict__ cellOf, const int* __restrict__ slot, const int* __restrict__ cellStart,
@@ -202,7 +217,14 @@ void CellList::build(const T* positions, const T* box, const int* tags, float cu
     const int tb = 256, nb = (n + tb - 1) / tb;
     geom_kernel<T><<<1, 1024, 0, stream>>>(positions, n, box, cutoff, maxCells, geom, run);
     count_kernel<T><<<nb, tb, 0, stream>>>(positions, n, geom, cellCount, cellOf, slot, run);
-    scan_kernel<<<1, 1024, 0, stream>>>(cellCount, cellStart, geom, maxCells, run);
+    static bool attr[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr[dev]) {
+        NNP_CUDA_CHECK(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanTile * (int)sizeof(int)));
+        attr[dev] = true;
+    }
+    scan_kernel<<<1, 1024, kScanTile * sizeof(int), stream>>>(cellCount, cellStart, geom, maxCells, run);
     scatter_kernel<<<nb, tb, 0, stream>>>(n, cellOf, slot, cellStart, tmpIdx, run);
     order_kernel<T><<<nb, tb, 0, stream>>>(positions, tags, n, cellOf, cellStart, tmpIdx, sorted, sortedOrig, sortedCell, run);
     count_launch(5);
