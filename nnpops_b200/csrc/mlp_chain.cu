@@ -11,11 +11,12 @@
 // Every operand is an fp16 hi/lo pair (mlp_tcgen05.cu: x = hi + 2^-11 lo, three MMAs per product, fp32 accumulation), so the
 // result carries ~22 mantissa bits.  Activations alternate between tensor memory and shared memory because neither holds two
 // consecutive ones: TMEM = 2 accumulator stages x 128 columns + 256 columns of packed fp16 A operand (K <= 256); shared memory
-// = X (<= 64 KB) + one activation buffer (<= 96 KB) + a ring of 16 KB weight blocks.  The only activation that does not fit, A1
-// (needed again for celu' in G2), goes through a per-CTA fp32 scratch that stays in L2 (128 KB per CTA, rewritten every chain).
+// = one activation buffer (<= 96 KB: X during F1, A2 from F2 to G3, dZ1 from G3 to G2; X is re-fetched per chain from L2 under G1 of the
+// previous chain, which buys 64 KB for the weight ring) + a ring of eight 16 KB weight blocks.  The only activation that does not
+// fit, A1 (needed again for celu' in G2), goes through a per-CTA fp32 scratch that stays in L2 (128 KB per CTA, rewritten every chain).
 //
 // Work split inside the CTA (576 threads):
-//   warp 0        TMA producer: X once per tile, then one 16 KB weight block [64 hi rows + 64 lo rows][64 k] per (n-chunk, k-chunk)
+//   warp 0        TMA producer: X once per chain, then one 16 KB weight block [64 hi rows + 64 lo rows][64 k] per (n-chunk, k-chunk)
 //   warp 1        TMEM allocator + MMA issuer (one elected lane): per k16 step  [D1 | D2] (+)= Ahi . [Bhi; Blo]  (N = 128) and
 //                 D2 += Alo . Bhi (N = 64); tcgen05.commit frees ring slots and publishes accumulator stages
 //   warps 2-9     epilogue group 0 (accumulator stage 0),  warps 10-17 epilogue group 1 (stage 1): 64-column chunks alternate
@@ -27,6 +28,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <cstdio>
 #include "tcgen05_util.cuh"
 
 namespace nnpops {
@@ -90,6 +92,22 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+#ifdef CHAIN_TRACE
+// development: per-role event log of CTA 0 (role 0/1 = MMA issuers, 2/3 = lane 0 of the first warp of each epilogue group); entry =
+// tag << 40 | clock.  Printed by the kernel itself when it ends.
+constexpr int kTraceLen = 1024;
+__device__ long long gTrace[4][kTraceLen];
+__device__ int gTraceN[4];
+__device__ __forceinline__ void trace_ev(int role, int tag) {
+    if (blockIdx.x != 0) return;
+    const int n = gTraceN[role];
+    if (n < kTraceLen) { gTrace[role][n] = ((long long)tag << 40) | (clock64() & 0xffffffffffLL); gTraceN[role] = n + 1; }
+}
+#define TRACE(role, tag) trace_ev(role, tag)
+#else
+#define TRACE(role, tag)
+#endif
+
 // tcgen05.mma with the shared-memory descriptors given as low words (start address | LBO) + one common high word: the issue loop
 // then runs on 32-bit adds only
 __device__ __forceinline__ void umma_ss_lo(uint32_t tmemD, uint32_t aLo, uint32_t bLo, uint32_t descHi, uint32_t idesc, uint32_t accumulate) {
@@ -122,94 +140,170 @@ struct EpiCtx {
     uint32_t sLoOff;        // byte offset of the lo tiles of that buffer
     int r7;                 // row & 7 (swizzle phase)
     int hsel, n0, c;
+    int trace;              // development (CHAIN_TRACE): event-log role of this thread's warp, or -1
     bool rowOk;
 };
 
-// TYPE: 0 F1, 1 F2, 2 F3, 3 G3, 4 G2, 5 G1.  Processes the thread's 32 columns [n0, n0 + 32) of chunk c as two halves of 16.
+// packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2: one issue slot for two columns).  The epilogue warps share their schedulers with the
+// MMA issuers and are issue-bound, so every instruction saved here shortens the phases in which the tensor pipe waits for an operand.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float a, float b) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ u64 pk2u(uint32_t a, uint32_t b) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ void unpk2(u64 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float ex2_f(float x) { float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x)); return e; }
+// (a, b) as a packed pair -> packed fp16 pair of the high parts and packed pair of the scaled low parts
+__device__ __forceinline__ void split_pack2(u64 v, uint32_t& hi, uint32_t& lo) {
+    float a, b;
+    unpk2(v, a, b);
+    const __half2 h2 = __floats2half2_rn(a, b);
+    const float2 f2 = __half22float2(h2);
+    hi = *reinterpret_cast<const uint32_t*>(&h2);
+    const u64 d = fmul2(ffma2(pk2(f2.x, f2.y), pk2(-1.0f, -1.0f), v), pk2(kLoScale, kLoScale));   // (v - hi) * 2^11, exact
+    unpk2(d, a, b);
+    lo = pack_h2(a, b);
+}
+
+// TYPE: 0 F1, 1 F2, 2 F3, 3 G3, 4 G2, 5 G1.  Processes the thread's 32 columns [n0, n0 + 32) of chunk c: the accumulator pair (D1, D2) is
+// pulled into registers as 16 packed column pairs and the stage is handed back to the MMA warp BEFORE any arithmetic.
 template <int TYPE>
 __device__ __forceinline__ void epi_chunk(const ChainParams& P, const EpiCtx& x, const float* __restrict__ colA, const float* __restrict__ colB,
                                           float* stash, float* dxRow, bool firstMember, uint32_t accFullBar, uint32_t fullPhase, uint32_t accEmptyBar, int lane,
                                           float& esum) {
-    float st[TYPE == 4 ? 32 : 1];
-    if (TYPE == 4) {   // A1 of these columns, written by F1's epilogue of this chain: fetch before the accumulator is needed
+    // fetched before the accumulator is needed (with 224 KB of shared memory in use the L1 is small: a load after the wait may cost an
+    // L2 trip): the biases of the thread's columns (every lane reads the same 16-byte words: broadcast), or -- G2 -- A1 of these columns,
+    // written to the stash by F1's epilogue of this chain
+    u64 pre[(TYPE <= 2 || TYPE == 4) ? 16 : 1];
+#ifndef CHAIN_EXP_EPI_LITE
+    if (TYPE <= 2) {
+        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(colA + x.n0);
 #pragma unroll
-        for (int i = 0; i < 32; i++) st[i] = __ldcg(stash + (size_t)(x.n0 + i) * kRows);
+        for (int i = 0; i < 8; i++) { const ulonglong2 t = __ldg(src + i); pre[2 * i] = t.x; pre[2 * i + 1] = t.y; }
     }
-    // per-column constants (bias; output-layer weight): lane l fetches column n0 + l before the wait and every lane picks its
-    // values up by shuffle -- with 224 KB of shared memory in use the L1 holds next to nothing, a load after the wait costs an L2 trip
-    float colConstA = 0.0f, colConstB = 0.0f;
-    if (TYPE <= 2) colConstA = __ldg(colA + x.n0 + lane);
-    if (TYPE == 2) colConstB = __ldg(colB + x.n0 + lane);
+    if (TYPE == 4) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) pre[i] = pk2(__ldcg(stash + (size_t)(x.n0 + 2 * i) * kRows), __ldcg(stash + (size_t)(x.n0 + 2 * i + 1) * kRows));
+    }
+#endif
+    if (x.trace >= 0 && lane == 0) TRACE(x.trace, 0x600 | TYPE << 4 | x.c);
     mbar_wait(accFullBar, fullPhase);
     tc_fence_after();
+    if (x.trace >= 0 && lane == 0) TRACE(x.trace, 0x700 | TYPE << 4 | x.c);
+    u64 vv[16];
+    const u64 loInv2 = pk2(kLoInv, kLoInv);
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         uint32_t r1[16], r2[16];
         tmem_ld16(x.laneBase + x.accCol + 16 * h, r1);
         tmem_ld16(x.laneBase + x.accCol + 64 + 16 * h, r2);
         tmem_ld_wait();
-        if (h == 1) {   // the accumulator stage has been read completely: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(accEmptyBar);
-        }
-        float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; j++) v[j] = fmaf(__uint_as_float(r2[j]), kLoInv, __uint_as_float(r1[j]));
+        for (int i = 0; i < 8; i++) vv[8 * h + i] = ffma2(pk2u(r2[2 * i], r2[2 * i + 1]), loInv2, pk2u(r1[2 * i], r1[2 * i + 1]));
+    }
+    // the accumulator stage has been read completely: hand it back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(accEmptyBar);
+    if (x.trace >= 0 && lane == 0) TRACE(x.trace, 0x800 | TYPE << 4 | x.c);
+
+    if (TYPE == 5) {
+        if (x.rowOk) {
+            const u64 os2 = pk2(P.outScale, P.outScale);
+            float* dst = dxRow + x.n0;
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                float a, b, c, d;
+                unpk2(fmul2(vv[i], os2), a, b);
+                unpk2(fmul2(vv[i + 1], os2), c, d);
+                if (firstMember) *reinterpret_cast<float4*>(dst + 2 * i) = make_float4(a, b, c, d);
+                else red_add_v4(dst + 2 * i, a, b, c, d);
+            }
+        }
+        return;
+    }
+#ifdef CHAIN_EXP_EPI_LITE
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        uint32_t ph[8], pl[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { float a, b; unpk2(vv[8 * h + i], a, b); ph[i] = pack_h2(a, b); pl[i] = 0; }
+        const int u0 = x.hsel * 4 + 2 * h;
+        const uint32_t sA = x.sbufRow + (uint32_t)x.c * kTile + (uint32_t)((u0 ^ x.r7) << 4);
+        const uint32_t sB = x.sbufRow + (uint32_t)x.c * kTile + (uint32_t)(((u0 + 1) ^ x.r7) << 4);
+        if (TYPE == 1 || TYPE == 3) {
+            st_shared_v4(sA, ph[0], ph[1], ph[2], ph[3]);
+            st_shared_v4(sB, ph[4], ph[5], ph[6], ph[7]);
+            st_shared_v4(sA + x.sLoOff, pl[0], pl[1], pl[2], pl[3]);
+            st_shared_v4(sB + x.sLoOff, pl[4], pl[5], pl[6], pl[7]);
+        } else {
+            tmem_st8(x.laneBase + kOpaHi + (uint32_t)((x.n0 + 16 * h) >> 1), ph);
+            tmem_st8(x.laneBase + kOpaLo + (uint32_t)((x.n0 + 16 * h) >> 1), pl);
+        }
+    }
+#else
+    const u64 celuScale2 = pk2(1.4426950408889634f / kCeluAlpha, 1.4426950408889634f / kCeluAlpha);
+    const u64 alpha2 = pk2(kCeluAlpha, kCeluAlpha), negAlpha2 = pk2(-kCeluAlpha, -kCeluAlpha);
+    const u64 invAlpha2 = pk2(1.0f / kCeluAlpha, 1.0f / kCeluAlpha), one2 = pk2(1.0f, 1.0f);
+    u64 esum2 = pk2(0.0f, 0.0f);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
         const int col = x.n0 + 16 * h;
-        if (TYPE == 5) {
-            if (x.rowOk) {
-                float* dst = dxRow + col;
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    const float a = v[j] * P.outScale, b = v[j + 1] * P.outScale, c = v[j + 2] * P.outScale, d = v[j + 3] * P.outScale;
-                    if (firstMember) *reinterpret_cast<float4*>(dst + j) = make_float4(a, b, c, d);
-                    else red_add_v4(dst + j, a, b, c, d);
-                }
-            }
-            continue;
-        }
-        if (TYPE == 0 || TYPE == 1) {
-#pragma unroll
-            for (int j = 0; j < 16; j++) v[j] = celu_f(v[j] + __shfl_sync(0xffffffffu, colConstA, 16 * h + j));
-            if (TYPE == 0) {
-#pragma unroll
-                for (int j = 0; j < 16; j++) __stcg(stash + (size_t)(col + j) * kRows, v[j]);
-            }
-        } else if (TYPE == 2) {
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-                const float z = v[j] + __shfl_sync(0xffffffffu, colConstA, 16 * h + j);
-                const float w = __shfl_sync(0xffffffffu, colConstB, 16 * h + j);
-                float e;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * (1.4426950408889634f / kCeluAlpha)));
-                const bool pos = z > 0.0f;
-                const float a = pos ? z : fmaf(kCeluAlpha, e, -kCeluAlpha);
-                esum = fmaf(x.rowOk ? a : 0.0f, w, esum);
-                v[j] = (w * P.seedScale) * (pos ? 1.0f : e);
-            }
-        } else if (TYPE == 4) {
-#pragma unroll
-            for (int j = 0; j < 16; j++) v[j] *= celu_grad_from_act_f(st[16 * h + j]);
-        }
         // where the two 16-byte units of this half live in the thread's row of the swizzled shared-memory tile
         const int u0 = x.hsel * 4 + 2 * h;
         const uint32_t sA = x.sbufRow + (uint32_t)x.c * kTile + (uint32_t)((u0 ^ x.r7) << 4);
         const uint32_t sB = x.sbufRow + (uint32_t)x.c * kTile + (uint32_t)(((u0 + 1) ^ x.r7) << 4);
+        u64 w3v[TYPE == 2 ? 8 : 1];
+        uint32_t hh[TYPE == 3 ? 8 : 1], ll[TYPE == 3 ? 8 : 1];
+        if (TYPE == 2) {   // output-layer weights of these columns
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(colB + col);
+#pragma unroll
+            for (int i = 0; i < 4; i++) { const ulonglong2 t = __ldg(src + i); w3v[2 * i] = t.x; w3v[2 * i + 1] = t.y; }
+        }
         if (TYPE == 3) {   // celu'(A2) from the activation tile this thread is about to overwrite
             const uint4 h0 = ld_shared_v4(sA), h1 = ld_shared_v4(sB), l0 = ld_shared_v4(sA + x.sLoOff), l1 = ld_shared_v4(sB + x.sLoOff);
-            const uint32_t hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-            const uint32_t ll[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const float2 fh = unpack_h2(hh[i]), fl = unpack_h2(ll[i]);
-                v[2 * i] *= celu_grad_from_act_f(fmaf(fl.x, kLoInv, fh.x));
-                v[2 * i + 1] *= celu_grad_from_act_f(fmaf(fl.y, kLoInv, fh.y));
-            }
+            hh[0] = h0.x; hh[1] = h0.y; hh[2] = h0.z; hh[3] = h0.w; hh[4] = h1.x; hh[5] = h1.y; hh[6] = h1.z; hh[7] = h1.w;
+            ll[0] = l0.x; ll[1] = l0.y; ll[2] = l0.z; ll[3] = l0.w; ll[4] = l1.x; ll[5] = l1.y; ll[6] = l1.z; ll[7] = l1.w;
         }
         uint32_t ph[8], pl[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) split_pack(v[2 * i], v[2 * i + 1], ph[i], pl[i]);
+        for (int i = 0; i < 8; i++) {
+            u64 v = vv[8 * h + i];
+            if (TYPE <= 2) {
+                const u64 z2 = fadd2(v, pre[8 * h + i]);
+                float z0, z1, t0, t1, n0, n1;
+                unpk2(z2, z0, z1);
+                unpk2(fmul2(z2, celuScale2), t0, t1);
+                const float e0 = ex2_f(t0), e1 = ex2_f(t1);
+                unpk2(ffma2(pk2(e0, e1), alpha2, negAlpha2), n0, n1);   // for large positive z the exponential overflows to +inf, which the select discards
+                const bool p0 = z0 > 0.0f, p1 = z1 > 0.0f;
+                const u64 a2 = pk2(p0 ? z0 : n0, p1 ? z1 : n1);
+                if (TYPE == 2) {
+                    esum2 = ffma2(a2, w3v[i], esum2);
+                    const u64 seed2 = pk2(P.seedScale, P.seedScale);
+                    v = fmul2(fmul2(w3v[i], seed2), pk2(p0 ? 1.0f : e0, p1 ? 1.0f : e1));
+                } else {
+                    v = a2;
+                    if (TYPE == 0) {
+                        __stcg(stash + (size_t)(col + 2 * i) * kRows, p0 ? z0 : n0);
+                        __stcg(stash + (size_t)(col + 2 * i + 1) * kRows, p1 ? z1 : n1);
+                    }
+                }
+            } else {
+                u64 act2;
+                if (TYPE == 4) act2 = pre[8 * h + i];
+                else {
+                    const float2 fh = unpack_h2(hh[i]), fl = unpack_h2(ll[i]);
+                    act2 = ffma2(pk2(fl.x, fl.y), loInv2, pk2(fh.x, fh.y));
+                }
+                float a0, a1, g0, g1;
+                unpk2(act2, a0, a1);
+                unpk2(ffma2(act2, invAlpha2, one2), g0, g1);   // celu'(z) from celu(z): 1 for a > 0, a / alpha + 1 otherwise
+                v = fmul2(v, pk2(a0 > 0.0f ? 1.0f : g0, a1 > 0.0f ? 1.0f : g1));
+            }
+            split_pack2(v, ph[i], pl[i]);
+        }
         if (TYPE == 1 || TYPE == 3) {
             st_shared_v4(sA, ph[0], ph[1], ph[2], ph[3]);
             st_shared_v4(sB, ph[4], ph[5], ph[6], ph[7]);
@@ -220,14 +314,19 @@ __device__ __forceinline__ void epi_chunk(const ChainParams& P, const EpiCtx& x,
             tmem_st8(x.laneBase + kOpaLo + (uint32_t)(col >> 1), pl);
         }
     }
+    if (TYPE == 2 && x.rowOk) {   // rows beyond the species' last atom hold zeros in X (TMA out-of-bounds fill), finite everywhere
+        float s0, s1;
+        unpk2(esum2, s0, s1);
+        esum += s0 + s1;
+    }
+#endif
 }
 
 __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_constant__ ChainParams P) {
     extern __shared__ unsigned char smemRaw[];
     const uint32_t rawAddr = smem_u32(smemRaw);
     const uint32_t base = (rawAddr + 1023u) & ~1023u;
-    const uint32_t xbuf = base;
-    const uint32_t sbuf = xbuf + 2u * P.xChunks * kTile;
+    const uint32_t sbuf = base;   // X of the chain (F1), then A2 (F2 -> F3, G3), then dZ1 (G3 -> G2): hi tiles [0, sChunks), lo tiles behind
     const uint32_t ring = sbuf + 2u * P.sChunks * kTile;
     const uint32_t barBase = ring + (uint32_t)P.ring * kTile;
     auto bFull = [&](int s) { return barBase + 8u * s; };
@@ -294,18 +393,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
                 const int upt = P.M / P.mpu, t = u / upt, e0 = (u - t * upt) * P.mpu, e1 = e0 + P.mpu;
                 const int si = species_of(t);
                 const ChainSpecies& sp = P.sp[si];
-                if (g == 0) {
-                    const int row0 = (t - sp.tileBegin) * kRows;
-                    const int cx = chunks_of(sp.d0);
-                    mbar_wait(xEmpty, xPhase ^ 1u);
-                    xPhase ^= 1u;
-                    mbar_expect_tx(xFull, 2u * cx * kTile);
-                    for (int kc = 0; kc < cx; kc++) {
-                        tma_load_2d(xbuf + kc * kTile, &P.maps[si][6], xFull, kc * 64, row0);
-                        tma_load_2d(xbuf + (P.xChunks + kc) * kTile, &P.maps[si][7], xFull, kc * 64, row0);
-                    }
-                }
                 for (int e = e0; e < e1; e++) {
+                    if (g == 0) {
+                        // X shares the activation buffer: it is (re)loaded for every chain, as soon as G2 of the previous chain -- the
+                        // last reader of that buffer -- has completed (both issuers arrive on xEmpty when they have seen G1's operand)
+                        const int row0 = (t - sp.tileBegin) * kRows;
+                        const int cx = chunks_of(sp.d0);
+                        mbar_wait(xEmpty, xPhase ^ 1u);
+                        xPhase ^= 1u;
+                        mbar_expect_tx(xFull, 2u * cx * kTile);
+                        for (int kc = 0; kc < cx; kc++) {
+                            tma_load_2d(sbuf + kc * kTile, &P.maps[si][6], xFull, kc * 64, row0);
+                            tma_load_2d(sbuf + (P.sChunks + kc) * kTile, &P.maps[si][7], xFull, kc * 64, row0);
+                        }
+                    }
                     int chunkIdx = 0;
                     for (int j = 0; j < 6; j++) {
                         int N, K;
@@ -338,7 +439,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
             auto desc_lo = [](uint32_t addr) { return ((addr >> 4) & 0x3fffu) | (1u << 16); };   // start address | LBO = 1
             constexpr uint32_t kTile16 = kTile >> 4;
             const int half = P.ring >> 1, s0 = g * half;   // this issuer's half of the weight ring
-            const uint32_t ringLo = desc_lo(ring) + s0 * kTile16, xLo = desc_lo(xbuf), sLo = desc_lo(sbuf);
+            const uint32_t ringLo = desc_lo(ring) + s0 * kTile16, sLo = desc_lo(sbuf);
             const uint32_t d = tmemBase + g * kAccCols;
             const uint32_t accFullBar = accFull(g), accEmptyBar = accEmpty(g);
             int stage = 0;
@@ -347,10 +448,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
                 const int upt = P.M / P.mpu, t = u / upt, e0 = (u - t * upt) * P.mpu, e1 = e0 + P.mpu;
                 const int si = species_of(t);
                 const ChainSpecies& sp = P.sp[si];
-                mbar_wait(xFull, xPhase);
-                xPhase ^= 1u;
-                tc_fence_after();
                 for (int e = e0; e < e1; e++) {
+                    mbar_wait(xFull, xPhase);
+                    xPhase ^= 1u;
+                    tc_fence_after();
                     int chunkIdx = 0;
                     for (int j = 0; j < 6; j++) {
                         int N, K;
@@ -359,28 +460,36 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
                         const int lastSteps = (K - (ck - 1) * 64) >> 4;
                         const bool aTmem = (j & 1) != 0;                 // F2, G3, G1 read their A operand from tensor memory
                         // A operand: address of k-chunk 0 (TMEM column, or descriptor low word), stride per k-chunk, offset of the lo part
-                        const uint32_t aBase = aTmem ? tmemBase + kOpaHi : (j == 0 ? xLo : sLo);
+                        const uint32_t aBase = aTmem ? tmemBase + kOpaHi : sLo;
                         const uint32_t aChunk = aTmem ? 32u : kTile16;
-                        const uint32_t aLoOff = aTmem ? (kOpaLo - kOpaHi) : (uint32_t)(j == 0 ? P.xChunks : P.sChunks) * kTile16;
+                        const uint32_t aLoOff = aTmem ? (kOpaLo - kOpaHi) : (uint32_t)P.sChunks * kTile16;
                         bool needOp = j > 0;   // the A operand of this layer has not been waited for yet (by this issuer)
                         bool chainCommitted = false;
                         for (int c = 0; c < cn; c++) {
                             const int acc = chunkIdx & 1;
                             chunkIdx++;
                             if (acc != g) continue;   // the other issuer's chunk
+                            TRACE(g, 0x100 | j << 4 | c);
                             mbar_wait(accEmptyBar, accPhase ^ 1u);
                             accPhase ^= 1u;
                             tc_fence_after();
+                            TRACE(g, 0x200 | j << 4 | c);
                             for (int kc = 0; kc < ck; kc++) {
                                 if (needOp) {   // columns [64 kc, 64 kc + 64) of the A operand come from the previous layer's epilogue
                                     mbar_wait(opReady(kc), (opBits >> kc) & 1u);
                                     opBits ^= 1u << kc;
+                                    TRACE(g, 0x300 | j << 4 | kc);
                                 }
                                 mbar_wait(bFull(s0 + stage), phase);
                                 tc_fence_after();
+                                TRACE(g, 0x400 | j << 4 | kc);
                                 const uint32_t bLo = ringLo + stage * kTile16;
                                 const uint32_t a = aBase + kc * aChunk;
+#ifdef CHAIN_EXP_MMA_LITE
+                                const int steps = 1;
+#else
                                 const int steps = kc == ck - 1 ? lastSteps : 4;
+#endif
                                 if (aTmem) {
 #pragma unroll
                                     for (int k = 0; k < 4; k++)
@@ -398,6 +507,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
                                 }
                                 umma_commit(bEmpty(s0 + stage));
                                 if (kc == ck - 1) {
+                                    TRACE(g, 0x500 | j << 4 | c);
                                     umma_commit(accFullBar);
                                     // G1 reads dZ0 from the TMEM operand columns the next chain's first epilogue overwrites: that epilogue waits
                                     // until the last G1 chunk of BOTH issuers has completed
@@ -408,8 +518,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
                             if (needOp) {
                                 needOp = false;
                                 // every slice of this layer's A operand is published, so all MMAs of the previous layer are complete: when
-                                // that layer was the last F1 of the tile, X may be replaced
-                                if (j == 1 && e == e1 - 1) mbar_arrive(xEmpty);
+                                // that layer was G2, the activation buffer is free for the next chain's X
+                                if (j == 5) mbar_arrive(xEmpty);
                             }
                         }
                         if (needOp) {
@@ -420,7 +530,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
                                 mbar_wait(opReady(kc), (opBits >> kc) & 1u);
                                 opBits ^= 1u << kc;
                             }
-                            if (j == 1 && e == e1 - 1) mbar_arrive(xEmpty);
+                            if (j == 5) mbar_arrive(xEmpty);
                         }
                         if (j == 5 && !chainCommitted) mbar_arrive(chainDone);   // G1 had a single chunk and it was the other issuer's
                     }
@@ -439,6 +549,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
         x.sLoOff = (uint32_t)P.sChunks * kTile;
         x.r7 = r & 7;
         x.hsel = hsel;
+        x.trace = (ew & 7) == 0 ? 2 + g : -1;
         float* const stash = P.stash + (size_t)blockIdx.x * (kStashCols * kRows) + r;
         uint32_t fullPhase = 0, chainPhase = 0;
         for (int u = blockIdx.x; u < P.numUnits; u += gridDim.x) {
@@ -487,6 +598,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
                             else { tmem_st_wait(); tc_fence_before(); }
                             __syncwarp();
                             if (lane == 0) mbar_arrive(opReady(c));
+                            if (x.trace >= 0 && lane == 0) TRACE(x.trace, 0x900 | j << 4 | c);
                         }
                     }
                 }
@@ -498,6 +610,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
     }
     tc_fence_before();
     __syncthreads();
+#ifdef CHAIN_TRACE
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int r = 0; r < 4; r++) {
+            for (int i = 0; i < gTraceN[r]; i++) printf("T %d %x %lld\n", r, (int)(gTrace[r][i] >> 40), gTrace[r][i] & 0xffffffffffLL);
+            gTraceN[r] = 0;
+        }
+    }
+#endif
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(512u) : "memory");
@@ -543,9 +663,9 @@ bool MlpChain::eligible(int numSpecies, const SpeciesDesc* sp, int featureStride
         if (d[0] != featureStride || d[0] > 128 || d[1] > 256 || d[2] > 256 || d[3] > 256) return false;
         for (int l = 0; l < 4; l++)
             if (d[l] <= 0 || d[l] % 32 != 0) return false;
-        sMax = std::max(sMax, chunks_of(d[2]));
+        sMax = std::max(sMax, std::max(chunks_of(d[2]), chunks_of(d[0])));
     }
-    const uint32_t fixed = 2u * (chunks_of(featureStride) + sMax) * kTile + 1024 + 512;
+    const uint32_t fixed = 2u * sMax * kTile + 1024 + 512;
     return fixed + 4 * kTile <= kMaxSmem;
 }
 
@@ -567,7 +687,7 @@ MlpChain::MlpChain(int ensemble, int numSpecies, const SpeciesDesc* sp, const __
         impl_->rows = std::max<long long>(impl_->rows, (long long)c.rowStart + c.rows);
         for (int l = 0; l < 3; l++) c.bias[l] = sp[s].bias[l];
         c.w3 = sp[s].w3;
-        P.sChunks = std::max(P.sChunks, chunks_of(c.d2));
+        P.sChunks = std::max(P.sChunks, std::max(chunks_of(c.d2), chunks_of(c.d0)));
         // GEMM j: N, K, layer, transposed
         const int gN[6] = {c.d1, c.d2, c.d3, c.d2, c.d1, c.d0}, gK[6] = {c.d0, c.d1, c.d2, c.d3, c.d2, c.d1};
         const int gL[6] = {0, 1, 2, 2, 1, 0};
@@ -589,8 +709,9 @@ MlpChain::MlpChain(int ensemble, int numSpecies, const SpeciesDesc* sp, const __
         }
     }
     P.numTiles = tiles;
-    const uint32_t fixed = 2u * (P.xChunks + P.sChunks) * kTile + 1024 + 512;
+    const uint32_t fixed = 2u * P.sChunks * kTile + 1024 + 512;
     P.ring = (int)std::min<uint32_t>(kMaxRing, (kMaxSmem - fixed) / kTile) & ~1;   // an even number of slots: one half per MMA issuer
+    if (const char* e = std::getenv("NNPOPS_CHAIN_RING")) P.ring = std::max(2, std::min(P.ring, std::atoi(e))) & ~1;   // development: ring depth sensitivity
     impl_->smem = fixed + P.ring * kTile;
     int dev = 0, sms = 0;
     NNP_CUDA_CHECK(cudaGetDevice(&dev));
