@@ -175,6 +175,15 @@ NNPOPS_API int nnpops_neighbor_pairs_backward_f64(const int* neighbors, const do
 NNPOPS_API int nnpops_pme_direct(const float* positions, const float* charges, const int* neighbors, const float* deltas,
                                  const float* distances, const int* exclusions, int num_atoms, long long num_pairs, int max_exclusions,
                                  float alpha, float coulomb, float* energy, float* pos_deriv, float* charge_deriv, void* stream);
+/* Direct space WITHOUT a pair list: what PME.compute_direct does in two steps (pme.py:131-165: getNeighborPairs + pme::pme_direct;
+ * kernels getNeighborPairsCUDA.cu:31-101 + pmeCUDA.cu:30-95) as one centre-owned traversal of a cell list -- same accepted pairs
+ * (reference minimum-image arithmetic, distance <= cutoff), same exclusion test and correction, no 24-bytes-per-pair list and no
+ * atomics.  box: [3][3].  shard_index / shard_count (0 / 1 for everything) select a contiguous range of the cell-sorted atoms, a
+ * slab of the box, as the centres of this call: energy and derivatives of the shards add up to the whole (atoms outside the range
+ * receive zeros), so one process per GPU evaluates one shard and the results are summed by an all-reduce. */
+NNPOPS_API int nnpops_pme_direct_fused(const float* positions, const float* charges, const float* box, const int* exclusions,
+                                       int num_atoms, int max_exclusions, float cutoff, float alpha, float coulomb, int shard_index,
+                                       int shard_count, float* energy, float* pos_deriv, float* charge_deriv, void* stream);
 NNPOPS_API int nnpops_pme_reciprocal_forward(const float* positions, const float* charges, const float* box, int num_atoms, int gridx,
                                              int gridy, int gridz, int order, float alpha, float coulomb, const float* xmoduli,
                                              const float* ymoduli, const float* zmoduli, float* energy, float* recip_grid, void* stream);

@@ -27,6 +27,8 @@ void cfconv_compute(const CFConvFilter*, const CFConvNeighborList*, const float*
 void cfconv_backprop(const CFConvFilter*, const CFConvNeighborList*, const float*, const float*, float*, float*, cudaStream_t);
 void pme_direct(const float*, const float*, const int*, const float*, const float*, const int*, int, long long, int, float, float, float*,
                 float*, float*, cudaStream_t);
+void pme_direct_fused(const float*, const float*, const float*, const int*, int, int, float, float, float, int, int, float*, float*, float*,
+                      cudaStream_t);
 void pme_reciprocal_forward(const float*, const float*, const float*, int, int, int, int, int, float, float, const float*, const float*,
                             const float*, float*, float*, cudaStream_t);
 void pme_reciprocal_backward(const float*, const float*, const float*, int, int, int, int, int, float, const float*, float*, float*,
@@ -434,6 +436,16 @@ int nnpops_pme_direct(const float* positions, const float* charges, const int* n
         require_device();
         pme_direct(positions, charges, neighbors, deltas, distances, exclusions, num_atoms, num_pairs, max_exclusions, alpha, coulomb, energy,
                    pos_deriv, charge_deriv, (cudaStream_t)stream);
+    });
+}
+
+int nnpops_pme_direct_fused(const float* positions, const float* charges, const float* box, const int* exclusions, int num_atoms,
+                            int max_exclusions, float cutoff, float alpha, float coulomb, int shard_index, int shard_count, float* energy,
+                            float* pos_deriv, float* charge_deriv, void* stream) {
+    return guarded([&] {
+        require_device();
+        pme_direct_fused(positions, charges, box, exclusions, num_atoms, max_exclusions, cutoff, alpha, coulomb, shard_index, shard_count,
+                         energy, pos_deriv, charge_deriv, (cudaStream_t)stream);
     });
 }
 

@@ -1,0 +1,231 @@
+// PME direct space fused into the cell-list traversal: no pair list, no atomics.
+//
+// The reference evaluates the direct-space sum from a materialised pair list (pme.py:131-165: getNeighborPairs, then the kernel
+// computeDirect, pmeCUDA.cu:30-95, one thread per pair with eight float atomics per pair).  At BASELINE config 5 (200 000 charges,
+// 0.9 nm) that list is 29.5 M pairs = 730 MB written and read back, and the atomics bound the kernel.  Here ONE kernel does both
+// steps, centre-owned: a warp takes a centre atom, walks the 27 cells around it, accepts a neighbour with exactly the arithmetic of
+// getNeighborPairs (pair_delta.cuh: delta = pos[row] - pos[col] with row > col, sequential minimum image by division, distance <=
+// cutoff), applies the exclusion test of computeDirect (the row atom's sorted exclusion list is scanned for the column atom) and
+// accumulates the centre's own dE/dx, dE/dq in registers; every pair is visited from both ends, its energy is counted at the row end.
+// The exclusion correction (pmeCPU.cpp:133-157: minus the erf part, NON-periodic displacement) is centre-owned too.  Outputs are
+// plain stores -- nothing is zeroed or reduced across warps -- so a range of centres is a complete, independent piece of work:
+// `shardIndex / shardCount` select a contiguous range of the CELL-SORTED atoms (cells are ordered x-major: a slab of the box) for
+// one GPU of several (pme.py: PME.compute_direct_sharded); atoms outside the range get zeros.
+#include <memory>
+#include "cell_list.cuh"
+#include "pair_delta.cuh"
+#include "workspace_cache.cuh"
+
+namespace nnpops {
+
+namespace {
+
+constexpr int kWPB = 8;
+constexpr float kTwoOverSqrtPi = 1.1283791670955126f;   // M_2_SQRTPI
+
+// the terms of one pair as computeDirect forms them (c1 = charge of the row atom, c2 = of the column atom)
+struct PairTerms {
+    float energy, dq1, dq2, dEdR;
+};
+__device__ __forceinline__ PairTerms erfc_terms(float r, float c1, float c2, float alpha, float coulomb) {
+    const float invR = 1.0f / r;
+    const float alphaR = alpha * r;
+    const float expTerm = expf(-alphaR * alphaR);
+    const float erfcTerm = erfcf(alphaR);
+    const float pref = coulomb * invR;
+    PairTerms t;
+    t.energy = pref * erfcTerm * c1 * c2;
+    t.dq1 = pref * erfcTerm * c2;
+    t.dq2 = pref * erfcTerm * c1;
+    t.dEdR = pref * c1 * c2 * (erfcTerm + alphaR * expTerm * kTwoOverSqrtPi) * invR * invR;
+    return t;
+}
+
+// is `target` in the descending row `row` of the exclusion table?
+__device__ __forceinline__ bool excluded(const int* __restrict__ exclusions, int maxExcl, int row, int target) {
+    for (int j = 0; j < maxExcl; j++) {
+        const int x = exclusions[(size_t)row * maxExcl + j];
+        if (x < target) return false;
+        if (x == target) return true;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(kWPB * 32)
+pme_direct_fused_kernel(int n, int pLo, int pHi, const float* __restrict__ boxPtr, const float4* __restrict__ sorted,
+                        const int* __restrict__ sortedOrig, const int* __restrict__ sortedCell, const Geom* __restrict__ geom,
+                        const int* __restrict__ cellStart, const float* __restrict__ pos, const float* __restrict__ charges,
+                        const int* __restrict__ exclusions, int maxExcl, float cutoff, float alpha, float coulomb,
+                        float* __restrict__ posDeriv, float* __restrict__ chargeDeriv, double* __restrict__ energyAcc) {
+    __shared__ Geom g;
+    __shared__ Box<float> bx;
+    __shared__ int queueAll[kWPB][64];
+    __shared__ double part[kWPB];
+    if (threadIdx.x == 0) {
+        g = *geom;
+        bx.periodic = boxPtr != nullptr;
+        for (int i = 0; i < 9; i++) bx.b[i] = boxPtr ? boxPtr[i] : 0.0f;
+    }
+    __syncthreads();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = pLo + blockIdx.x * kWPB + w;
+    double energy = 0.0;
+    if (p < pHi) {
+        const int op = sortedOrig[p];
+        const float4 cp = sorted[p];
+        const float pp[3] = {cp.x, cp.y, cp.z};
+        const float qp = cp.w;   // the centre's own charge (tag word)
+        const float pre2 = cutoff * cutoff * 1.0201f;
+        float fx = 0.0f, fy = 0.0f, fz = 0.0f, dq = 0.0f;
+        int* queue = queueAll[w];
+        int queued = 0;
+        auto drain = [&](int count) {   // exact test + the pair's terms for queue[0 .. count)
+            if (lane < count) {
+                const int q = queue[lane];
+                const int oq = sortedOrig[q];
+                const float4 cq = sorted[q];
+                const float pq[3] = {cq.x, cq.y, cq.z};
+                const bool centreIsRow = op > oq;
+                float dx, dy, dz;
+                const float d = centreIsRow ? pair_delta<float>(bx, pp, pq, dx, dy, dz) : pair_delta<float>(bx, pq, pp, dx, dy, dz);
+                if (d <= cutoff) {
+                    const int row = centreIsRow ? op : oq, col = centreIsRow ? oq : op;
+                    if (maxExcl == 0 || !excluded(exclusions, maxExcl, row, col)) {
+                        const PairTerms t = erfc_terms(d, centreIsRow ? qp : cq.w, centreIsRow ? cq.w : qp, alpha, coulomb);
+                        // posDeriv[row] -= dEdR * delta, posDeriv[col] += dEdR * delta
+                        const float s = centreIsRow ? -t.dEdR : t.dEdR;
+                        fx += s * dx; fy += s * dy; fz += s * dz;
+                        dq += centreIsRow ? t.dq1 : t.dq2;
+                        if (centreIsRow) energy += (double)t.energy;
+                    }
+                }
+            }
+        };
+        // runs that do not cross a periodic face need no minimum-image step in the pre-test (it would subtract zero; cell_list.cuh)
+        const bool alwaysImage = g.periodic && (g.triclinic || g.anyOutside);
+        for_each_candidate_run_w(g, cellStart, sortedCell[p], [&](int b, int e, bool wrapped) {
+            const bool image = alwaysImage || wrapped;
+            for (int q0 = b; q0 < e; q0 += 32) {
+                const int q = q0 + lane;
+                bool keep = false;
+                if (q < e && q != p) {
+                    const float4 cq = sorted[q];
+                    float ax = cq.x - cp.x, ay = cq.y - cp.y, az = cq.z - cp.z;
+                    keep = (image ? min_image_mul(g, ax, ay, az) : ax * ax + ay * ay + az * az) <= pre2;
+                }
+                const unsigned m = __ballot_sync(kFull, keep);
+                if (keep) queue[queued + __popc(m & ((1u << lane) - 1u))] = q;
+                queued += __popc(m);
+                __syncwarp();
+                if (queued >= 32) {
+                    drain(32);
+                    __syncwarp();
+                    const int carry = (lane < queued - 32) ? queue[32 + lane] : 0;
+                    __syncwarp();
+                    if (lane < queued - 32) queue[lane] = carry;
+                    queued -= 32;
+                    __syncwarp();
+                }
+            }
+        });
+        if (queued > 0) drain(queued);
+        // exclusion correction, centre-owned: the reference handles the pair (a1, a2), a2 > a1, when a2 is in a1's list
+        for (int j = lane; j < maxExcl; j += 32) {
+            const int x = exclusions[(size_t)op * maxExcl + j];
+            if (x < 0 || x == op) continue;
+            const int a1 = min(op, x), a2 = max(op, x);
+            if (x < op && !excluded(exclusions, maxExcl, a1, a2)) continue;   // the pair is only corrected when a1 lists a2
+            float dr[3];
+            for (int k = 0; k < 3; k++) dr[k] = pos[3 * (size_t)a1 + k] - pos[3 * (size_t)a2 + k];
+            const float rr = sqrtf(dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2]);
+            const float invR = 1.0f / rr;
+            const float alphaR = alpha * rr;
+            const float expTerm = expf(-alphaR * alphaR);
+            const float erfTerm = erff(alphaR);
+            const float pref = coulomb * invR;
+            const float c1 = charges[a1], c2 = charges[a2];
+            const float dEdR = pref * c1 * c2 * (erfTerm - alphaR * expTerm * kTwoOverSqrtPi) * invR * invR;
+            const float s = op == a1 ? dEdR : -dEdR;   // posDeriv[a1] += dEdR * dr, posDeriv[a2] -= dEdR * dr
+            fx += s * dr[0]; fy += s * dr[1]; fz += s * dr[2];
+            dq -= pref * erfTerm * (op == a1 ? c2 : c1);
+            if (op == a1) energy -= (double)(pref * erfTerm * c1 * c2);
+        }
+        fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz); dq = warp_sum(dq);
+        if (lane == 0) {
+            posDeriv[3 * (size_t)op] = fx; posDeriv[3 * (size_t)op + 1] = fy; posDeriv[3 * (size_t)op + 2] = fz;
+            chargeDeriv[op] = dq;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) energy += __shfl_xor_sync(kFull, energy, o);
+    if (lane == 0) part[w] = energy;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int i = 0; i < kWPB; i++) t += part[i];
+        if (t != 0.0) atomicAdd(energyAcc, t);
+    }
+}
+
+// atoms outside the shard's range of sorted positions receive zeros
+__global__ void pme_zero_outside_kernel(int n, int pLo, int pHi, const int* __restrict__ sortedOrig, float* __restrict__ posDeriv,
+                                        float* __restrict__ chargeDeriv) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n || (p >= pLo && p < pHi)) return;
+    const int o = sortedOrig[p];
+    posDeriv[3 * (size_t)o] = 0.0f; posDeriv[3 * (size_t)o + 1] = 0.0f; posDeriv[3 * (size_t)o + 2] = 0.0f;
+    chargeDeriv[o] = 0.0f;
+}
+
+__global__ void pme_publish_kernel(double* __restrict__ acc, float* __restrict__ out) { *out = (float)*acc; *acc = 0.0; }
+
+struct FusedWorkspace : WorkspaceBase {
+    CellList cells;
+    double* acc = nullptr;   // zero between calls (the publish kernel resets it)
+    ~FusedWorkspace() override {
+        cells.release();
+        cudaFree(acc);
+    }
+};
+
+WorkspaceCache<FusedWorkspace, std::pair<int, int>> g_fusedWs(16);
+
+}  // namespace
+
+// energy: device float [1]; posDeriv [n][3], chargeDeriv [n]: overwritten.  box: device float [3][3] or nullptr (non-periodic).
+void pme_direct_fused(const float* positions, const float* charges, const float* box, const int* exclusions, int numAtoms, int maxExcl,
+                      float cutoff, float alpha, float coulomb, int shardIndex, int shardCount, float* energy, float* posDeriv,
+                      float* chargeDeriv, cudaStream_t stream) {
+    NNP_REQUIRE(numAtoms > 0, "Expected the 1nd dimension size of \"positions\" to be more than 0");
+    NNP_REQUIRE(cutoff > 0, "Expected \"cutoff\" to be positive");
+    NNP_REQUIRE(shardCount >= 1 && shardIndex >= 0 && shardIndex < shardCount, "pme_direct_fused: invalid shard");
+    int dev = 0;
+    NNP_CUDA_CHECK(cudaGetDevice(&dev));
+    const int n = numAtoms;
+    const std::shared_ptr<FusedWorkspace> hold = g_fusedWs.get(std::make_pair(dev, n), stream, [n]() {
+        std::unique_ptr<FusedWorkspace> ws(new FusedWorkspace);
+        ws->cells.init(n);
+        NNP_CUDA_CHECK(cudaMalloc(&ws->acc, sizeof(double)));
+        NNP_CUDA_CHECK(cudaMemset(ws->acc, 0, sizeof(double)));
+        return ws.release();
+    });
+    FusedWorkspace& ws = *hold;
+    // the charge rides in the tag word of the sorted coordinates: one 16-byte load brings a candidate's position and charge
+    ws.cells.build<float>(positions, box, reinterpret_cast<const int*>(charges), cutoff * 1.0001f + 1e-30f, stream);
+    const int per = (n + shardCount - 1) / shardCount;
+    const int pLo = std::min(n, shardIndex * per), pHi = std::min(n, pLo + per);
+    if (shardCount > 1) {
+        pme_zero_outside_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, pLo, pHi, ws.cells.sortedOrig, posDeriv, chargeDeriv);
+        count_launch();
+    }
+    if (pHi > pLo) {
+        pme_direct_fused_kernel<<<(pHi - pLo + kWPB - 1) / kWPB, kWPB * 32, 0, stream>>>(
+            n, pLo, pHi, box, ws.cells.sorted, ws.cells.sortedOrig, ws.cells.sortedCell, ws.cells.geom, ws.cells.cellStart, positions, charges,
+            exclusions, exclusions ? maxExcl : 0, cutoff, alpha, coulomb, posDeriv, chargeDeriv, ws.acc);
+        count_launch();
+    }
+    pme_publish_kernel<<<1, 1, 0, stream>>>(ws.acc, energy);
+    count_launch();
+    NNP_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace nnpops

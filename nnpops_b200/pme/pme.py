@@ -14,6 +14,7 @@ from ..neighbors import getNeighborPairs
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 register({
     "nnpops_pme_direct": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _f, _f, _vp, _vp, _vp, _vp],
+    "nnpops_pme_direct_fused": [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp],
     "nnpops_pme_reciprocal_forward": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp],
     "nnpops_pme_reciprocal_backward": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp],
     "nnpops_pme_spread": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp],
@@ -44,6 +45,33 @@ class _Direct(torch.autograd.Function):
             check(lib.nnpops_pme_direct(ptr(pos), ptr(q), ptr(nb), ptr(d), ptr(r), ptr(ex) if ex.numel() else None, n, nb.shape[1],
                                         ex.shape[1] if ex.dim() == 2 else 0, float(alpha), float(coulomb), ptr(energy), ptr(pos_deriv),
                                         ptr(charge_deriv), current_stream(pos.device)))
+        ctx.save_for_backward(pos_deriv, charge_deriv)
+        return energy
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad):
+        pos_deriv, charge_deriv = ctx.saved_tensors
+        return pos_deriv * grad, charge_deriv * grad, None, None, None, None, None, None
+
+
+class _DirectFused(torch.autograd.Function):
+    """Direct space straight from positions (nnpops_pme_direct_fused: cell list + centre-owned erfc sum, no pair list); `shard` =
+    (index, count) restricts the centres to one slab of the cell-sorted atoms."""
+
+    @staticmethod
+    def forward(ctx, positions, charges, box_vectors, exclusions, cutoff, alpha, coulomb, shard):
+        pos, q, box = _f32(positions, "positions"), _f32(charges, "charges"), _f32(box_vectors, "box_vectors")
+        ex = exclusions.detach().to(device=pos.device, dtype=torch.int32).contiguous()
+        n = q.shape[0]
+        energy = torch.empty((), dtype=torch.float32, device=pos.device)
+        pos_deriv = torch.empty((n, 3), dtype=torch.float32, device=pos.device)
+        charge_deriv = torch.empty((n,), dtype=torch.float32, device=pos.device)
+        with torch.cuda.device(pos.device):
+            check(lib.nnpops_pme_direct_fused(ptr(pos), ptr(q), ptr(box), ptr(ex) if ex.numel() else None, n,
+                                              ex.shape[1] if ex.dim() == 2 else 0, float(cutoff), float(alpha), float(coulomb),
+                                              int(shard[0]), int(shard[1]), ptr(energy), ptr(pos_deriv), ptr(charge_deriv),
+                                              current_stream(pos.device)))
         ctx.save_for_backward(pos_deriv, charge_deriv)
         return energy
 
@@ -86,6 +114,12 @@ class _Reciprocal(torch.autograd.Function):
 def pme_direct(positions, charges, neighbors, deltas, distances, exclusions, alpha, coulomb):
     """Functional form of the op pme::pme_direct (pme.cpp:3-4)."""
     return _Direct.apply(positions, charges, neighbors, deltas, distances, exclusions, alpha, coulomb)
+
+
+def pme_direct_fused(positions, charges, box_vectors, exclusions, cutoff, alpha, coulomb, shard=(0, 1)):
+    """getNeighborPairs + pme::pme_direct in one traversal (same accepted pairs, same terms; sums in a different order).  `exclusions`
+    as PME prepares them: int32 [atoms, max_exclusions], rows sorted descending, padded with -1, symmetric."""
+    return _DirectFused.apply(positions, charges, box_vectors, exclusions, cutoff, alpha, coulomb, shard)
 
 
 def pme_reciprocal(positions, charges, box_vectors, gridx, gridy, gridz, order, alpha, coulomb, xmoduli, ymoduli, zmoduli):
@@ -270,13 +304,36 @@ class PME:
             raise ValueError('box_vectors must have shape (3, 3)')
 
     def compute_direct(self, positions: Tensor, charges: Tensor, cutoff: float, box_vectors: Tensor, max_num_pairs: int = -1):
-        """Direct-space energy (pme.py:131-165): neighbour list + erfc sum + exclusion correction."""
+        """Direct-space energy (pme.py:131-165): neighbour list + erfc sum + exclusion correction.  With the default
+        max_num_pairs = -1 (the reference then allocates N (N - 1) / 2 pair slots) nothing about the list is observable, and the sum
+        is evaluated by the fused kernel without materialising it; a positive max_num_pairs keeps the reference's two steps and
+        their capacity semantics (pairs beyond it are dropped)."""
         self._validate(positions, charges, box_vectors)
         if cutoff <= 0:
             raise ValueError('cutoff must be positive')
-        neighbors, deltas, distances, _ = getNeighborPairs(positions, cutoff, max_num_pairs, box_vectors)
         self.exclusions = self.exclusions.to(positions.device)
+        if max_num_pairs == -1:
+            return pme_direct_fused(positions, charges, box_vectors, self.exclusions, cutoff, self.alpha, self.coulomb)
+        neighbors, deltas, distances, _ = getNeighborPairs(positions, cutoff, max_num_pairs, box_vectors)
         return pme_direct(positions, charges, neighbors, deltas, distances, self.exclusions, self.alpha, self.coulomb)
+
+    def compute_direct_sharded(self, positions: Tensor, charges: Tensor, cutoff: float, box_vectors: Tensor, group=None, emulate=None):
+        """compute_direct for one box over the ranks of a torch.distributed group (PME row): positions and
+        charges are replicated, rank r evaluates the centres of slab r of the cell-sorted atoms with the fused kernel (each is a
+        complete sum over its neighbours: no halo exchange, no atomics), and the energy is summed by one scalar all-reduce.
+        Returns the total energy on every rank; a rank's autograd gradient holds the derivatives of ITS centres (zeros elsewhere),
+        so the caller sums position / charge gradients over the ranks (one all-reduce of [atoms, 4]), as for
+        pme_reciprocal_sharded.  `emulate` = (rank, world) evaluates one rank's term without a process group (tests)."""
+        self._validate(positions, charges, box_vectors)
+        if cutoff <= 0:
+            raise ValueError('cutoff must be positive')
+        self.exclusions = self.exclusions.to(positions.device)
+        if emulate is not None:
+            return pme_direct_fused(positions, charges, box_vectors, self.exclusions, cutoff, self.alpha, self.coulomb, emulate)
+        import torch.distributed as dist
+        shard = (dist.get_rank(group), dist.get_world_size(group))
+        e = pme_direct_fused(positions, charges, box_vectors, self.exclusions, cutoff, self.alpha, self.coulomb, shard)
+        return _AllReduceSum.apply(e, group)
 
     def compute_reciprocal(self, positions: Tensor, charges: Tensor, box_vectors: Tensor):
         """Reciprocal-space energy including the self term (pme.py:167-196)."""

@@ -60,6 +60,13 @@ def bench_pme():
     gbs = 24.0 * found / (ms * 1e-3) / 1e9
     emit(path="pme_direct", config="pair list of the row above (forward computes energy and both derivatives)", ms=round(ms, 4), pairs=found,
          achieved_gbs=round(gbs, 1), peak_gbs=PEAK, frac=round(gbs / PEAK, 4), bound="hbm", unit_bytes="24 B per pair")
+    from nnpops_b200.pme.pme import pme_direct_fused
+    ms = timed(lambda: pme_direct_fused(pos, q, box, excl, 0.9, 2.92, 138.935), 10, 3)
+    emit(path="pme_direct_fused (cell list + centre-owned erfc sum: replaces the two rows above)", config="200000 charges, cutoff 0.9 nm",
+         ms=round(ms, 4), pairs=found, bound="fp32 issue", flops_note="every pair evaluated from both ends: 2 x %d erfc terms + the candidate tests of 27 cells" % found)
+    for world in (2, 8):
+        ms = timed(lambda: pme_direct_fused(pos, q, box, excl, 0.9, 2.92, 138.935, (world // 2, world)), 10, 3)
+        emit(path="pme_direct_fused, one slab of %d (what one GPU of %d does)" % (world, world), ms=round(ms, 4))
     pme = PME(128, 128, 128, 5, 2.92, 138.935, torch.zeros((n, 0), dtype=torch.int32))
     pr = pos.clone().requires_grad_(True)
     qr = q.clone().requires_grad_(True)
@@ -125,5 +132,7 @@ if __name__ == "__main__":
         cpu_rows()
     else:
         bench_pme()
+        if "--pme-only" in sys.argv:
+            sys.exit(0)
         bench_cfconv(5.0)
         bench_cfconv(10.0)

@@ -204,6 +204,17 @@ def test_config5_pme_200k_vs_oracle():
     sample = rng.choice(n, 400, replace=False)
     fd0, qd0, _ = NP.pme_direct_sampled(pos, q, L, cutoff, alpha, coulomb, sample)
     errs.update(fdirect=float(np.abs(gd[sample] - fd0).max() / np.abs(fd0).max()), qdirect=float(np.abs(qd[sample] - qd0).max() / np.abs(qd0).max()))
+    # the fused direct-space kernel (no pair list; PME.compute_direct with the default max_num_pairs) on the same samples, and
+    # against the list path over all atoms
+    p.grad = None; ch.grad = None
+    ef = pme.compute_direct(p, ch, cutoff, b)
+    ef.backward()
+    gf = p.grad.cpu().numpy(); qf = ch.grad.cpu().numpy()
+    errs.update(fdirect_fused=float(np.abs(gf[sample] - fd0).max() / np.abs(fd0).max()),
+                qdirect_fused=float(np.abs(qf[sample] - qd0).max() / np.abs(qd0).max()),
+                fused_vs_list_f=rel_err(gf, gd), fused_vs_list_q=rel_err(qf, qd), fused_vs_list_e=abs(ef.item() - ed.item()) / abs(ed.item()))
+    assert errs["fdirect_fused"] < TOL and errs["qdirect_fused"] < TOL
+    assert errs["fused_vs_list_f"] < TOL and errs["fused_vs_list_q"] < TOL and errs["fused_vs_list_e"] < TOL
     print("config 5 PME 200k / 128^3 / order 5:", errs, "pairs", npairs_exact)
     assert errs["erecip"] < TOL and errs["frecip"] < TOL and errs["qrecip"] < TOL
     assert errs["fdirect"] < TOL and errs["qdirect"] < TOL

@@ -223,6 +223,69 @@ def test_pme_random_system_vs_oracle():
     assert rel_err(ch.grad.cpu().numpy(), q0d + q0r) < 1e-4
 
 
+def _random_pme_system(n, seed, with_exclusions):
+    rng = np.random.default_rng(seed)
+    box = np.array([[3.0, 0, 0], [0.4, 3.1, 0], [-0.3, 0.5, 2.9]], np.float32)
+    pos = (rng.uniform(-0.5, 1.5, (n, 3)) @ box).astype(np.float32)
+    q = rng.uniform(-0.5, 0.5, n).astype(np.float32); q -= q.mean()
+    if with_exclusions:   # "molecules" of three consecutive atoms exclude each other (symmetric, padded with -1)
+        excl = -np.ones((n, 2), np.int32)
+        for i in range(n):
+            mates = [j for j in range(3 * (i // 3), min(3 * (i // 3) + 3, n)) if j != i]
+            excl[i, :len(mates)] = mates
+    else:
+        excl = np.zeros((n, 0), np.int32)
+    return pos, q, box, excl
+
+
+@pytest.mark.parametrize("with_exclusions", [False, True])
+@pytest.mark.parametrize("n", [3, 50, 700])
+def test_pme_direct_fused_matches_list_path(n, with_exclusions):
+    """The fused direct-space kernel (cell list + centre-owned erfc sum, no pair list) against the reference's two steps
+    (getNeighborPairs + pme_direct, the path the OpenMM goldens pin): same accepted pairs and terms, sums in a different order."""
+    from nnpops_b200.pme import PME
+    pos, q, box, excl = _random_pme_system(n, 100 + n, with_exclusions)
+    pme = PME(32, 30, 36, 5, 3.2, 138.935, torch.tensor(excl))
+    b = torch.tensor(box, device="cuda")
+    out = []
+    for max_pairs in (n * n, -1):     # list path, fused path
+        p = torch.tensor(pos, device="cuda", requires_grad=True); ch = torch.tensor(q, device="cuda", requires_grad=True)
+        e = pme.compute_direct(p, ch, 1.2, b, max_num_pairs=max_pairs)
+        e.backward()
+        out.append((e.item(), p.grad.cpu().numpy(), ch.grad.cpu().numpy()))
+    (e0, g0, q0), (e1, g1, q1) = out
+    assert abs(e1 - e0) <= 2e-6 * abs(e0) + 1e-5
+    assert rel_err(g1, g0) < 5e-6 and rel_err(q1, q0) < 5e-6
+    e_ref, f_ref, q_ref = NP.pme_direct(pos, q, box, 1.2, 3.2, 138.935, excl if excl.size else None)
+    assert abs(e1 - e_ref) <= 2e-5 * abs(e_ref) + 1e-3 and rel_err(g1, f_ref) < 1e-4 and rel_err(q1, q_ref) < 1e-4
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_pme_direct_sharded_partials_sum_to_the_whole(world):
+    """One box over `world` ranks (emulated on one GPU): rank r owns slab r of the cell-sorted atoms as centres; energies and
+    derivatives of the ranks add up to the unsharded result, and every atom's derivative comes from exactly one rank."""
+    from nnpops_b200.pme import PME
+    n = 901
+    pos, q, box, excl = _random_pme_system(n, 7, True)
+    pme = PME(32, 30, 36, 5, 3.2, 138.935, torch.tensor(excl))
+    b = torch.tensor(box, device="cuda")
+    p0 = torch.tensor(pos, device="cuda", requires_grad=True); c0 = torch.tensor(q, device="cuda", requires_grad=True)
+    e0 = pme.compute_direct(p0, c0, 1.2, b)
+    e0.backward()
+    esum = 0.0
+    gp = torch.zeros_like(p0); gq = torch.zeros_like(c0); owners = torch.zeros(n, device="cuda")
+    for r in range(world):
+        p = torch.tensor(pos, device="cuda", requires_grad=True); c = torch.tensor(q, device="cuda", requires_grad=True)
+        e = pme.compute_direct_sharded(p, c, 1.2, b, emulate=(r, world))
+        e.backward()
+        esum += e.item()
+        gp += p.grad; gq += c.grad
+        owners += (p.grad.abs().sum(dim=1) > 0).float()
+    assert abs(esum - e0.item()) <= 2e-6 * abs(e0.item()) + 1e-5
+    assert torch.equal(gp, p0.grad) and torch.equal(gq, c0.grad)      # a centre's sums do not depend on the sharding
+    assert float(owners.max()) == 1.0
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_pme_reciprocal_sharded_matches_single(world):
     """Reciprocal PME with the atoms dealt to `world` ranks, emulated on one GPU: every rank spreads its block, the
