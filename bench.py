@@ -272,6 +272,14 @@ def run_ours(args):
         torch.cuda.empty_cache()
         box = measure_box(args, dist, dev, nets, rank, world, local)
 
+    # ---- the PME row of the path (BASELINE config 5), on every N: one box of 200 000 charges, direct space sharded by slabs
+    pme = None
+    if not args.no_pme:
+        try:
+            pme = measure_pme(args, dist, dev, rank, world)
+        except Exception as exc:   # noqa: BLE001  (an extra leg must not cost the bench line)
+            pme = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -371,6 +379,8 @@ def run_ours(args):
         out["box"] = box
     if md is not None:
         out["md"] = md
+    if pme is not None:
+        out["pme"] = pme
     if fp32_measured:
         out["fp32_fma_peak_measured_tflops"] = fp32_measured
     if world == 1 and not args.no_cpu_baseline:
@@ -550,6 +560,90 @@ def measure_box(args, dist, dev, nets, rank, world, local):
             "local_model_note": "the brick-local model alone, launched kernel by kernel without the halo phases and the all-reduce (MAX over ranks): "
                                 "the difference to ms_per_step is what the exchange and the collectives cost -- or, when negative, what the CUDA graph saves",
             "energy": float(e.cpu()[0])}
+
+
+def measure_pme(args, dist, dev, rank, world):
+    """BASELINE config 5 as an extra key of the bench line: PME energy + dE/dx + dE/dq of ONE periodic box of 200 000 point charges
+    (cubic, 128^3 grid, order 5, alpha 2.92 / nm, direct cutoff 0.9 nm) through nnpops_b200.pme.PME, strong scaling over the ranks.
+    Direct space: the fused cell-list kernel, rank r owning slab r of the cell-sorted atoms as centres (no halo, no atomics), the
+    per-atom derivatives assembled by ONE all-reduce of [atoms, 4] floats + one scalar all-reduce of the energy (NCCL).  Reciprocal
+    space: replicated on every rank (the 128^3 grid is too small to pay for a grid exchange: DESIGN.md section 7).  Device-event
+    time, MAX over ranks.  At N = 1 the reference's two-step direct path (getNeighborPairs + pme_direct) is timed beside it."""
+    import numpy as np
+    import torch
+    from systems import lattice, cubic_box
+    from nnpops_b200.neighbors import getNeighborPairs
+    from nnpops_b200.pme import PME
+    from nnpops_b200.pme.pme import pme_direct
+    n, cutoff, alpha, coulomb = 200000, 0.9, 2.92, 138.935
+    pos_np, L = lattice(n, 0.2154, 0.3, 5005)
+    rng = np.random.default_rng(5005)
+    q_np = rng.uniform(-0.5, 0.5, n).astype(np.float32)
+    q_np -= q_np.mean(dtype=np.float64).astype(np.float32)
+    pos = torch.tensor(pos_np, device=dev, requires_grad=True)
+    q = torch.tensor(q_np, device=dev, requires_grad=True)
+    box = torch.tensor(cubic_box(L), device=dev)
+    pme = PME(128, 128, 128, 5, alpha, coulomb, torch.zeros((n, 0), dtype=torch.int32))
+    packed = torch.zeros((n, 4), dtype=torch.float32, device=dev)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def direct():
+        pos.grad = None; q.grad = None
+        e = pme.compute_direct_sharded(pos, q, cutoff, box) if world > 1 else pme.compute_direct(pos, q, cutoff, box)
+        e.backward()
+        if world > 1:   # every rank holds the derivatives of its own centres: assemble them
+            packed[:, :3] = pos.grad; packed[:, 3] = q.grad
+            dist.all_reduce(packed)
+        return e
+
+    def recip():
+        pos.grad = None; q.grad = None
+        e = pme.compute_reciprocal(pos, q, box)
+        e.backward()
+        return e
+
+    def timed(fn, iters):
+        for _ in range(3):
+            fn()
+        sync_all()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(iters):
+            out = fn()
+        t1.record()
+        sync_all()
+        return max_over_ranks(t0.elapsed_time(t1), dist, dev) / iters, out
+
+    iters = 10
+    d_ms, e_d = timed(direct, iters)
+    r_ms, e_r = timed(recip, iters)
+    t_ms, _ = timed(lambda: (direct(), recip()), iters)
+    out = {"workload": "BASELINE configs[4]: PME, one periodic box of 200000 charges, 128^3 grid, order 5, direct cutoff 0.9 nm; energy + dE/dx + dE/dq",
+           "value": round(1e3 / t_ms, 2), "unit": "evals/s", "ms_per_step": round(t_ms, 4), "scaling": "strong",
+           "direct_ms": round(d_ms, 4), "reciprocal_ms": round(r_ms, 4),
+           "direct": "fused cell-list kernel (no pair list, centre-owned, no atomics)" + (
+               "; rank r owns slab r of the cell-sorted atoms; ncclAllReduce of [200000, 4] floats (3.2 MB) + 1 scalar all-reduce per step" if world > 1 else ""),
+           "reciprocal": "replicated on every rank" if world > 1 else "spread, rFFT (cuFFT), convolution, irFFT, gather",
+           "energy_direct": float(e_d.detach().cpu()), "energy_reciprocal": float(e_r.detach().cpu())}
+    if world == 1:
+        cap = 33_000_000
+        pd, qd = pos.detach(), q.detach()
+        excl = torch.zeros((n, 0), dtype=torch.int32, device=dev)
+        keep = {}
+
+        def nb():
+            keep["r"] = getNeighborPairs(pd, cutoff, cap, box)
+        nb_ms, _ = timed(nb, 5)
+        nbrs, deltas, dists, found = keep["r"]
+        ld_ms, e_l = timed(lambda: pme_direct(pd, qd, nbrs, deltas, dists, excl, alpha, coulomb), 5)
+        out["reference_two_step_direct"] = {"getNeighborPairs_ms": round(nb_ms, 4), "pme_direct_ms": round(ld_ms, 4), "pairs": int(found.item()),
+                                            "energy_direct": float(e_l.cpu())}
+    return out
 
 
 def run_box(args):
@@ -744,6 +838,7 @@ def main():
     ap.add_argument("--sustain", type=float, default=3.0, help="seconds of the extra sustained leg (0 = skip)")
     ap.add_argument("--md-steps", type=int, default=64, help="steps of the extra MD-like leg with a Verlet skin (0 = skip; N = 1 only)")
     ap.add_argument("--no-graph", action="store_true", help="box mode: launch the step kernel by kernel instead of replaying its CUDA graph")
+    ap.add_argument("--no-pme", action="store_true", help="skip the extra PME leg (BASELINE config 5, 200 000 charges)")
     ap.add_argument("--no-box", action="store_true", help="N > 1: skip the extra one-box strong-scaling measurement")
     ap.add_argument("--no-model-check", action="store_true", help="--impl reference: skip the one real full-size AEV evaluation (~80 s)")
     ap.add_argument("--mode", default="conformers", choices=["conformers", "box"],

@@ -59,7 +59,8 @@ pme_direct_fused_kernel(int n, int pLo, int pHi, const float* __restrict__ boxPt
                         float* __restrict__ posDeriv, float* __restrict__ chargeDeriv, double* __restrict__ energyAcc) {
     __shared__ Geom g;
     __shared__ Box<float> bx;
-    __shared__ int queueAll[kWPB][64];
+    __shared__ float4 queueAll[kWPB][64];
+    __shared__ int queueIdxAll[kWPB][64];
     __shared__ double part[kWPB];
     if (threadIdx.x == 0) {
         g = *geom;
@@ -73,56 +74,70 @@ pme_direct_fused_kernel(int n, int pLo, int pHi, const float* __restrict__ boxPt
     if (p < pHi) {
         const int op = sortedOrig[p];
         const float4 cp = sorted[p];
-        const float pp[3] = {cp.x, cp.y, cp.z};
         const float qp = cp.w;   // the centre's own charge (tag word)
         const float pre2 = cutoff * cutoff * 1.0201f;
+        // |component| of a minimum-image displacement at which the multiply-by-reciprocal image used below could pick another image
+        // than the reference's division (a rounding tie at half a box edge): such a survivor is re-derived with the reference form
+        const float tieX = 0.499f * bx.b[0], tieY = 0.499f * bx.b[4], tieZ = 0.499f * bx.b[8];
         float fx = 0.0f, fy = 0.0f, fz = 0.0f, dq = 0.0f;
-        int* queue = queueAll[w];
+        float4* queue = queueAll[w];      // {delta = candidate - centre (minimum image), charge}
+        int* queueIdx = queueIdxAll[w];   // sorted position of the candidate
         int queued = 0;
         auto drain = [&](int count) {   // exact test + the pair's terms for queue[0 .. count)
             if (lane < count) {
-                const int q = queue[lane];
-                const int oq = sortedOrig[q];
-                const float4 cq = sorted[q];
-                const float pq[3] = {cq.x, cq.y, cq.z};
-                const bool centreIsRow = op > oq;
-                float dx, dy, dz;
-                const float d = centreIsRow ? pair_delta<float>(bx, pp, pq, dx, dy, dz) : pair_delta<float>(bx, pq, pp, dx, dy, dz);
+                float4 e = queue[lane];
+                const int q = queueIdx[lane];
+                if (bx.periodic && (fabsf(e.x) >= tieX || fabsf(e.y) >= tieY || fabsf(e.z) >= tieZ)) {
+                    const float4 cq = sorted[q];
+                    const float pq[3] = {cq.x, cq.y, cq.z}, pp[3] = {cp.x, cp.y, cp.z};
+                    pair_delta<float>(bx, pq, pp, e.x, e.y, e.z);
+                }
+                // the reference's distance: sqrt of the sum of squares, every step rounded (getNeighborPairsCPU.cpp:71-73)
+                const float d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(e.x, e.x), __fmul_rn(e.y, e.y)), __fmul_rn(e.z, e.z)));
                 if (d <= cutoff) {
-                    const int row = centreIsRow ? op : oq, col = centreIsRow ? oq : op;
-                    if (maxExcl == 0 || !excluded(exclusions, maxExcl, row, col)) {
-                        const PairTerms t = erfc_terms(d, centreIsRow ? qp : cq.w, centreIsRow ? cq.w : qp, alpha, coulomb);
-                        // posDeriv[row] -= dEdR * delta, posDeriv[col] += dEdR * delta
-                        const float s = centreIsRow ? -t.dEdR : t.dEdR;
-                        fx += s * dx; fy += s * dy; fz += s * dz;
-                        dq += centreIsRow ? t.dq1 : t.dq2;
-                        if (centreIsRow) energy += (double)t.energy;
+                    bool include = true;
+                    if (maxExcl > 0) {   // computeDirect scans the row atom's list (the larger index) for the column atom
+                        const int oq = sortedOrig[q];
+                        include = !excluded(exclusions, maxExcl, max(op, oq), min(op, oq));
+                    }
+                    if (include) {
+                        const PairTerms t = erfc_terms(d, qp, e.w, alpha, coulomb);
+                        // posDeriv[row] -= dEdR (pos[row] - pos[col]), posDeriv[col] += the same: for the centre, either way, dEdR * (other - centre)
+                        fx += t.dEdR * e.x; fy += t.dEdR * e.y; fz += t.dEdR * e.z;
+                        dq += t.dq1;
+                        if (q < p) energy += (double)t.energy;   // every pair is seen from both ends: counted once
                     }
                 }
             }
         };
-        // runs that do not cross a periodic face need no minimum-image step in the pre-test (it would subtract zero; cell_list.cuh)
+        // runs that do not cross a periodic face need no minimum-image step (it would subtract zero; cell_list.cuh)
         const bool alwaysImage = g.periodic && (g.triclinic || g.anyOutside);
         for_each_candidate_run_w(g, cellStart, sortedCell[p], [&](int b, int e, bool wrapped) {
             const bool image = alwaysImage || wrapped;
+            float4 cq = (b + lane < e) ? sorted[b + lane] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             for (int q0 = b; q0 < e; q0 += 32) {
                 const int q = q0 + lane;
+                const float4 cur = cq;
+                if (q + 32 < e) cq = sorted[q + 32];   // next sweep's coordinates are in flight while this one is tested
                 bool keep = false;
-                if (q < e && q != p) {
-                    const float4 cq = sorted[q];
-                    float ax = cq.x - cp.x, ay = cq.y - cp.y, az = cq.z - cp.z;
-                    keep = (image ? min_image_mul(g, ax, ay, az) : ax * ax + ay * ay + az * az) <= pre2;
-                }
+                float ax = cur.x - cp.x, ay = cur.y - cp.y, az = cur.z - cp.z;
+                if (q < e && q != p) keep = (image ? min_image_mul(g, ax, ay, az) : ax * ax + ay * ay + az * az) <= pre2;
                 const unsigned m = __ballot_sync(kFull, keep);
-                if (keep) queue[queued + __popc(m & ((1u << lane) - 1u))] = q;
+                if (keep) {
+                    const int slot = queued + __popc(m & ((1u << lane) - 1u));
+                    queue[slot] = make_float4(ax, ay, az, cur.w);
+                    queueIdx[slot] = q;
+                }
                 queued += __popc(m);
                 __syncwarp();
                 if (queued >= 32) {
                     drain(32);
                     __syncwarp();
-                    const int carry = (lane < queued - 32) ? queue[32 + lane] : 0;
+                    float4 carry = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    int carryIdx = 0;
+                    if (lane < queued - 32) { carry = queue[32 + lane]; carryIdx = queueIdx[32 + lane]; }
                     __syncwarp();
-                    if (lane < queued - 32) queue[lane] = carry;
+                    if (lane < queued - 32) { queue[lane] = carry; queueIdx[lane] = carryIdx; }
                     queued -= 32;
                     __syncwarp();
                 }
