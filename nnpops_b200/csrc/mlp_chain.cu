@@ -191,6 +191,12 @@ __device__ __forceinline__ void epi_chunk(const ChainParams& P, const EpiCtx& x,
     mbar_wait(accFullBar, fullPhase);
     tc_fence_after();
     if (x.trace >= 0 && lane == 0) TRACE(x.trace, 0x700 | TYPE << 4 | x.c);
+#ifdef CHAIN_EXP_EPI_NONE
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(accEmptyBar);
+    return;
+#endif
     u64 vv[16];
     const u64 loInv2 = pk2(kLoInv, kLoInv);
 #pragma unroll

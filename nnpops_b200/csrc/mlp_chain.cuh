@@ -34,4 +34,22 @@ private:
     Impl* impl_;
 };
 
+// Variant of the same kernel (mlp_chain2.cu, behind NNPOPS_CHAIN_V2=1): one accumulator per output column (the hi.lo cross terms are
+// folded in by the tensor core's input scaling, tcgen05.mma scale-input-d), chunks of 128 output columns, one in-order MMA issuer, all
+// epilogue warps on every chunk.  Same interface, limits and results; measured slower on B200 (0.65 vs 0.54 ms on the bench box: 1.8 x
+// the mbarrier waits per chain on the issuing thread), kept as the starting point for a cta_group::2 version.
+class MlpChain2 {
+public:
+    static bool eligible(int numSpecies, const MlpChain::SpeciesDesc* sp, int featureStride);
+    MlpChain2(int ensemble, int numSpecies, const MlpChain::SpeciesDesc* sp, const __half* featHi, const __half* featLo, int featureStride);
+    ~MlpChain2();
+    MlpChain2(const MlpChain2&) = delete;
+    MlpChain2& operator=(const MlpChain2&) = delete;
+    void launch(double* energyAcc, float* dX, float seedScale, float outScale, cudaStream_t stream);
+
+private:
+    struct Impl;
+    Impl* impl_;
+};
+
 }  // namespace nnpops

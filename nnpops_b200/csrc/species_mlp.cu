@@ -318,7 +318,10 @@ void SpeciesMlp::setImpl(MlpImpl impl) {
         }
         bool padOk = true;   // the chain reads featureStride columns of X: they must all be real (padded) input columns
         for (int s = 0; s < S_; s++) padOk = padOk && layers_[s][0].inP == featStride_;
-        if (padOk && MlpChain::eligible(S_, sd.data(), featStride_))
+        // NNPOPS_CHAIN_V2=1: the single-accumulator variant (mlp_chain2.cu; correct, measured slower: DESIGN.md section 4)
+        if (padOk && std::getenv("NNPOPS_CHAIN_V2") != nullptr && MlpChain2::eligible(S_, sd.data(), featStride_))
+            chain2_.reset(new MlpChain2(M_, S_, sd.data(), featHi_, featLo_, featStride_));
+        else if (padOk && MlpChain::eligible(S_, sd.data(), featStride_))
             chain_.reset(new MlpChain(M_, S_, sd.data(), featHi_, featLo_, featStride_));
     }
     hW_.clear();
@@ -326,9 +329,10 @@ void SpeciesMlp::setImpl(MlpImpl impl) {
 }
 
 void SpeciesMlp::forwardBackward(float* energy, float* featureGrad, cudaStream_t stream) {
-    NNP_REQUIRE(chain_ != nullptr, "SpeciesMlp::forwardBackward needs the fused chain kernel");
+    NNP_REQUIRE(fused(), "SpeciesMlp::forwardBackward needs the fused chain kernel");
     NNP_CUDA_CHECK(cudaMemsetAsync(energyAcc_, 0, sizeof(double), stream));
-    chain_->launch(energyAcc_, featureGrad, kGradScale / M_, 1.0f / kGradScale, stream);
+    if (chain2_) chain2_->launch(energyAcc_, featureGrad, kGradScale / M_, 1.0f / kGradScale, stream);
+    else chain_->launch(energyAcc_, featureGrad, kGradScale / M_, 1.0f / kGradScale, stream);
     finish_energy_kernel<<<1, 1, 0, stream>>>(energyAcc_, energyBias_, M_, energy);
     count_launch();
     NNP_CUDA_CHECK(cudaGetLastError());

@@ -40,7 +40,7 @@ public:
     void backward(float* featureGrad, cudaStream_t stream);
     // Tensor-core path with the fused layer-chain kernel (mlp_chain.cu): energy and dE/dfeatures of one evaluation in one launch.
     // fused() says whether the network shape allows it (else call forward + backward); NNPOPS_NO_CHAIN=1 switches it off.
-    bool fused() const { return chain_ != nullptr; }
+    bool fused() const { return chain_ != nullptr || chain2_ != nullptr; }
     void forwardBackward(float* energy, float* featureGrad, cudaStream_t stream);
 
     // tensor-core path: the feature matrix as fp16 hi/lo pairs [rows][featureStride]; the AEV kernels write it directly and
@@ -73,7 +73,8 @@ private:
     void backwardTc(float* featureGrad, cudaStream_t stream);
     void forwardRowsTc(int s, int r0, int nr, int w0, cudaStream_t stream);
     void backwardRowsTc(int s, int r0, int nr, int w0, float* featureGrad, cudaStream_t stream);
-    std::unique_ptr<MlpChain> chain_;
+    std::unique_ptr<MlpChain> chain_;     // the fused layer-chain kernel (default)
+    std::unique_ptr<MlpChain2> chain2_;   // its single-accumulator variant (NNPOPS_CHAIN_V2=1)
     std::vector<std::vector<std::vector<float>>> hW_;   // host copy of the padded weights [S][L] until setImpl has built its operands
     double* energyAcc_ = nullptr;
     double energyBias_ = 0;      // sum over atoms and members of the last-layer bias

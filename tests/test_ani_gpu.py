@@ -324,9 +324,11 @@ def test_full_size_box_rows_match_oracle_on_local_clusters():
     assert worst < 2e-5   # the cluster uses re-centred coordinates, so deltas differ from the box arithmetic by fp32 round-off
 
 
+@pytest.mark.parametrize("variant", ["default", "single_accumulator"])
 @pytest.mark.parametrize("hidden,ensemble", [(ANI2X_HIDDEN, 8), ([(64, 64, 32)] * 7, 2), ([(96, 32, 64)] * 7, 3), ([(256, 192, 160)] * 7, 1)])
-def test_fused_chain_kernel_matches_per_layer_path(hidden, ensemble, monkeypatch):
-    """The one-kernel layer chain (csrc/mlp_chain.cu: activations in tensor / shared memory, two MMA issuers) against the per-layer
+def test_fused_chain_kernel_matches_per_layer_path(hidden, ensemble, variant, monkeypatch):
+    """The one-kernel layer chain (csrc/mlp_chain.cu: activations in tensor / shared memory, two MMA issuers; variant
+    "single_accumulator": csrc/mlp_chain2.cu behind NNPOPS_CHAIN_V2=1, cross terms folded in by scale-input-d) against the per-layer
     tcgen05 GEMMs it replaces (NNPOPS_NO_CHAIN=1), on a water box with several 128-atom tiles per species: widths that give one,
     two, three and four 64-column chunks per layer and odd/even chunk counts per chain; repeated evaluations must agree too (the
     barrier phases of the persistent kernel carry over from tile to tile and member to member)."""
@@ -340,6 +342,8 @@ def test_fused_chain_kernel_matches_per_layer_path(hidden, ensemble, monkeypatch
     monkeypatch.setenv("NNPOPS_NO_CHAIN", "1")
     e0, g0 = FusedANI(*args).energy_and_gradient(p, b)
     monkeypatch.delenv("NNPOPS_NO_CHAIN")
+    if variant == "single_accumulator":
+        monkeypatch.setenv("NNPOPS_CHAIN_V2", "1")
     m = FusedANI(*args)
     e0 = float(e0.cpu()[0]); g0 = g0.cpu().numpy()
     for rep in range(6):
