@@ -51,7 +51,10 @@ __device__ __forceinline__ bool excluded(const int* __restrict__ exclusions, int
     return false;
 }
 
-__global__ void __launch_bounds__(kWPB * 32)
+#ifndef PME_MIN_BLOCKS
+#define PME_MIN_BLOCKS 3   // 75 registers, no spills (ptxas settles on 64 registers with spills when left alone)
+#endif
+__global__ void __launch_bounds__(kWPB * 32, PME_MIN_BLOCKS)
 pme_direct_fused_kernel(int n, int pLo, int pHi, const float* __restrict__ boxPtr, const float4* __restrict__ sorted,
                         const int* __restrict__ sortedOrig, const int* __restrict__ sortedCell, const Geom* __restrict__ geom,
                         const int* __restrict__ cellStart, const float* __restrict__ pos, const float* __restrict__ charges,
@@ -59,8 +62,8 @@ pme_direct_fused_kernel(int n, int pLo, int pHi, const float* __restrict__ boxPt
                         float* __restrict__ posDeriv, float* __restrict__ chargeDeriv, double* __restrict__ energyAcc) {
     __shared__ Geom g;
     __shared__ Box<float> bx;
-    __shared__ float4 queueAll[kWPB][64];
-    __shared__ int queueIdxAll[kWPB][64];
+    __shared__ float4 queueAll[kWPB][96];   // up to 31 waiting survivors + 64 new ones
+    __shared__ int queueIdxAll[kWPB][96];
     __shared__ double part[kWPB];
     if (threadIdx.x == 0) {
         g = *geom;
@@ -112,35 +115,52 @@ pme_direct_fused_kernel(int n, int pLo, int pHi, const float* __restrict__ boxPt
         };
         // runs that do not cross a periodic face need no minimum-image step (it would subtract zero; cell_list.cuh)
         const bool alwaysImage = g.periodic && (g.triclinic || g.anyOutside);
+        auto flush = [&]() {   // a full batch of survivors: evaluate it and move the rest of the queue down
+            drain(32);
+            __syncwarp();
+            float4 carry0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), carry1 = carry0;   // up to 63 entries stay behind
+            int carryIdx0 = 0, carryIdx1 = 0;
+            if (lane < queued - 32) { carry0 = queue[32 + lane]; carryIdx0 = queueIdx[32 + lane]; }
+            if (lane < queued - 64) { carry1 = queue[64 + lane]; carryIdx1 = queueIdx[64 + lane]; }
+            __syncwarp();
+            if (lane < queued - 32) { queue[lane] = carry0; queueIdx[lane] = carryIdx0; }
+            if (lane < queued - 64) { queue[32 + lane] = carry1; queueIdx[32 + lane] = carryIdx1; }
+            queued -= 32;
+            __syncwarp();
+        };
         for_each_candidate_run_w(g, cellStart, sortedCell[p], [&](int b, int e, bool wrapped) {
             const bool image = alwaysImage || wrapped;
-            float4 cq = (b + lane < e) ? sorted[b + lane] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            for (int q0 = b; q0 < e; q0 += 32) {
-                const int q = q0 + lane;
-                const float4 cur = cq;
-                if (q + 32 < e) cq = sorted[q + 32];   // next sweep's coordinates are in flight while this one is tested
-                bool keep = false;
-                float ax = cur.x - cp.x, ay = cur.y - cp.y, az = cur.z - cp.z;
-                if (q < e && q != p) keep = (image ? min_image_mul(g, ax, ay, az) : ax * ax + ay * ay + az * az) <= pre2;
-                const unsigned m = __ballot_sync(kFull, keep);
-                if (keep) {
-                    const int slot = queued + __popc(m & ((1u << lane) - 1u));
-                    queue[slot] = make_float4(ax, ay, az, cur.w);
-                    queueIdx[slot] = q;
+            // two sweeps of 32 candidates per iteration: two independent loads and tests in flight per lane
+            for (int q0 = b; q0 < e; q0 += 64) {
+                const int qa = q0 + lane, qb = qa + 32;
+                const float4 ca = qa < e ? sorted[qa] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                const float4 cb = qb < e ? sorted[qb] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                float ax = ca.x - cp.x, ay = ca.y - cp.y, az = ca.z - cp.z;
+                float bx2 = cb.x - cp.x, by2 = cb.y - cp.y, bz2 = cb.z - cp.z;
+                bool keepA = false, keepB = false;
+                if (image) {
+                    const float ra = min_image_mul(g, ax, ay, az), rb = min_image_mul(g, bx2, by2, bz2);
+                    keepA = qa < e && qa != p && ra <= pre2;
+                    keepB = qb < e && qb != p && rb <= pre2;
+                } else {
+                    keepA = qa < e && qa != p && ax * ax + ay * ay + az * az <= pre2;
+                    keepB = qb < e && qb != p && bx2 * bx2 + by2 * by2 + bz2 * bz2 <= pre2;
                 }
-                queued += __popc(m);
+                const unsigned ma = __ballot_sync(kFull, keepA), mb = __ballot_sync(kFull, keepB);
+                const unsigned below = (1u << lane) - 1u;
+                if (keepA) {
+                    const int slot = queued + __popc(ma & below);
+                    queue[slot] = make_float4(ax, ay, az, ca.w);
+                    queueIdx[slot] = qa;
+                }
+                if (keepB) {
+                    const int slot = queued + __popc(ma) + __popc(mb & below);
+                    queue[slot] = make_float4(bx2, by2, bz2, cb.w);
+                    queueIdx[slot] = qb;
+                }
+                queued += __popc(ma) + __popc(mb);
                 __syncwarp();
-                if (queued >= 32) {
-                    drain(32);
-                    __syncwarp();
-                    float4 carry = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    int carryIdx = 0;
-                    if (lane < queued - 32) { carry = queue[32 + lane]; carryIdx = queueIdx[32 + lane]; }
-                    __syncwarp();
-                    if (lane < queued - 32) { queue[lane] = carry; queueIdx[lane] = carryIdx; }
-                    queued -= 32;
-                    __syncwarp();
-                }
+                while (queued >= 32) flush();
             }
         });
         if (queued > 0) drain(queued);
