@@ -467,9 +467,77 @@ def gpu_comparator(local):
                            "own CPU implementation; ours agrees with the CPU reference to < 1e-5 (tests/test_reference_cuda_gpu.py) -- the timing "
                            "comparison stands, the result comparison does not")
         res.append(run)
-    return {"what": "AEV forward + backward, reference CudaANISymmetryFunctions (unmodified source, nvcc -gencode arch=compute_100a,code=sm_100a) "
-                    "vs this library, same GPU, same inputs, device-resident, CUDA events (the reference launches on the legacy default "
-                    "stream, ours on torch's current stream)", "runs": res}
+    out = {"what": "AEV forward + backward, reference CudaANISymmetryFunctions (unmodified source, nvcc -gencode arch=compute_100a,code=sm_100a) "
+                   "vs this library, same GPU, same inputs, device-resident, CUDA events (the reference launches on the legacy default "
+                   "stream, ours on torch's current stream)", "runs": res}
+    try:
+        out["cfconv"] = cfconv_comparator(dev)
+    except Exception as exc:   # noqa: BLE001
+        out["cfconv"] = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
+    return out
+
+
+def cfconv_comparator(dev):
+    """SchNet CFConv on the reference's own CUDA classes (CudaCFConvNeighbors + CudaCFConv, unmodified, sm_100a) next to ours: neighbour
+    build + one layer forward + backprop on a 10 000-atom periodic box (width 128, 50 Gaussians, cutoff 5 A; the reference's N x N pair
+    table in managed memory stops at about 16 000 atoms -- BASELINE config 4's 100 000 atoms are out of its reach)."""
+    import numpy as np
+    import torch
+    import oracle_lib as O
+    from systems import cubic_box, lattice
+    from nnpops_b200.CFConv import CFConv
+    from nnpops_b200.CFConvNeighbors import CFConvNeighbors
+    l = O.ref_cuda_lib()
+    if l is None or not hasattr(l, "refcuda_cfconv_create"):
+        return {"unavailable": "oracle/_ref/libnnpops_ref_cuda.so has no CFConv classes (needs /root/reference at build time)"}
+    n, W, Gn, cutoff, sigma = 10000, 128, 50, 5.0, 0.2
+    rng = np.random.default_rng(17)
+    pos, edge = lattice(n, 2.154, 0.3, 4004)
+    w1 = rng.normal(0, 0.1, (W, Gn)).astype(np.float32); b1 = rng.normal(0, 0.1, W).astype(np.float32)
+    w2 = rng.normal(0, 0.1, (W, W)).astype(np.float32); b2 = rng.normal(0, 0.1, W).astype(np.float32)
+    x = torch.tensor(rng.standard_normal((n, W)).astype(np.float32), device=dev)
+    go = torch.tensor(rng.standard_normal((n, W)).astype(np.float32), device=dev)
+    p = torch.tensor(pos, device=dev); b = torch.tensor(cubic_box(edge), device=dev)
+    ref = O.RefCudaCFConv(n, W, Gn, cutoff, True, sigma, "ssp", w1, b1, w2, b2)
+    y0, ig0, pg0 = torch.empty_like(x), torch.empty_like(x), torch.empty_like(p)
+
+    def run_ref():
+        ref.build(p, b)
+        ref.compute(p, b, x, y0)
+        ref.backprop(p, b, x, go, ig0, pg0)
+
+    nb = CFConvNeighbors(cutoff)
+    conv = CFConv(sigma, "ssp", torch.tensor(w1.reshape(Gn, W)), torch.tensor(b1), torch.tensor(w2), torch.tensor(b2))
+    pr = p.clone().requires_grad_(True); xr = x.clone().requires_grad_(True)
+    keep = {}
+
+    def run_ours():
+        pr.grad = None; xr.grad = None
+        nb.build(pr, b)
+        keep["y"] = conv(nb, pr, xr)
+        keep["y"].backward(go)
+
+    times = {}
+    for key, fn, reps in (("reference_cuda_ms", run_ref, 3), ("ours_ms", run_ours, 10)):
+        fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        times[key] = e0.elapsed_time(e1) / reps
+    res = {"what": "SchNet CFConv: neighbour build + one layer forward + backprop, reference CudaCFConvNeighbors + CudaCFConv (unmodified source, "
+                   "sm_100a) vs this library through its torch module (autograd included), same GPU, same inputs",
+           "system": "10000-atom periodic box, width 128, 50 Gaussians, cutoff 5 A", "pairs": ref.num_pairs(), "pairs_ours": nb.num_pairs(),
+           "reference_cuda_ms": round(times["reference_cuda_ms"], 4), "ours_ms": round(times["ours_ms"], 4),
+           "speedup": round(times["reference_cuda_ms"] / times["ours_ms"], 2),
+           "output_rel_diff": float((keep["y"].detach() - y0).abs().max() / y0.abs().max()),
+           "input_grad_rel_diff": float((xr.grad - ig0).abs().max() / ig0.abs().max()),
+           "position_grad_rel_diff": float((pr.grad - pg0).abs().max() / pg0.abs().max())}
+    ref.close()
+    return res
 
 
 def forces_check(nets, mlp_impl, local, n_atoms=6000):

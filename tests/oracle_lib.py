@@ -57,6 +57,17 @@ def ref_cuda_lib():
             l.refcuda_ani_destroy.argtypes = [C.c_void_p]
             l.refcuda_ani_forward.argtypes = [C.c_void_p] * 5
             l.refcuda_ani_backward.argtypes = [C.c_void_p] * 4
+            if hasattr(l, "refcuda_cfconv_create"):
+                l.refcuda_cfconv_neighbors_create.restype = C.c_void_p
+                l.refcuda_cfconv_neighbors_create.argtypes = [C.c_int, C.c_float, C.c_int]
+                l.refcuda_cfconv_neighbors_destroy.argtypes = [C.c_void_p]
+                l.refcuda_cfconv_neighbors_build.argtypes = [C.c_void_p] * 3
+                l.refcuda_cfconv_neighbors_count.argtypes = [C.c_void_p]
+                l.refcuda_cfconv_create.restype = C.c_void_p
+                l.refcuda_cfconv_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int] + [C.c_void_p] * 4
+                l.refcuda_cfconv_destroy.argtypes = [C.c_void_p]
+                l.refcuda_cfconv_compute.argtypes = [C.c_void_p] * 6
+                l.refcuda_cfconv_backprop.argtypes = [C.c_void_p] * 8
         _libs["refcuda"] = l
     return _libs["refcuda"]
 
@@ -94,6 +105,47 @@ class RefCudaANI:
         if self.h:
             self.l.refcuda_ani_destroy(self.h)
             self.h = None
+
+
+class RefCudaCFConv:
+    """The reference's CudaCFConvNeighbors + CudaCFConv on torch CUDA tensors (device pointers; src/schnet/CudaCFConv.h:37-190).
+    w1: [width][numGaussians] in the reference's storage order, w2: [width][width] (host arrays)."""
+
+    def __init__(self, n, width, n_gaussians, cutoff, periodic, gaussian_width, activation, w1, b1, w2, b2):
+        self.l = ref_cuda_lib()
+        self.n, self.w = n, width
+        self.nb = self.l.refcuda_cfconv_neighbors_create(n, cutoff, int(periodic))
+        arrs = [np.ascontiguousarray(a, np.float32) for a in (w1, b1, w2, b2)]
+        self.h = self.l.refcuda_cfconv_create(n, width, n_gaussians, cutoff, int(periodic), gaussian_width, 0 if activation == "ssp" else 1,
+                                              *[a.ctypes.data for a in arrs])
+        if not self.nb or not self.h:
+            raise RuntimeError("reference CudaCFConv could not be constructed")
+
+    def build(self, pos, box):
+        assert self.l.refcuda_cfconv_neighbors_build(self.nb, pos.data_ptr(), box.data_ptr() if box is not None else None) == 0
+
+    def num_pairs(self):
+        return self.l.refcuda_cfconv_neighbors_count(self.nb)
+
+    def compute(self, pos, box, x, out=None):
+        import torch
+        out = torch.empty_like(x) if out is None else out
+        assert self.l.refcuda_cfconv_compute(self.h, self.nb, pos.data_ptr(), box.data_ptr() if box is not None else None, x.data_ptr(), out.data_ptr()) == 0
+        return out
+
+    def backprop(self, pos, box, x, out_grad, in_grad=None, pos_grad=None):
+        import torch
+        in_grad = torch.empty_like(x) if in_grad is None else in_grad
+        pos_grad = torch.empty_like(pos) if pos_grad is None else pos_grad
+        assert self.l.refcuda_cfconv_backprop(self.h, self.nb, pos.data_ptr(), box.data_ptr() if box is not None else None, x.data_ptr(),
+                                              out_grad.data_ptr(), in_grad.data_ptr(), pos_grad.data_ptr()) == 0
+        return in_grad, pos_grad
+
+    def close(self):
+        if self.h:
+            self.l.refcuda_cfconv_destroy(self.h)
+            self.l.refcuda_cfconv_neighbors_destroy(self.nb)
+            self.h = self.nb = None
 
 
 def _opt(a, dtype):

@@ -218,9 +218,11 @@ def test_pme_random_system_vs_oracle():
     e.backward()
     e0d, f0d, q0d = NP.pme_direct(pos, q, box, 1.2, 3.2, 138.935)
     e0r, f0r, q0r = NP.pme_reciprocal(pos, q, box, (32, 30, 36), 4, 3.2, 138.935)
-    assert abs(e.item() - (e0d + e0r)) < 2e-5 * abs(e0d + e0r) + 1e-2
-    assert rel_err(p.grad.cpu().numpy(), f0d + f0r) < 1e-4
-    assert rel_err(ch.grad.cpu().numpy(), q0d + q0r) < 1e-4
+    errs = dict(energy=abs(e.item() - (e0d + e0r)) / abs(e0d + e0r), forces=rel_err(p.grad.cpu().numpy(), f0d + f0r),
+                dq=rel_err(ch.grad.cpu().numpy(), q0d + q0r))
+    print("PME random 300-atom triclinic system vs fp64 oracle:", errs)
+    # north-star tolerance 1e-5 (the OpenMM goldens above carry five digits and keep the reference's own rtol 1e-4, TestPme.py:38-63)
+    assert errs["energy"] < 1e-5 and errs["forces"] < 1e-5 and errs["dq"] < 1e-5
 
 
 def _random_pme_system(n, seed, with_exclusions):
@@ -257,7 +259,10 @@ def test_pme_direct_fused_matches_list_path(n, with_exclusions):
     assert abs(e1 - e0) <= 2e-6 * abs(e0) + 1e-5
     assert rel_err(g1, g0) < 5e-6 and rel_err(q1, q0) < 5e-6
     e_ref, f_ref, q_ref = NP.pme_direct(pos, q, box, 1.2, 3.2, 138.935, excl if excl.size else None)
-    assert abs(e1 - e_ref) <= 2e-5 * abs(e_ref) + 1e-3 and rel_err(g1, f_ref) < 1e-4 and rel_err(q1, q_ref) < 1e-4
+    errs = dict(energy_abs=abs(e1 - e_ref), energy_ref=e_ref, forces=rel_err(g1, f_ref), dq=rel_err(q1, q_ref))
+    print("fused direct space vs fp64 oracle, n=%d exclusions=%s:" % (n, with_exclusions), errs)
+    # the energy is returned as ONE fp32 number (kJ/mol, up to 1e4 here): 2e-3 is its resolution
+    assert errs["energy_abs"] <= 1e-5 * abs(e_ref) + 2e-3 and errs["forces"] < 1e-5 and errs["dq"] < 1e-5, errs
 
 
 @pytest.mark.parametrize("world", [2, 3, 8])

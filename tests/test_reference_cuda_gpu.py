@@ -63,3 +63,43 @@ def test_aev_forward_backward_match_the_reference_cuda_kernels(name, n, periodic
         refcuda_vs_cpu = {"angular": rel_err(a0.cpu().numpy(), a_o), "grad": rel_err(d0.cpu().numpy(), g_o)}
         print(name, "ours vs CPU reference:", ours_vs_cpu, " reference CUDA vs CPU reference:", refcuda_vs_cpu)
         assert ours_vs_cpu["radial"] < 1e-5 and ours_vs_cpu["angular"] < 1e-5 and ours_vs_cpu["grad"] < 1e-5, ours_vs_cpu
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_cfconv_matches_the_reference_cuda_kernels(periodic):
+    """SchNet CFConv (neighbour build, forward, backprop) against the reference's own CUDA classes CudaCFConvNeighbors / CudaCFConv
+    (unmodified source, sm_100a) on 6 000 atoms, width 128, 50 Gaussians, cutoff 5 A: same pair count, outputs and gradients to 1e-5.
+    (The reference's N x N pair table in managed memory limits it to about 16 000 atoms.)"""
+    l = O.ref_cuda_lib()
+    if l is None or not hasattr(l, "refcuda_cfconv_create"):
+        pytest.skip("oracle/_ref/libnnpops_ref_cuda.so was not built with the CFConv classes (needs /root/reference at build time)")
+    from nnpops_b200.CFConv import CFConv
+    from nnpops_b200.CFConvNeighbors import CFConvNeighbors
+    n, W, Gn, cutoff, sigma = 6000, 128, 50, 5.0, 0.2
+    rng = np.random.default_rng(17)
+    pos, L = lattice(n, 2.154, 0.3, 4004)
+    box = cubic_box(L) if periodic else None
+    w1 = rng.normal(0, 0.1, (W, Gn)).astype(np.float32); b1 = rng.normal(0, 0.1, W).astype(np.float32)
+    w2 = rng.normal(0, 0.1, (W, W)).astype(np.float32); b2 = rng.normal(0, 0.1, W).astype(np.float32)
+    x = torch.tensor(rng.standard_normal((n, W)).astype(np.float32), device="cuda")
+    go = torch.tensor(rng.standard_normal((n, W)).astype(np.float32), device="cuda")
+    p = torch.tensor(pos, device="cuda")
+    b = torch.tensor(box, device="cuda") if box is not None else None
+    ref = O.RefCudaCFConv(n, W, Gn, cutoff, periodic, sigma, "ssp", w1, b1, w2, b2)
+    ref.build(p, b)
+    y0 = ref.compute(p, b, x)
+    ig0, pg0 = ref.backprop(p, b, x, go)
+    torch.cuda.synchronize()
+    pairs0 = ref.num_pairs()
+    nb = CFConvNeighbors(cutoff)
+    conv = CFConv(sigma, "ssp", torch.tensor(w1.reshape(Gn, W)), torch.tensor(b1), torch.tensor(w2), torch.tensor(b2))
+    pr = p.clone().requires_grad_(True); xr = x.clone().requires_grad_(True)
+    nb.build(pr, b)
+    y1 = conv(nb, pr, xr)
+    y1.backward(go)
+    errs = {"out": rel_err(y1.detach().cpu().numpy(), y0.cpu().numpy()), "input_grad": rel_err(xr.grad.cpu().numpy(), ig0.cpu().numpy()),
+            "pos_grad": rel_err(pr.grad.cpu().numpy(), pg0.cpu().numpy())}
+    print("CFConv vs reference CUDA kernels (periodic=%s): pairs %d / %d" % (periodic, nb.num_pairs(), pairs0), errs)
+    ref.close()
+    assert nb.num_pairs() == pairs0
+    assert errs["out"] < 1e-5 and errs["input_grad"] < 1e-5 and errs["pos_grad"] < 1e-5, errs
