@@ -54,7 +54,15 @@ pairs_kernel(int n, const T* __restrict__ pos, const T* __restrict__ boxPtr, con
     // Survivors of the pre-test are queued (ballot compaction, scan order preserved) and the exact test runs on full batches of
     // 32, so the divisions of the reference arithmetic execute on dense lanes instead of the ~15 % that survive each sweep.
     __shared__ int queueAll[kWPB][64];
+    // fp32 only: the survivor's minimum-image displacement (candidate - centre) travels with it.  The sorted coordinates ARE the fp32
+    // positions, and the multiply-by-reciprocal image of the pre-test equals the reference's division image step for step unless a
+    // quotient sits on a rounding tie (|component| of half a box edge): only those survivors are re-derived with the division form.
+    // A negated displacement is the displacement of the swapped pair exactly (rint is odd), so orientation row > col costs a sign.
+    constexpr bool kCarry = sizeof(T) == 4;
+    __shared__ float4 deltaAll[kCarry ? kWPB : 1][64];
     int* queue = queueAll[w];
+    float4* qdelta = deltaAll[kCarry ? w : 0];
+    const float tieX = 0.499f * (float)bx.b[0], tieY = 0.499f * (float)bx.b[4], tieZ = 0.499f * (float)bx.b[8];
     int queued = 0;
     auto drain = [&](int count) {   // exact test + output for queue[0 .. count)
         bool ok = false;
@@ -62,9 +70,22 @@ pairs_kernel(int n, const T* __restrict__ pos, const T* __restrict__ boxPtr, con
         T dx = 0, dy = 0, dz = 0, d = 0;
         if (lane < count) {
             const int oq = sortedOrig[queue[lane]];
-            const T pq[3] = {pos[3 * (size_t)oq], pos[3 * (size_t)oq + 1], pos[3 * (size_t)oq + 2]};
-            if (oq > op) { row = oq; col = op; d = pair_delta<T>(bx, pq, pp, dx, dy, dz); }
-            else         { row = op; col = oq; d = pair_delta<T>(bx, pp, pq, dx, dy, dz); }
+            bool exact = !kCarry;
+            if (kCarry) {
+                const float4 e = qdelta[lane];
+                exact = bx.periodic && (fabsf(e.x) >= tieX || fabsf(e.y) >= tieY || fabsf(e.z) >= tieZ);
+                if (!exact) {
+                    const float sgn = oq > op ? 1.0f : -1.0f;   // delta = pos[row] - pos[col], row the larger original index
+                    dx = (T)(sgn * e.x); dy = (T)(sgn * e.y); dz = (T)(sgn * e.z);
+                    d = (T)__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(e.x, e.x), __fmul_rn(e.y, e.y)), __fmul_rn(e.z, e.z)));
+                    row = max(op, oq); col = min(op, oq);
+                }
+            }
+            if (exact) {
+                const T pq[3] = {pos[3 * (size_t)oq], pos[3 * (size_t)oq + 1], pos[3 * (size_t)oq + 2]};
+                if (oq > op) { row = oq; col = op; d = pair_delta<T>(bx, pq, pp, dx, dy, dz); }
+                else         { row = op; col = oq; d = pair_delta<T>(bx, pp, pq, dx, dy, dz); }
+            }
             ok = d <= cutoff;
         }
         const unsigned m = __ballot_sync(kFull, ok);
@@ -89,21 +110,28 @@ pairs_kernel(int n, const T* __restrict__ pos, const T* __restrict__ boxPtr, con
         for (int q0 = max(b, p + 1); q0 < e; q0 += 32) {
             const int q = q0 + lane;
             bool keep = false;
+            float ax = 0.0f, ay = 0.0f, az = 0.0f;
             if (q < e) {
                 const float4 cq = sorted[q];
-                float ax = cq.x - cp.x, ay = cq.y - cp.y, az = cq.z - cp.z;
+                ax = __fsub_rn(cq.x, cp.x); ay = __fsub_rn(cq.y, cp.y); az = __fsub_rn(cq.z, cp.z);
                 keep = (image ? min_image_mul(g, ax, ay, az) : ax * ax + ay * ay + az * az) <= pre2;
             }
             const unsigned m = __ballot_sync(kFull, keep);
-            if (keep) queue[queued + __popc(m & ((1u << lane) - 1u))] = q;
+            if (keep) {
+                const int slot = queued + __popc(m & ((1u << lane) - 1u));
+                queue[slot] = q;
+                if (kCarry) qdelta[slot] = make_float4(ax, ay, az, 0.0f);
+            }
             queued += __popc(m);
             __syncwarp();
             if (queued >= 32) {
                 drain(32);
                 __syncwarp();
                 const int carry = (lane < queued - 32) ? queue[32 + lane] : 0;
+                float4 carryD = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (kCarry && lane < queued - 32) carryD = qdelta[32 + lane];
                 __syncwarp();
-                if (lane < queued - 32) queue[lane] = carry;
+                if (lane < queued - 32) { queue[lane] = carry; if (kCarry) qdelta[lane] = carryD; }
                 queued -= 32;
                 __syncwarp();
             }
