@@ -335,6 +335,71 @@ class PME:
         e = pme_direct_fused(positions, charges, box_vectors, self.exclusions, cutoff, self.alpha, self.coulomb, shard)
         return _AllReduceSum.apply(e, group)
 
+    def energy_and_derivatives(self, positions: Tensor, charges: Tensor, cutoff: float, box_vectors: Tensor, group=None, world=None):
+        """Total PME energy (direct + reciprocal + self term) with dE/dpositions and dE/dcharges in ONE call, without autograd: the
+        form an MD engine needs (forces = -dE/dx), and the form that shards.  Returns (energy [] , dE/dx [atoms, 3], dE/dq [atoms]).
+
+        When torch.distributed is initialised (ranks of `group`, default group if None; pass world=1 for a rank-local evaluation) ONE
+        box is evaluated by all N ranks; positions, charges and the results are replicated:
+          direct space      rank r evaluates the centres of slab r of the cell-sorted atoms (fused kernel, no halo, no atomics);
+          reciprocal space  rank r spreads ITS block of atoms, the charge grids are summed by one all-reduce (8.4 MB at 128^3), every
+                            rank solves the same grid (FFT, convolution, energy) and interpolates the derivatives of its own atoms;
+          assembly          ONE all-reduce of the packed [atoms, 4] derivatives (direct + reciprocal + self term together) and one
+                            of the two energy scalars.
+        Same arithmetic as compute_direct + compute_reciprocal + backward (tests/test_neighbors_pme_gpu.py)."""
+        import torch.distributed as dist
+        self._validate(positions, charges, box_vectors)
+        if cutoff <= 0:
+            raise ValueError('cutoff must be positive')
+        pos, q, box = _f32(positions, "positions"), _f32(charges, "charges"), _f32(box_vectors, "box_vectors")
+        dev = pos.device
+        self.exclusions = self.exclusions.to(dev)
+        for i in range(3):
+            self.moduli[i] = self.moduli[i].to(device=dev, dtype=torch.float32).contiguous()
+        if world is None:
+            world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+        n = q.shape[0]
+        ex = self.exclusions.contiguous()
+        gx, gy, gz = self.gridx, self.gridy, self.gridz
+        packed = torch.empty((n, 4), dtype=torch.float32, device=dev)        # dE/dx | dE/dq
+        pos_deriv = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        charge_deriv = torch.empty((n,), dtype=torch.float32, device=dev)
+        energies = torch.empty((2,), dtype=torch.float32, device=dev)       # direct (this rank's slab), reciprocal (replicated)
+        stream = current_stream(dev)
+        with torch.cuda.device(dev):
+            check(lib.nnpops_pme_direct_fused(ptr(pos), ptr(q), ptr(box), ptr(ex) if ex.numel() else None, n, ex.shape[1] if ex.dim() == 2 else 0,
+                                              float(cutoff), float(self.alpha), float(self.coulomb), rank, world, ptr(energies[0:1]),
+                                              ptr(pos_deriv), ptr(charge_deriv), stream))
+            packed[:, :3] = pos_deriv
+            packed[:, 3] = charge_deriv
+            lo, hi = shard_range(n, rank, world)
+            grid = torch.empty((gx, gy, gz), dtype=torch.float32, device=dev)
+            pl, ql = pos[lo:hi].contiguous(), q[lo:hi].contiguous()
+            check(lib.nnpops_pme_spread(ptr(pl), ptr(ql), ptr(box), hi - lo, gx, gy, gz, self.order, float(self.coulomb), ptr(grid), stream))
+            if world > 1:
+                dist.all_reduce(grid, group=group)
+            recip = torch.empty((gx, gy, gz // 2 + 1, 2), dtype=torch.float32, device=dev)
+            check(lib.nnpops_pme_solve(ptr(grid), ptr(box), gx, gy, gz, float(self.alpha), ptr(self.moduli[0]), ptr(self.moduli[1]),
+                                       ptr(self.moduli[2]), ptr(energies[1:2]), ptr(recip), stream))
+            if hi > lo:
+                pd = torch.empty((hi - lo, 3), dtype=torch.float32, device=dev)
+                cd = torch.empty((hi - lo,), dtype=torch.float32, device=dev)
+                check(lib.nnpops_pme_reciprocal_backward(ptr(pl), ptr(ql), ptr(box), hi - lo, gx, gy, gz, self.order, float(self.coulomb),
+                                                         ptr(recip), ptr(pd), ptr(cd), stream))
+                self_scale = self.coulomb * self.alpha / math.sqrt(math.pi)
+                packed[lo:hi, :3] += pd
+                packed[lo:hi, 3] += cd - (2.0 * self_scale) * ql           # d/dq of the self term -k alpha / sqrt(pi) sum q^2
+        if world > 1:
+            dist.all_reduce(packed, group=group)
+            e_direct = energies[0:1].clone()
+            dist.all_reduce(e_direct, group=group)
+        else:
+            e_direct = energies[0:1]
+        self_energy = -torch.sum(q * q) * (self.coulomb * self.alpha / math.sqrt(math.pi))
+        energy = (e_direct[0] + energies[1] + self_energy)
+        return energy, packed[:, :3], packed[:, 3]
+
     def compute_reciprocal(self, positions: Tensor, charges: Tensor, box_vectors: Tensor):
         """Reciprocal-space energy including the self term (pme.py:167-196)."""
         self._validate(positions, charges, box_vectors)
