@@ -244,6 +244,7 @@ void pme_direct_fused(const float* positions, const float* charges, const float*
         return ws.release();
     });
     FusedWorkspace& ws = *hold;
+    NNP_CUDA_CHECK(cudaMemsetAsync(ws.acc, 0, sizeof(double), stream));   // (also reset by the publish kernel; a failed call must not leak into the next)
     // the charge rides in the tag word of the sorted coordinates: one 16-byte load brings a candidate's position and charge
     ws.cells.build<float>(positions, box, reinterpret_cast<const int*>(charges), cutoff * 1.0001f + 1e-30f, stream);
     const int per = (n + shardCount - 1) / shardCount;
