@@ -740,7 +740,6 @@ MlpChain::MlpChain(int ensemble, int numSpecies, const SpeciesDesc* sp, const __
     P.numUnits = tiles * (ensemble / mpu);
     impl_->grid = std::max(1, std::min(P.numUnits, sms));
     if (const char* e = std::getenv("NNPOPS_CHAIN_GRID")) impl_->grid = std::max(1, std::min(impl_->grid, std::atoi(e)));   // development: several units per CTA on small systems
-    if (const char* e = std::getenv("NNPOPS_CHAIN_GRID")) impl_->grid = std::max(1, std::min(impl_->grid, std::atoi(e)));   // development: force several tiles per CTA
     NNP_CUDA_CHECK(cudaMalloc(&impl_->stash, sizeof(float) * (size_t)impl_->grid * kStashCols * kRows));
     P.stash = impl_->stash;
 }
