@@ -49,6 +49,35 @@ def test_compute_fails_loudly_without_gpu():
         getNeighborPairs(torch.zeros((3, 3)), 1.0)
 
 
+def test_pme_host_logic_without_gpu():
+    """PME: argument validation as the reference raises it (pme.py:76-92, 151-160), shard ranges of the multi-GPU forms, and no CPU
+    path for any of the compute methods -- including the fused direct-space form and the one-call form."""
+    from nnpops_b200.pme import PME
+    from nnpops_b200.pme.pme import shard_range
+    excl = torch.full((4, 1), -1, dtype=torch.int32)
+    for bad in ((0, 8, 8, 5, 1.0, 1.0), (8, 8, 8, 0, 1.0, 1.0), (8, 8, 8, 5, 0.0, 1.0), (8, 8, 8, 5, 1.0, -1.0)):
+        with pytest.raises(ValueError):
+            PME(*bad, excl)
+    pme = PME(8, 8, 8, 5, 1.0, 1.0, excl)
+    pos, q, box = torch.zeros((4, 3)), torch.zeros(4), torch.eye(3)
+    with pytest.raises(ValueError):
+        pme.compute_direct(pos, q, -1.0, box)
+    with pytest.raises(ValueError):
+        pme.compute_direct(torch.zeros((5, 3)), q, 1.0, box)          # lengths differ from the exclusion table
+    with pytest.raises(ValueError):
+        pme.energy_and_derivatives(pos, q, 0.0, box, world=1)
+    for call in (lambda: pme.compute_direct(pos, q, 1.0, box), lambda: pme.compute_direct(pos, q, 1.0, box, max_num_pairs=10),
+                 lambda: pme.compute_direct_sharded(pos, q, 1.0, box, emulate=(0, 2)), lambda: pme.compute_reciprocal(pos, q, box),
+                 lambda: pme.energy_and_derivatives(pos, q, 1.0, box, world=1)):
+        with pytest.raises(RuntimeError):
+            call()                                                       # CPU tensors: "runs on CUDA devices only"
+    # contiguous blocks that cover [0, n) exactly once, whatever the remainder
+    for n, world in ((10, 3), (200000, 8), (5, 8), (0, 2)):
+        blocks = [shard_range(n, r, world) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n and all(b[1] == c[0] for b, c in zip(blocks, blocks[1:]))
+        assert all(lo <= hi for lo, hi in blocks)
+
+
 def test_function_tables_follow_reference_order():
     from nnpops_b200.SymmetryFunctions import function_tables
     r, a = function_tables([1, 2], [10, 20, 30], [5, 6], [7], [0.1, 0.2], [0.5, 1.5, 2.5])
