@@ -303,10 +303,9 @@ __device__ __forceinline__ void epi_chunk(const ChainParams& P, const EpiCtx& x,
                     const float2 fh = unpack_h2(hh[i]), fl = unpack_h2(ll[i]);
                     act2 = ffma2(pk2(fl.x, fl.y), loInv2, pk2(fh.x, fh.y));
                 }
-                float a0, a1, g0, g1;
-                unpk2(act2, a0, a1);
-                unpk2(ffma2(act2, invAlpha2, one2), g0, g1);   // celu'(z) from celu(z): 1 for a > 0, a / alpha + 1 otherwise
-                v = fmul2(v, pk2(a0 > 0.0f ? 1.0f : g0, a1 > 0.0f ? 1.0f : g1));
+                float g0, g1;
+                unpk2(ffma2(act2, invAlpha2, one2), g0, g1);   // celu'(z) from celu(z): 1 for a > 0, a / alpha + 1 (<= 1) otherwise
+                v = fmul2(v, pk2(fminf(g0, 1.0f), fminf(g1, 1.0f)));
             }
             split_pack2(v, ph[i], pl[i]);
         }
