@@ -2,7 +2,7 @@
 //
 // One persistent CTA per SM walks over tiles of 128 atoms of one species and, per tile, over the M ensemble members; for each
 // (tile, member) it runs the six GEMMs of the network back to back ("chain"):
-//     F1  A1  = celu(X   W0^T + b0)        N = d1, K = d0     A operand: X    (shared memory, TMA, loaded once per tile)
+//     F1  A1  = celu(X   W0^T + b0)        N = d1, K = d0     A operand: X    (shared memory, TMA, re-fetched per chain)
 //     F2  A2  = celu(A1  W1^T + b1)        N = d2, K = d1     A operand: A1   (tensor memory)
 //     F3  a3  = celu(A2  W2^T + b2)        N = d3, K = d2     A operand: A2   (shared memory); E += a3 . w3; dZ2 = w3/M celu'
 //     G3  dZ1 = (dZ2 W2) * celu'(A2)       N = d2, K = d3     A operand: dZ2  (tensor memory); overwrites A2 in place
@@ -15,15 +15,19 @@
 // previous chain, which buys 64 KB for the weight ring) + a ring of eight 16 KB weight blocks.  The only activation that does not
 // fit, A1 (needed again for celu' in G2), goes through a per-CTA fp32 scratch that stays in L2 (128 KB per CTA, rewritten every chain).
 //
-// Work split inside the CTA (576 threads):
-//   warp 0        TMA producer: X once per chain, then one 16 KB weight block [64 hi rows + 64 lo rows][64 k] per (n-chunk, k-chunk)
-//   warp 1        TMEM allocator + MMA issuer (one elected lane): per k16 step  [D1 | D2] (+)= Ahi . [Bhi; Blo]  (N = 128) and
-//                 D2 += Alo . Bhi (N = 64); tcgen05.commit frees ring slots and publishes accumulator stages
-//   warps 2-9     epilogue group 0 (accumulator stage 0),  warps 10-17 epilogue group 1 (stage 1): 64-column chunks alternate
+// Work split inside the CTA (20 warps, 640 threads):
+//   warps 0, 3    TMA producers (one elected lane each): warp 0 feeds MMA issuer 0 and loads X once per chain, warp 3 feeds issuer 1;
+//                 one 16 KB weight block [64 hi rows + 64 lo rows][64 k] per (n-chunk, k-chunk) into the issuer's half of the ring
+//   warps 1, 2    MMA issuers (one elected lane each; warp 1 also allocates the tensor memory): issuer g owns accumulator stage g and
+//                 the chunks of a chain with parity g; per k16 step  [D1 | D2] (+)= Ahi . [Bhi; Blo]  (N = 128) and D2 += Alo . Bhi
+//                 (N = 64); tcgen05.commit frees ring slots and publishes accumulator stages
+//   warps 4-11    epilogue group 0 (accumulator stage 0),  warps 12-19 epilogue group 1 (stage 1): 64-column chunks alternate
 //                 between the groups, so the epilogue of chunk c overlaps the MMAs of chunk c + 1.  A thread owns one row (TMEM
-//                 lane) and 32 columns; it writes the next layer's A operand straight into tensor memory (tcgen05.st) or into
-//                 the swizzled K-major shared-memory tiles, then arrives on the per-64-column "operand ready" barrier the MMA
-//                 warp waits on before it issues the first k-chunk that needs those columns.
+//                 lane) and 32 columns; it pulls its accumulators into registers, hands the stage back, and writes the next layer's
+//                 A operand straight into tensor memory (tcgen05.st) or into the swizzled K-major shared-memory tiles, then arrives
+//                 on the per-64-column "operand ready" barrier the MMA warps wait on before they issue the first k-chunk that needs
+//                 those columns.
+// What bounds it (measured with the CHAIN_EXP_* / CHAIN_TRACE switches below): DESIGN.md section 4, profiles/r08_summary.md.
 #include "mlp_chain.cuh"
 #include <algorithm>
 #include <cstdlib>
